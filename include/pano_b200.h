@@ -1,0 +1,244 @@
+/*
+ * pano_b200.h — C ABI of the B200-native SIFT + match + blend engine.
+ *
+ * This is the drop-in boundary for the hot path of ppwwyyxx/OpenPano
+ * (SURVEY.md §8b).  The reference has no FFI layer: its seams are four C++
+ * classes.  Each entry point below names the reference interface it replaces
+ * (paths relative to the reference's src/).  Plain pointers and sizes only; no
+ * torch / C++ types.  All functions return 0 on success or a negative
+ * pano_status; they never call exit().
+ *
+ * Threading: a pano_ctx owns one CUDA stream and scratch pools; calls on one
+ * ctx must be serialized by the caller (create one ctx per host thread, or use
+ * the *_batch entry points, which is how the reference's
+ * `#pragma omp parallel for` over images maps to this engine).
+ */
+#ifndef PANO_B200_H
+#define PANO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pano_status {
+  PANO_OK = 0,
+  PANO_ERR_CUDA = -1,        /* a CUDA runtime call failed: pano_last_error() */
+  PANO_ERR_INVALID = -2,     /* bad argument (null pointer, non-positive size…) */
+  PANO_ERR_CAPACITY = -3,    /* a fixed-capacity device list overflowed */
+  PANO_ERR_NO_DEVICE = -4,   /* no CUDA device / extension built without one */
+  PANO_ERR_NO_FEATURE = -5   /* reference: error_exit("Cannot find feature…"), stitcherbase.cc:20 */
+} pano_status;
+
+/* Snapshot of the reference's mutable config globals (lib/config.hh:24-68,
+ * defaults from config.cfg:2-69) that the hot path reads. */
+typedef struct pano_params {
+  int   sift_working_size;         /* SIFT_WORKING_SIZE 800 */
+  int   num_octave;                /* NUM_OCTAVE 4 */
+  int   num_scale;                 /* NUM_SCALE 7 */
+  float scale_factor;              /* SCALE_FACTOR 1.4142135623 */
+  float gauss_sigma;               /* GAUSS_SIGMA 1.4142135623 */
+  int   gauss_window_factor;       /* GAUSS_WINDOW_FACTOR 6 */
+  float judge_extrema_diff_thres;  /* JUDGE_EXTREMA_DIFF_THRES 2e-3 */
+  float contrast_thres;            /* CONTRAST_THRES 4e-2 */
+  float pre_color_thres;           /* PRE_COLOR_THRES 5e-2 */
+  float edge_ratio;                /* EDGE_RATIO 6 */
+  int   calc_offset_depth;         /* CALC_OFFSET_DEPTH 4 */
+  float offset_thres;              /* OFFSET_THRES 0.5 */
+  float ori_radius;                /* ORI_RADIUS 4.5 */
+  int   ori_hist_smooth_count;     /* ORI_HIST_SMOOTH_COUNT 2 */
+  int   desc_hist_scale_factor;    /* DESC_HIST_SCALE_FACTOR 3 */
+  int   desc_int_factor;           /* DESC_INT_FACTOR 512 */
+  float match_reject_next_ratio;   /* MATCH_REJECT_NEXT_RATIO 0.8 */
+  float focal_length;              /* FOCAL_LENGTH 37 */
+  int   ordered_input;             /* ORDERED_INPUT 0 */
+  int   lazy_read;                 /* LAZY_READ 1 */
+  int   multiband;                 /* MULTIBAND 0 */
+  int   max_output_size;           /* MAX_OUTPUT_SIZE 8000 */
+} pano_params;
+
+/* Fills *p with the defaults of the reference's config.cfg. */
+void pano_params_default(pano_params* p);
+
+/* One scale-space point: POD image of the reference's SSPoint
+ * (feature/feature.hh:33-39). */
+typedef struct pano_sspoint {
+  int    x, y;            /* Coor coor: integer coordinate in the octave */
+  double real_x, real_y;  /* Vec2D real_coor in [0,1) */
+  int    pyr_id, scale_id;
+  float  dir;
+  float  scale_factor;
+} pano_sspoint;
+
+/* ---------------------------------------------------------------- context */
+
+typedef struct pano_ctx pano_ctx;
+
+/* Creates an engine context on CUDA device `device`.  `cuda_stream` may be
+ * NULL (the ctx creates its own non-blocking stream) or a cudaStream_t cast to
+ * void* (e.g. torch.cuda.current_stream().cuda_stream) on which every kernel
+ * of this ctx is then launched. */
+int  pano_create(pano_ctx** out, int device, void* cuda_stream);
+void pano_destroy(pano_ctx* ctx);
+/* Message of the last failure on this ctx ("" if none).  ctx may be NULL for
+ * the last pano_create failure. */
+const char* pano_last_error(const pano_ctx* ctx);
+/* Blocks until all work queued on the ctx stream has finished. */
+int  pano_sync(pano_ctx* ctx);
+/* The stream (cudaStream_t as void*) the ctx launches on. */
+void* pano_stream(pano_ctx* ctx);
+
+/* Per-kernel timing (CUDA events on the ctx stream).  When enabled, every
+ * kernel launch is bracketed by events; pano_kernel_times reports, per kernel
+ * name, the launch count and summed duration since the last reset.  Used by
+ * bench.py for the roofline line; adds host overhead, so it is off by default
+ * and never on inside a timed end-to-end region. */
+int  pano_profile_enable(pano_ctx* ctx, int on);
+int  pano_profile_reset(pano_ctx* ctx);
+/* names: buffer of cap entries × 64 bytes; returns number of distinct kernels. */
+int  pano_profile_read(pano_ctx* ctx, int cap, char* names, int* launches, double* total_ms);
+/* Total number of kernels this ctx has launched since creation. */
+long long pano_launch_count(const pano_ctx* ctx);
+
+/* ---------------------------------------------------------------- features
+ * Replaces FeatureDetector::detect_feature / SIFTDetector::do_detect_feature
+ * (feature/feature.hh:42-57, feature/feature.cc:20-47): working-size resize,
+ * ScaleSpace (feature/dog.cc:96-114), DOGSpace (dog.cc:131-143),
+ * ExtremaDetector::get_extrema (extrema.cc:36-61), OrientationAssign::work
+ * (orientation.cc:22-32), SIFT::get_descriptor (sift.cc:77-85).
+ *
+ * A pano_featureset holds, per image, the descriptors (n×128 f32, row-major)
+ * and coordinates (n×2 f64, image-centred input pixels: (c-0.5)*w) ON THE
+ * DEVICE so that matching runs without a host round trip; download copies
+ * them out in the reference's Descriptor layout (feature.hh:18-30). */
+typedef struct pano_featureset pano_featureset;
+
+/* Host images: n pointers to H×W×3 f32 RGB in [0,1] (Mat32f layout,
+ * lib/mat.h:7-60).  Includes H2D of the images (pinned staging + async). */
+int pano_sift_detect_batch(pano_ctx* ctx, int n, const float* const* rgb_hwc,
+                           const int* w, const int* h, const pano_params* p,
+                           pano_featureset** out);
+/* Same, images already resident in device memory (device pointers). */
+int pano_sift_detect_batch_dev(pano_ctx* ctx, int n, const float* const* d_rgb_hwc,
+                               const int* w, const int* h, const pano_params* p,
+                               pano_featureset** out);
+/* Single-image convenience = detect_feature(const Mat32f&). */
+int pano_sift_detect(pano_ctx* ctx, const float* rgb_hwc, int w, int h,
+                     const pano_params* p, pano_featureset** out);
+
+/* Builds a featureset from host descriptors = PairWiseMatcher ctor
+ * (feature/matcher.hh:40-46; matcher.cc:73-88 without the kd-forest).
+ * desc[i]: n_kp[i]×128 f32; coor[i] may be NULL. */
+int pano_featureset_upload(pano_ctx* ctx, int n_images, const int* n_kp,
+                           const float* const* desc, const double* const* coor_xy,
+                           pano_featureset** out);
+int pano_featureset_num_images(const pano_featureset* fs);
+/* Number of descriptors of image i (synchronizes on first use). */
+int pano_featureset_count(pano_featureset* fs, int image);
+/* Copies image i's results to host: coor_xy (2·n f64) and desc (128·n f32);
+ * either may be NULL. */
+int pano_featureset_download(pano_featureset* fs, int image, double* coor_xy, float* desc);
+void pano_featureset_free(pano_featureset* fs);
+
+/* --------------------------------------------------------------- matching
+ * Replaces PairWiseMatcher::match(i, j) (feature/matcher.cc:90-135) with the
+ * exact rule of FeatureMatcher::match (matcher.cc:15-71), which is the parity
+ * contract: loop over the smaller set, exact fp32 top-2 with
+ * lowest-index ties, two-way ratio test with REJECT_RATIO_SQR = ratio².
+ * Output pairs are (idx in image i, idx in image j), ascending index of the
+ * smaller set. */
+typedef struct pano_matches {
+  int  n_pairs;      /* number of image pairs */
+  int* count;        /* [n_pairs] matches of pair k */
+  int* offset;       /* [n_pairs+1] prefix into idx */
+  int* idx;          /* [2*offset[n_pairs]] (first, second) */
+} pano_matches;
+
+int  pano_match_pairs(pano_ctx* ctx, pano_featureset* fs, int n_pairs,
+                      const int* image_ij /* 2*n_pairs */, const pano_params* p,
+                      pano_matches* out);
+void pano_matches_free(pano_matches* m);
+/* Device-resident variant for the timed-in-HBM bench leg: results stay on the
+ * device, only the total match count is returned. */
+int  pano_match_pairs_dev(pano_ctx* ctx, pano_featureset* fs, int n_pairs,
+                          const int* image_ij, const pano_params* p, int* total_matches);
+/* FeatureMatcher(f1,f2).match() on two host descriptor arrays
+ * (matcher.hh:27-38); pairs_out holds 2*min(n,m) ints. */
+int  pano_match_bruteforce(pano_ctx* ctx, const float* desc_a, int n,
+                           const float* desc_b, int m, const pano_params* p,
+                           int* pairs_out, int* n_pairs_out);
+
+/* ---------------------------------------------------------- cylinder warp
+ * Replaces CylinderWarper(h_factor).warp(Mat32f&, vector<Vec2D>&)
+ * (stitch/warp.hh:41-66, warp.cc:25-75). */
+/* Output shape and offset for an input of w×h (CylinderProject::project(shape),
+ * warp.cc:46-67); host-only arithmetic. */
+int pano_cyl_warp_shape(int w, int h, double h_factor, const pano_params* p,
+                        int* out_w, int* out_h, double* offset_x, double* offset_y);
+/* out_hwc: out_h×out_w×3 f32 (Color::NO = -1 where unmapped); kpts_xy (n_kpts
+ * pairs, image-centred) are rewritten in place; may be NULL/0. */
+int pano_cyl_warp(pano_ctx* ctx, const float* rgb_hwc, int w, int h, double h_factor,
+                  const pano_params* p, float* out_hwc, int out_w, int out_h,
+                  double* kpts_xy, int n_kpts);
+
+/* ----------------------------------------------------------------- blend
+ * Replaces BlenderBase::add_image + run (stitch/blender.hh:14-59) for
+ * LinearBlender (blender.cc:24-96) and MultiBandBlender (multiband.cc:19-151).
+ * The reference passes an opaque std::function per image; it is always the
+ * closed form built at stitcher_image.cc:142-151 (and cylstitcher.cc:176-178),
+ * so the ABI takes that form's parameters. */
+typedef enum pano_projection { PANO_PROJ_FLAT = 0, PANO_PROJ_CYLINDRICAL = 1, PANO_PROJ_SPHERICAL = 2 } pano_projection;
+
+typedef struct pano_blend_image {
+  const float* rgb_hwc;   /* H×W×3 f32, host (pano_blend) or device (pano_blend_dev) */
+  int w, h;
+  int x0, y0, x1, y1;     /* Range{upper_left, bottom_right}, both inclusive (blender.hh:19-26) */
+  double homo_inv[9];     /* ImageComponent::homo_inv (stitcher_image.hh:40-43) */
+} pano_blend_image;
+
+typedef struct pano_blend_geom {
+  int    projection;             /* pano_projection */
+  double res_x, res_y;           /* `resolution` (stitcher_image.cc:119) */
+  double proj_min_x, proj_min_y; /* proj_range.min */
+} pano_blend_geom;
+
+/* target_size = componentwise max of bottom_right (blender.cc:21, multiband.cc:16). */
+int pano_blend_target_size(int n, const pano_blend_image* imgs, int* out_w, int* out_h);
+/* bands == 0: LinearBlender::run; bands > 0: MultiBandBlender{bands}::run.
+ * out_hwc: out_h×out_w×3 f32, -1 where no image contributes. */
+int pano_blend(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g,
+               int bands, const pano_params* p, float* out_hwc, int out_w, int out_h);
+/* Device-resident variant: imgs[k].rgb_hwc and d_out_hwc are device pointers. */
+int pano_blend_dev(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g,
+                   int bands, const pano_params* p, float* d_out_hwc, int out_w, int out_h);
+
+/* ------------------------------------------------------- device utilities */
+int pano_dev_alloc(pano_ctx* ctx, size_t bytes, void** d_ptr);
+int pano_dev_free(pano_ctx* ctx, void* d_ptr);
+int pano_dev_upload(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int pano_dev_download(pano_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+
+/* ------------------------------------------------------ stage inspection
+ * Parity-test hooks: run the SIFT chain on ONE host image and keep every
+ * intermediate on the device so tests can compare each stage with the oracle
+ * (SURVEY.md §4 "per-stage oracle tests"). */
+typedef struct pano_sift_trace pano_sift_trace;
+int  pano_sift_trace_run(pano_ctx* ctx, const float* rgb_hwc, int w, int h,
+                         const pano_params* p, pano_sift_trace** out);
+int  pano_sift_trace_working_size(const pano_sift_trace* t, int* w0, int* h0);
+int  pano_sift_trace_octave_size(const pano_sift_trace* t, int octave, int* w, int* h);
+/* kind: 0 working RGB (3ch, octave ignored), 1 gaussian level i∈[0,nscale),
+ * 2 |DoG| level i∈[0,nscale-1), 3 mag level i∈[1,nscale), 4 ort level. */
+int  pano_sift_trace_plane(pano_sift_trace* t, int kind, int octave, int level, float* out);
+/* stage: 0 raw extrema (x,y,pyr_id,scale_id valid), 1 refined+edge-tested
+ * keypoints, 2 oriented keypoints.  Returns count; copies min(count,cap). */
+int  pano_sift_trace_points(pano_sift_trace* t, int stage, int cap, pano_sspoint* out);
+int  pano_sift_trace_descriptors(pano_sift_trace* t, int cap, double* coor_xy, float* desc);
+void pano_sift_trace_free(pano_sift_trace* t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANO_B200_H */

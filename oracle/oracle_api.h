@@ -1,0 +1,55 @@
+/*
+ * oracle_api.h — the checker API.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Two libraries implement this same set of functions:
+ *   - oracle/liboracle.so        prefix orc_  : plain-C restatement of the
+ *                                               reference algorithm (the orc_ C files)
+ *   - oracle/_ref/libopenpano_ref.so prefix ref_: the reference's own
+ *                                               translation units compiled from
+ *                                               /root/reference/src (refshim/)
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load them.  The product (openpano_b200) never does.
+ */
+#ifndef ORACLE_API_H
+#define ORACLE_API_H
+#include "../include/pano_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORACLE_DECLARE(P)                                                              \
+  typedef struct P##_sift P##_sift;                                                    \
+  /* runs the whole SIFT chain on one image, keeps every intermediate */              \
+  P##_sift* P##_sift_run(const float* rgb_hwc, int w, int h, const pano_params* p);    \
+  void P##_sift_working_size(const P##_sift* s, int* w0, int* h0);                     \
+  int  P##_sift_octave_size(const P##_sift* s, int octave, int* w, int* h);            \
+  /* kind: 0 working RGB, 1 gaussian level, 2 |DoG| level, 3 mag, 4 ort */             \
+  int  P##_sift_plane(const P##_sift* s, int kind, int octave, int level, float* out); \
+  /* stage: 0 raw extrema, 1 refined keypoints, 2 oriented keypoints */                \
+  int  P##_sift_points(const P##_sift* s, int stage, int cap, pano_sspoint* out);      \
+  int  P##_sift_descriptors(const P##_sift* s, int cap, double* coor_xy, float* desc); \
+  void P##_sift_free(P##_sift* s);                                                     \
+  /* detect_feature only (no intermediates kept): returns count, -1 if > cap */        \
+  int  P##_sift_detect(const float* rgb_hwc, int w, int h, const pano_params* p,       \
+                       int cap, double* coor_xy, float* desc);                         \
+  /* FeatureMatcher::match */                                                          \
+  int  P##_match(const float* a, int n, const float* b, int m, const pano_params* p,   \
+                 int* pairs_out, int* n_pairs_out);                                    \
+  int  P##_cyl_warp_shape(int w, int h, double h_factor, const pano_params* p,         \
+                          int* out_w, int* out_h, double* off_x, double* off_y);       \
+  int  P##_cyl_warp(const float* rgb_hwc, int w, int h, double h_factor,               \
+                    const pano_params* p, float* out_hwc, int out_w, int out_h,        \
+                    double* kpts_xy, int n_kpts);                                      \
+  int  P##_blend(int n, const pano_blend_image* imgs, const pano_blend_geom* g,        \
+                 int bands, const pano_params* p, float* out_hwc, int out_w, int out_h);\
+  /* number of host threads the library will use (1 for the scalar port) */            \
+  int  P##_num_threads(void);
+
+ORACLE_DECLARE(orc)
+ORACLE_DECLARE(ref)
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,231 @@
+"""ctypes front-end to the CHECKERS (oracle/liboracle.so = orc_*, the plain-C
+restatement; oracle/_ref/libopenpano_ref.so = ref_*, the reference's own
+translation units).  Test infrastructure: never imported by the product."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+from openpano_b200._abi import (PanoBlendGeom, PanoBlendImage, PanoParams, PanoSSPoint,
+                                default_params)
+
+ROOT = Path(__file__).resolve().parent.parent
+ORACLE_SO = ROOT / "oracle" / "liboracle.so"
+REF_SO = ROOT / "oracle" / "_ref" / "libopenpano_ref.so"
+REF_FAST_SO = ROOT / "oracle" / "_ref" / "libopenpano_ref_fast.so"
+
+SSPOINT_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("real_x", "<f8"), ("real_y", "<f8"),
+                          ("pyr_id", "<i4"), ("scale_id", "<i4"), ("dir", "<f4"),
+                          ("scale_factor", "<f4")], align=True)
+assert SSPOINT_DTYPE.itemsize == C.sizeof(PanoSSPoint)
+
+_fp = C.POINTER(C.c_float)
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def _f(a):
+    return a.ctypes.data_as(_fp)
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return a.ctypes.data_as(_ip)
+
+
+def make_blend_images(imgs, items):
+    """imgs: list of HxWx3 float32 arrays; items: (x0,y0,x1,y1,homo_inv[9])."""
+    arr = (PanoBlendImage * len(imgs))()
+    for k, (im, it) in enumerate(zip(imgs, items)):
+        assert im.dtype == np.float32 and im.flags.c_contiguous
+        arr[k].rgb_hwc = im.ctypes.data
+        arr[k].h, arr[k].w = im.shape[0], im.shape[1]
+        arr[k].x0, arr[k].y0, arr[k].x1, arr[k].y1 = it[0], it[1], it[2], it[3]
+        for q in range(9):
+            arr[k].homo_inv[q] = it[4][q]
+    return arr
+
+
+def make_geom(g):
+    return PanoBlendGeom(projection=g["projection"], res_x=g["res_x"], res_y=g["res_y"],
+                         proj_min_x=g["proj_min_x"], proj_min_y=g["proj_min_y"])
+
+
+def blend_target_size(items):
+    return max(it[2] for it in items), max(it[3] for it in items)
+
+
+class SiftTrace:
+    """One image's full SIFT chain with every intermediate (both checkers and
+    the CUDA engine expose the same getters)."""
+
+    def __init__(self, lib, prefix, handle):
+        self._lib, self._p, self._h = lib, prefix, handle
+
+    def _fn(self, name):
+        return getattr(self._lib, f"{self._p}_sift_{name}")
+
+    def working_size(self):
+        w, h = C.c_int(), C.c_int()
+        self._fn("working_size")(self._h, C.byref(w), C.byref(h))
+        return w.value, h.value
+
+    def octave_size(self, o):
+        w, h = C.c_int(), C.c_int()
+        rc = self._fn("octave_size")(self._h, o, C.byref(w), C.byref(h))
+        assert rc == 0
+        return w.value, h.value
+
+    def plane(self, kind, octave=0, level=0):
+        if kind == 0:
+            w, h = self.working_size()
+            out = np.empty((h, w, 3), np.float32)
+        else:
+            w, h = self.octave_size(octave)
+            out = np.empty((h, w), np.float32)
+        rc = self._fn("plane")(self._h, kind, octave, level, _f(out))
+        assert rc == 0, (kind, octave, level)
+        return out
+
+    def points(self, stage):
+        n = self._fn("points")(self._h, stage, 0, None)
+        out = np.zeros(n, SSPOINT_DTYPE)
+        if n:
+            self._fn("points")(self._h, stage, n, out.ctypes.data_as(C.POINTER(PanoSSPoint)))
+        return out
+
+    def descriptors(self):
+        n = self._fn("descriptors")(self._h, 0, None, None)
+        coor = np.zeros((n, 2), np.float64)
+        desc = np.zeros((n, 128), np.float32)
+        if n:
+            self._fn("descriptors")(self._h, n, _d(coor), _f(desc))
+        return coor, desc
+
+    def close(self):
+        if self._h:
+            self._fn("free")(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Checker:
+    def __init__(self, path: Path, prefix: str):
+        if not Path(path).exists():
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(str(path), mode=os.RTLD_LOCAL)
+        self.p = prefix
+        L, P = self.lib, prefix
+        fn = lambda n: getattr(L, f"{P}_{n}")
+        fn("sift_run").restype = C.c_void_p
+        fn("sift_run").argtypes = [_fp, C.c_int, C.c_int, C.POINTER(PanoParams)]
+        fn("sift_working_size").argtypes = [C.c_void_p, _ip, _ip]
+        fn("sift_working_size").restype = None
+        fn("sift_octave_size").argtypes = [C.c_void_p, C.c_int, _ip, _ip]
+        fn("sift_plane").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _fp]
+        fn("sift_points").argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(PanoSSPoint)]
+        fn("sift_descriptors").argtypes = [C.c_void_p, C.c_int, _dp, _fp]
+        fn("sift_free").argtypes = [C.c_void_p]
+        fn("sift_free").restype = None
+        fn("sift_detect").argtypes = [_fp, C.c_int, C.c_int, C.POINTER(PanoParams), C.c_int, _dp, _fp]
+        fn("match").argtypes = [_fp, C.c_int, _fp, C.c_int, C.POINTER(PanoParams), _ip, _ip]
+        fn("cyl_warp_shape").argtypes = [C.c_int, C.c_int, C.c_double, C.POINTER(PanoParams),
+                                         _ip, _ip, _dp, _dp]
+        fn("cyl_warp").argtypes = [_fp, C.c_int, C.c_int, C.c_double, C.POINTER(PanoParams), _fp,
+                                   C.c_int, C.c_int, _dp, C.c_int]
+        fn("blend").argtypes = [C.c_int, C.POINTER(PanoBlendImage), C.POINTER(PanoBlendGeom),
+                                C.c_int, C.POINTER(PanoParams), _fp, C.c_int, C.c_int]
+        fn("num_threads").restype = C.c_int
+        self._fn = fn
+
+    def num_threads(self):
+        return self._fn("num_threads")()
+
+    def sift_trace(self, img, params=None) -> SiftTrace:
+        params = params or default_params()
+        img = np.ascontiguousarray(img, np.float32)
+        h = self._fn("sift_run")(_f(img), img.shape[1], img.shape[0], C.byref(params))
+        assert h
+        return SiftTrace(self.lib, self.p, h)
+
+    def sift_detect(self, img, params=None, cap=65536):
+        params = params or default_params()
+        img = np.ascontiguousarray(img, np.float32)
+        coor = np.zeros((cap, 2), np.float64)
+        desc = np.zeros((cap, 128), np.float32)
+        n = self._fn("sift_detect")(_f(img), img.shape[1], img.shape[0], C.byref(params), cap,
+                                    _d(coor), _f(desc))
+        assert n >= 0
+        return coor[:n].copy(), desc[:n].copy()
+
+    def match(self, a, b, params=None):
+        params = params or default_params()
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.ascontiguousarray(b, np.float32)
+        pairs = np.zeros((max(1, min(len(a), len(b))), 2), np.int32)
+        n = C.c_int()
+        rc = self._fn("match")(_f(a), len(a), _f(b), len(b), C.byref(params), _i(pairs), C.byref(n))
+        assert rc == 0
+        return pairs[:n.value].copy()
+
+    def cyl_warp_shape(self, w, h, h_factor=1.0, params=None):
+        params = params or default_params()
+        ow, oh, ox, oy = C.c_int(), C.c_int(), C.c_double(), C.c_double()
+        rc = self._fn("cyl_warp_shape")(w, h, h_factor, C.byref(params), C.byref(ow), C.byref(oh),
+                                        C.byref(ox), C.byref(oy))
+        assert rc == 0
+        return ow.value, oh.value, ox.value, oy.value
+
+    def cyl_warp(self, img, kpts=None, h_factor=1.0, params=None):
+        params = params or default_params()
+        img = np.ascontiguousarray(img, np.float32)
+        ow, oh, _, _ = self.cyl_warp_shape(img.shape[1], img.shape[0], h_factor, params)
+        out = np.empty((oh, ow, 3), np.float32)
+        k = np.ascontiguousarray(kpts if kpts is not None else np.zeros((0, 2)), np.float64).copy()
+        rc = self._fn("cyl_warp")(_f(img), img.shape[1], img.shape[0], h_factor, C.byref(params),
+                                  _f(out), ow, oh, _d(k), len(k))
+        assert rc == 0
+        return out, k
+
+    def blend(self, imgs, items, geom, bands=0, params=None):
+        params = params or default_params()
+        arr = make_blend_images(imgs, items)
+        g = make_geom(geom)
+        ow, oh = blend_target_size(items)
+        out = np.empty((oh, ow, 3), np.float32)
+        rc = self._fn("blend")(len(imgs), arr, C.byref(g), bands, C.byref(params), _f(out), ow, oh)
+        assert rc == 0
+        return out
+
+
+_cache = {}
+
+
+def get_checker(kind: str) -> Checker:
+    """kind: 'orc' (C restatement), 'ref' (reference TUs, parity flags) or
+    'ref_fast' (reference TUs, perf flags + OpenMP)."""
+    if kind not in _cache:
+        if kind == "orc":
+            _cache[kind] = Checker(ORACLE_SO, "orc")
+        elif kind == "ref":
+            _cache[kind] = Checker(REF_SO, "ref")
+        elif kind == "ref_fast":
+            _cache[kind] = Checker(REF_FAST_SO, "ref")
+        else:
+            raise KeyError(kind)
+    return _cache[kind]
+
+
+def have(kind: str) -> bool:
+    return {"orc": ORACLE_SO, "ref": REF_SO, "ref_fast": REF_FAST_SO}[kind].exists()
