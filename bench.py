@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py — SIFT + match + blend throughput of the hot path (BASELINE.json).
+
+One "step" = one pass of the hot path over one synthetic stack of
+BASELINE.json configs[1]: 13 ordered images 1500x1112 -> SIFT on every image,
+the 13 adjacent-pair matches of linear_pairwise_match, and the LinearBlender
+composite (reference defaults MULTIBAND 0, LAZY_READ 1; ORDERED_INPUT 1) with
+generator-known homographies (RANSAC / bundle adjustment are host geometry
+outside the hot path).  Metric: megapixels of INPUT per second.
+
+  python bench.py [--gpus N --steps K --warmup W]       our engine (one rank per GPU)
+  python bench.py --impl reference [...]                 the reference's CPU path
+
+Prints ONE JSON line on rank 0 (contract in the task statement):
+  value    : K steps with inputs resident in HBM (device-timed, max over ranks)
+  e2e      : the same through the public API with pinned HOST inputs/outputs,
+             H2D of the images and D2H of the mosaic + matches inside the timing
+  roofline : dominant kernel, algorithmic bytes / event-timed duration
+  cpu_baseline : oracle/_ref (the reference's own TUs, OpenMP) on this host
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = "ordered_13x1500x1112"
+METRIC = "Mpixels/sec SIFT+match+blend"
+UNIT = "Mpx/s"
+
+
+# ----------------------------------------------------------------------------- workload
+def make_workload(rank: int, bands: int):
+    from openpano_b200 import synth
+    from openpano_b200._abi import default_params
+    from openpano_b200.stitcher import ordered_pairs
+
+    cfg = dict(synth.CONFIGS[WORKLOAD])
+    cfg["seed"] = cfg["seed"] + 1000 * rank          # each rank stitches its own stack (weak scaling)
+    imgs, origins = synth.make_stack(**cfg)
+    items, geom = synth.translation_blend_setup(origins, cfg["w"], cfg["h"])
+    params = default_params(ordered_input=1, multiband=bands)
+    pairs = ordered_pairs(len(imgs))
+    mpx = sum(im.shape[0] * im.shape[1] for im in imgs) / 1e6
+    return imgs, pairs, items, geom, params, mpx
+
+
+def octave_dims(w, h, params):
+    """Working/octave sizes with the reference's float arithmetic (feature.cc:33-34, dog.cc:105-107)."""
+    f32 = np.float32
+    ratio = f32(params.sift_working_size) * f32(2.0) / f32(w + h)
+    h0, w0 = int(f32(h) * ratio), int(f32(w) * ratio)
+    dims = [(w0, h0)]
+    for o in range(1, params.num_octave):
+        factor = f32(float(params.scale_factor) ** (-o))
+        dims.append((int(np.ceil(f32(w0) * factor)), int(np.ceil(f32(h0) * factor))))
+    return dims
+
+
+def algorithmic_bytes(imgs, items, params, counts):
+    """Per-launch algorithmic traffic of each kernel (compulsory-traffic model of
+    SURVEY.md §8d: every array one stage produces and another consumes is written
+    once and read once; fused temporaries are free).  Returns name -> (bytes, unit)."""
+    n = len(imgs)
+    ns = params.num_scale
+    p_in = sum(im.shape[0] * im.shape[1] for im in imgs)
+    p0 = 0
+    sp = 0
+    for im in imgs:
+        d = octave_dims(im.shape[1], im.shape[0], params)
+        p0 += d[0][0] * d[0][1]
+        sp += sum(a * b for a, b in d)
+    n_desc = sum(counts)
+    roi = sum((it[2] - it[0] + 1) * (it[3] - it[1] + 1) for it in items)
+    tw, th = max(it[2] for it in items), max(it[3] for it in items)
+    L = max(params.multiband, 0)
+    return {
+        "k_working_resize": min(p_in, 4 * p0) * 12 + p0 * 12,
+        "k_octave_grey": p0 * 12 + sp * 4,
+        "k_blur_dog": sp * 4 * (1 + 2 * (ns - 1)),            # read grey, write 6 levels + 6 |DoG|
+        "k_extrema_scan": sp * 4 * (ns - 1),                  # reads the |DoG| levels once
+        "k_rank_sort": n_desc * 8,
+        "k_refine": n_desc * (27 * 4 + 40),
+        "k_orientation": n_desc * (196 * 4 + 8),
+        "k_expand_scan": n_desc * 16,
+        "k_descriptor": n_desc * (16 + 512),                  # §8d: outputs n_kp*(16+512)
+        "k_match_top2": None,                                 # tensor-bound, see flops below
+        "k_match_decide": n_desc * 32,
+        "k_linear_blend": roi * 12 + tw * th * 12,
+        "k_mb_first_level": roi * (12 + 16),
+        "k_mb_weight_argmax": roi * 8,
+        "k_mb_blur_col": roi * 32, "k_mb_blur_row": roi * 32,
+        "k_mb_accumulate": roi * (16 + 12) + tw * th * 12,
+        "k_fill": tw * th * 12,
+    }
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.15)
+
+    def start(self):
+        self._thr = threading.Thread(target=self._run, daemon=True)
+        self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def cpu_pass(checker, imgs, pairs, items, geom, bands, params):
+    t = time.perf_counter()
+    nf, nm, out, secs = checker.hotpath(imgs, pairs, items, geom, bands, params, use_flann=True)
+    return time.perf_counter() - t, secs, int(nf.sum()), int(nm.sum())
+
+
+def load_cpu_checker():
+    from tests.checker import get_checker, have
+    if have("ref_fast"):
+        return get_checker("ref_fast"), "reference"
+    if have("ref"):
+        return get_checker("ref"), "reference"
+    return get_checker("orc"), "port"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    imgs, pairs, items, geom, params, mpx = make_workload(0, args.bands)
+    chk, kind = load_cpu_checker()
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)                                 # the reference prints timers on stdout
+    try:
+        for _ in range(args.warmup):
+            cpu_pass(chk, imgs, pairs, items, geom, args.bands, params)
+        t0 = time.perf_counter()
+        stage = np.zeros(3)
+        for _ in range(args.steps):
+            _, secs, nfeat, nmatch = cpu_pass(chk, imgs, pairs, items, geom, args.bands, params)
+            stage += secs
+        dt = (time.perf_counter() - t0) / args.steps
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+    val = mpx / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "bands": args.bands, "matcher": "PairWiseMatcher (FLANN kd-forest)",
+                   "geometry": "generator-known homographies", "features": nfeat, "matches": nmatch},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": chk.num_threads(), "kind": kind,
+                         "sample": f"full {WORKLOAD} workload per step (host cores: {os.cpu_count()})",
+                         "stage_ms": {"features": stage[0] / args.steps * 1e3, "match": stage[1] / args.steps * 1e3,
+                                      "blend": stage[2] / args.steps * 1e3}},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bands", type=int, default=0, help="0 = LinearBlender (reference default), k = MultiBandBlender{k}")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if args.steps > 5:
+            args.steps = 5          # bounded: each step is the full CPU workload (seconds)
+        args.warmup = min(args.warmup, 1)
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from openpano_b200.capi import Engine
+    from openpano_b200.stitcher import Stitcher
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    imgs, pairs, items, geom, params, mpx = make_workload(rank, args.bands)
+    shapes = [im.shape[:2] for im in imgs]
+    out_w, out_h = max(it[2] for it in items), max(it[3] for it in items)
+
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        eng = Engine(local_rank, stream.cuda_stream)
+        st = Stitcher(eng, params)
+        # pinned host inputs / output for the e2e leg
+        host = [torch.from_numpy(im).pin_memory() for im in imgs]
+        host_out = torch.empty((out_h, out_w, 3), dtype=torch.float32).pin_memory()
+        host_ptrs = [t.data_ptr() for t in host]
+        h2d_bytes = sum(t.numel() * 4 for t in host)
+
+        # ---- correctness guard + counts (untimed)
+        st.upload(host_ptrs, shapes, (out_w, out_h))
+        eng.sync()
+        fs, matches = st.run_device(pairs, items, geom, args.bands, want_matches=True)
+        counts = [fs.count(i) for i in range(len(imgs))]
+        n_matches = sum(len(m) for m in matches)
+        fs.free()
+        if min(counts) == 0 or n_matches == 0:
+            raise SystemExit("bench.py: degenerate workload (no features / matches)")
+
+        # ---- value: inputs resident in HBM
+        def step_device():
+            f, _ = st.run_device(pairs, items, geom, args.bands, want_matches=False)
+            f.free()
+
+        for _ in range(args.warmup):
+            step_device()
+        torch.cuda.synchronize()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        l0 = eng.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_device()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        launches = eng.launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        ms = e0.elapsed_time(e1)
+        t_dev = torch.tensor([ms], device="cuda")
+        if world > 1:
+            dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        ms_total = float(t_dev.item())
+        ms_per_step = ms_total / args.steps
+        value = world * mpx / (ms_per_step / 1e3)
+
+        # ---- e2e: pinned host images in, host mosaic + matches out, every step
+        d2h_bytes = out_w * out_h * 3 * 4
+        for _ in range(2):
+            st.build(host_ptrs, shapes, pairs, items, geom, host_out.data_ptr(), args.bands)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        nm_e2e = 0
+        for _ in range(args.steps):
+            m = st.build(host_ptrs, shapes, pairs, items, geom, host_out.data_ptr(), args.bands)
+            nm_e2e = sum(len(x) for x in m)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        t_e2e = torch.tensor([e2e_s], device="cuda")
+        if world > 1:
+            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+        e2e_per_step = float(t_e2e.item()) / args.steps
+        e2e_value = world * mpx / e2e_per_step
+        d2h_bytes += nm_e2e * 8 + len(imgs) * 8
+        assert float(host_out[out_h // 2, out_w // 2, 0]) >= 0.0      # the mosaic really came back
+
+        # ---- roofline of the dominant kernel (event-timed per launch, separate untimed pass)
+        roof = None
+        kernels = {}
+        if rank == 0:
+            st.upload(host_ptrs, shapes, (out_w, out_h))
+            eng.sync()
+            eng.profile(True)
+            eng.profile_reset()
+            PROF_STEPS = 5
+            for _ in range(PROF_STEPS):
+                step_device()
+            prof = eng.profile_read()
+            eng.profile(False)
+            ab = algorithmic_bytes(imgs, items, params, counts)
+            peaks = {}
+            pk = ROOT / "MEASURED_PEAKS.json"
+            peak_src = "fallback"
+            if pk.exists():
+                peaks = json.loads(pk.read_text())
+                peak_src = "measured"
+            hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+            tf_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
+            tot = sum(v[1] for v in prof.values())
+            for name, (cnt, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
+                avg = tms / max(cnt, 1)
+                ent = {"launches_per_step": cnt / PROF_STEPS, "avg_ms": avg, "share": tms / tot if tot else 0}
+                if name == "k_match_top2":
+                    flops = sum(2.0 * counts[i] * counts[j] * 128 for i, j in pairs)   # §8d: 2·N·M·128 per pair
+                    ent.update(bound="tensor", achieved=flops / (avg * 1e-3) / 1e12, peak=tf_peak, unit="TFLOP/s")
+                elif ab.get(name):
+                    ent.update(bound="hbm", achieved=ab[name] / (avg * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s")
+                if "achieved" in ent:
+                    ent["frac"] = ent["achieved"] / ent["peak"]
+                kernels[name] = ent
+            top = max(kernels, key=lambda k: kernels[k]["share"])
+            t = kernels[top]
+            roof = {"kernel": top, "bound": t.get("bound"), "achieved": t.get("achieved"), "peak": t.get("peak"),
+                    "unit": t.get("unit"), "frac": t.get("frac"), "traffic": None, "peak_source": peak_src,
+                    "share_of_step": t["share"], "avg_ms": t["avg_ms"]}
+
+        # ---- CPU baseline (rank 0, N == 1): the reference's own TUs on this host
+        cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            try:
+                chk, kind = load_cpu_checker()
+                devnull = os.open(os.devnull, os.O_WRONLY)
+                saved = os.dup(1)
+                os.dup2(devnull, 1)
+                try:
+                    dt, secs, _, _ = cpu_pass(chk, imgs, pairs, items, geom, args.bands, params)
+                finally:
+                    os.dup2(saved, 1)
+                    os.close(devnull)
+                cpu = {"value": mpx / dt, "unit": UNIT, "cores": chk.num_threads(), "kind": kind,
+                       "sample": f"one full pass of {WORKLOAD} ({dt:.2f} s; host has {os.cpu_count()} cores)",
+                       "stage_ms": {"features": secs[0] * 1e3, "match": secs[1] * 1e3, "blend": secs[2] * 1e3}}
+            except Exception as ex:  # the checker is optional equipment on the box
+                cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+
+        st.close()
+        eng.close()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "images": len(imgs), "image_wh": [imgs[0].shape[1], imgs[0].shape[0]],
+                       "pairs": len(pairs), "bands": args.bands, "blend": "linear" if args.bands == 0 else "multiband",
+                       "geometry": "generator-known homographies (flat projection)", "parallelism": f"dp{world}",
+                       "l2_policy": "inputs_exceed_l2 (260 MB of images + 0.9 GB pyramid arena per step)",
+                       "features": int(sum(counts)), "matches": int(n_matches)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_per_step * 1e3},
+            "gpu_launches": int(launches * world),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -22,6 +22,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 
 typedef enum pano_status {
   PANO_OK = 0,
@@ -219,6 +222,10 @@ int pano_dev_alloc(pano_ctx* ctx, size_t bytes, void** d_ptr);
 int pano_dev_free(pano_ctx* ctx, void* d_ptr);
 int pano_dev_upload(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 int pano_dev_download(pano_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+/* Stream-ordered variants: the host buffer must be pinned and stay valid until
+ * pano_sync(); used by the end-to-end path to overlap copies with kernels. */
+int pano_dev_upload_async(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int pano_dev_download_async(pano_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 
 /* ------------------------------------------------------ stage inspection
  * Parity-test hooks: run the SIFT chain on ONE host image and keep every
@@ -238,6 +245,9 @@ int  pano_sift_trace_points(pano_sift_trace* t, int stage, int cap, pano_sspoint
 int  pano_sift_trace_descriptors(pano_sift_trace* t, int cap, double* coor_xy, float* desc);
 void pano_sift_trace_free(pano_sift_trace* t);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,467 @@
+// engine.cu — context, memory, profiling and the extern "C" entry points of
+// libpano_b200.so that are not pure kernel drivers (see include/pano_b200.h).
+#include "sift.cuh"
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+
+static thread_local std::string g_create_err;
+
+int ctx_fail(pano_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_err = buf;
+  return code;
+}
+
+int ctx_cuda(pano_ctx* ctx, cudaError_t e, const char* what) {
+  return ctx_fail(ctx, PANO_ERR_CUDA, "CUDA error %s (%s) at %s", cudaGetErrorName(e), cudaGetErrorString(e), what);
+}
+
+int ctx_alloc(pano_ctx* ctx, void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+  if (e != cudaSuccess) return ctx_cuda(ctx, e, "cudaMallocAsync");
+  return PANO_OK;
+}
+
+void ctx_free(pano_ctx* ctx, void* p) {
+  if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+static void* grow_pinned(void** buf, size_t* cap, size_t bytes) {
+  if (bytes <= *cap) return *buf;
+  if (*buf) cudaFreeHost(*buf);
+  *buf = nullptr; *cap = 0;
+  size_t want = std::max(bytes, (size_t)1 << 20);
+  if (cudaMallocHost(buf, want) != cudaSuccess) { *buf = nullptr; return nullptr; }
+  *cap = want;
+  return *buf;
+}
+
+void* ctx_pinned(pano_ctx* ctx, size_t bytes) { return grow_pinned(&ctx->pinned, &ctx->pinned_bytes, bytes); }
+void* ctx_pinned2(pano_ctx* ctx, size_t bytes) {
+  // metadata staging is reused across calls: wait for earlier async copies
+  if (ctx->pinned2) cudaStreamSynchronize(ctx->stream);
+  return grow_pinned(&ctx->pinned2, &ctx->pinned2_bytes, bytes);
+}
+
+static cudaEvent_t get_event(pano_ctx* ctx) {
+  if (!ctx->event_pool.empty()) { cudaEvent_t e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return e; }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void ctx_prof_begin(pano_ctx* ctx, const char* name) {
+  ProfEvent pe;
+  pe.name = name;
+  pe.start = get_event(ctx);
+  pe.stop = get_event(ctx);
+  cudaEventRecord(pe.start, ctx->stream);
+  ctx->prof_pending.push_back(pe);
+}
+
+void ctx_prof_end(pano_ctx* ctx) { cudaEventRecord(ctx->prof_pending.back().stop, ctx->stream); }
+
+static void prof_drain(pano_ctx* ctx) {
+  if (ctx->prof_pending.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& pe : ctx->prof_pending) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, pe.start, pe.stop);
+    auto& acc = ctx->prof_acc[pe.name];
+    acc.first += 1; acc.second += ms;
+    ctx->event_pool.push_back(pe.start);
+    ctx->event_pool.push_back(pe.stop);
+  }
+  ctx->prof_pending.clear();
+}
+
+extern "C" {
+
+void pano_params_default(pano_params* p) {
+  // src/config.cfg:2-69
+  p->sift_working_size = 800; p->num_octave = 4; p->num_scale = 7;
+  p->scale_factor = 1.4142135623f; p->gauss_sigma = 1.4142135623f; p->gauss_window_factor = 6;
+  p->judge_extrema_diff_thres = 2e-3f; p->contrast_thres = 4e-2f; p->pre_color_thres = 5e-2f;
+  p->edge_ratio = 6.f; p->calc_offset_depth = 4; p->offset_thres = 0.5f; p->ori_radius = 4.5f;
+  p->ori_hist_smooth_count = 2; p->desc_hist_scale_factor = 3; p->desc_int_factor = 512;
+  p->match_reject_next_ratio = 0.8f; p->focal_length = 37.f; p->ordered_input = 0; p->lazy_read = 1;
+  p->multiband = 0; p->max_output_size = 8000;
+}
+
+int pano_create(pano_ctx** out, int device, void* cuda_stream) {
+  if (!out) return PANO_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return ctx_fail(nullptr, PANO_ERR_NO_DEVICE, "no CUDA device (%s): this engine has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) return ctx_fail(nullptr, PANO_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return ctx_cuda(nullptr, e, "cudaSetDevice");
+  pano_ctx* ctx = new pano_ctx;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { delete ctx; return ctx_cuda(nullptr, e, "cudaGetDeviceProperties"); }
+  if (prop.major < 10) {
+    int rc = ctx_fail(nullptr, PANO_ERR_NO_DEVICE, "device %d is sm_%d%d; libpano_b200 is built for sm_100a only", device, prop.major, prop.minor);
+    delete ctx; return rc;
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cuda_stream) { ctx->stream = (cudaStream_t)cuda_stream; ctx->owns_stream = false; }
+  else {
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return ctx_cuda(nullptr, e, "cudaStreamCreate"); }
+    ctx->owns_stream = true;
+  }
+  // keep freed blocks cached in the default pool: the same sizes recur every batch
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  *out = ctx;
+  return PANO_OK;
+}
+
+void pano_destroy(pano_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  prof_drain(ctx);
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->pinned2) cudaFreeHost(ctx->pinned2);
+  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* pano_last_error(const pano_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int pano_sync(pano_ctx* ctx) {
+  PANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PANO_OK;
+}
+
+void* pano_stream(pano_ctx* ctx) { return (void*)ctx->stream; }
+
+int pano_profile_enable(pano_ctx* ctx, int on) {
+  prof_drain(ctx);
+  ctx->profiling = on != 0;
+  return PANO_OK;
+}
+
+int pano_profile_reset(pano_ctx* ctx) {
+  prof_drain(ctx);
+  ctx->prof_acc.clear();
+  return PANO_OK;
+}
+
+int pano_profile_read(pano_ctx* ctx, int cap, char* names, int* launches, double* total_ms) {
+  prof_drain(ctx);
+  int i = 0;
+  for (auto& kv : ctx->prof_acc) {
+    if (i < cap) {
+      strncpy(names + (size_t)i * 64, kv.first.c_str(), 63);
+      names[(size_t)i * 64 + 63] = 0;
+      launches[i] = kv.second.first;
+      total_ms[i] = kv.second.second;
+    }
+    ++i;
+  }
+  return i;
+}
+
+long long pano_launch_count(const pano_ctx* ctx) { return ctx->launches; }
+
+// ---------------------------------------------------------------- device utilities
+int pano_dev_alloc(pano_ctx* ctx, size_t bytes, void** d_ptr) { return ctx_alloc(ctx, d_ptr, bytes); }
+int pano_dev_free(pano_ctx* ctx, void* d_ptr) { ctx_free(ctx, d_ptr); return PANO_OK; }
+int pano_dev_upload(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  PANO_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PANO_OK;
+}
+int pano_dev_download(pano_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  PANO_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PANO_OK;
+}
+
+int pano_dev_upload_async(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  PANO_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return PANO_OK;
+}
+int pano_dev_download_async(pano_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  PANO_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return PANO_OK;
+}
+
+// ---------------------------------------------------------------- features
+
+static void featureset_release(pano_featureset* fs) {
+  if (!fs) return;
+  pano_ctx* ctx = fs->ctx;
+  if (ctx) {
+    ctx_free(ctx, fs->d_desc); ctx_free(ctx, fs->d_coor); ctx_free(ctx, fs->d_count);
+  }
+  if (fs->counts_ready) cudaEventDestroy(fs->counts_ready);
+  if (fs->h_count_pinned) cudaFreeHost(fs->h_count_pinned);
+  delete fs;
+}
+
+int pano_sift_detect_batch_dev(pano_ctx* ctx, int n, const float* const* d_rgb, const int* w, const int* h,
+                               const pano_params* p, pano_featureset** out) {
+  if (!ctx || !out) return PANO_ERR_INVALID;
+  *out = nullptr;
+  pano_featureset* fs = new pano_featureset;
+  fs->ctx = ctx;
+  int rc = sift_run_batch(ctx, n, d_rgb, w, h, p, fs, nullptr);
+  if (rc != 0) { featureset_release(fs); return rc; }
+  *out = fs;
+  return PANO_OK;
+}
+
+static bool host_is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// Uploads host images through one pinned staging buffer (async H2D on the ctx
+// stream), then runs the device path.
+static int upload_images(pano_ctx* ctx, int n, const float* const* rgb, const int* w, const int* h,
+                         std::vector<float*>& d_imgs, float** d_block) {
+  size_t total = 0;
+  std::vector<size_t> offs(n);
+  for (int i = 0; i < n; ++i) {
+    if (!rgb[i] || w[i] <= 0 || h[i] <= 0) return ctx_fail(ctx, PANO_ERR_INVALID, "image %d: null or empty", i);
+    offs[i] = total;
+    total += align_up((size_t)w[i] * h[i] * 3, 64);
+  }
+  int rc = ctx_alloc(ctx, (void**)d_block, total * sizeof(float));
+  if (rc) return rc;
+  // the staging buffer may still feed an earlier async copy
+  PANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  bool all_pinned = true;
+  for (int i = 0; i < n; ++i) all_pinned = all_pinned && host_is_pinned(rgb[i]);
+  float* st = all_pinned ? (float*)ctx_pinned(ctx, 64) : (float*)ctx_pinned(ctx, total * sizeof(float));
+  if (!st) return ctx_fail(ctx, PANO_ERR_CUDA, "pinned staging allocation of %zu bytes failed", total * sizeof(float));
+  d_imgs.resize(n);
+  for (int i = 0; i < n; ++i) {
+    size_t bytes = (size_t)w[i] * h[i] * 3 * sizeof(float);
+    const float* src = rgb[i];
+    if (!host_is_pinned(rgb[i])) {  // pageable caller memory: stage it
+      memcpy(st + offs[i], rgb[i], bytes);
+      src = st + offs[i];
+    }
+    PANO_CUDA(ctx, cudaMemcpyAsync(*d_block + offs[i], src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    d_imgs[i] = *d_block + offs[i];
+  }
+  return PANO_OK;
+}
+
+int pano_sift_detect_batch(pano_ctx* ctx, int n, const float* const* rgb, const int* w, const int* h,
+                           const pano_params* p, pano_featureset** out) {
+  if (!ctx || !out || n <= 0 || !rgb || !w || !h || !p) return PANO_ERR_INVALID;
+  *out = nullptr;
+  std::vector<float*> d_imgs;
+  float* d_block = nullptr;
+  int rc = upload_images(ctx, n, rgb, w, h, d_imgs, &d_block);
+  if (rc) { ctx_free(ctx, d_block); return rc; }
+  rc = pano_sift_detect_batch_dev(ctx, n, d_imgs.data(), w, h, p, out);
+  ctx_free(ctx, d_block);
+  return rc;
+}
+
+int pano_sift_detect(pano_ctx* ctx, const float* rgb, int w, int h, const pano_params* p, pano_featureset** out) {
+  return pano_sift_detect_batch(ctx, 1, &rgb, &w, &h, p, out);
+}
+
+int pano_featureset_upload(pano_ctx* ctx, int n_images, const int* n_kp, const float* const* desc,
+                           const double* const* coor, pano_featureset** out) {
+  if (!ctx || !out || n_images <= 0 || !n_kp || !desc) return PANO_ERR_INVALID;
+  *out = nullptr;
+  pano_featureset* fs = new pano_featureset;
+  fs->ctx = ctx; fs->n_images = n_images;
+  fs->base.resize(n_images); fs->h_count.resize(n_images);
+  long long total = 0;
+  for (int i = 0; i < n_images; ++i) {
+    if (n_kp[i] < 0) { featureset_release(fs); return ctx_fail(ctx, PANO_ERR_INVALID, "negative count"); }
+    fs->base[i] = total; fs->h_count[i] = n_kp[i];
+    total += (n_kp[i] + 31) / 32 * 32;  // keep rows 32-aligned per image
+  }
+  int rc = ctx_alloc(ctx, (void**)&fs->d_desc, (size_t)std::max(total, 1LL) * 128 * sizeof(float));
+  if (!rc) rc = ctx_alloc(ctx, (void**)&fs->d_count, n_images * sizeof(int));
+  if (!rc && coor) rc = ctx_alloc(ctx, (void**)&fs->d_coor, (size_t)std::max(total, 1LL) * 2 * sizeof(double));
+  if (rc) { featureset_release(fs); return rc; }
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < n_images && e == cudaSuccess; ++i) {
+    if (!n_kp[i]) continue;
+    e = cudaMemcpyAsync(fs->d_desc + fs->base[i] * 128, desc[i], (size_t)n_kp[i] * 128 * sizeof(float),
+                        cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && coor && coor[i])
+      e = cudaMemcpyAsync(fs->d_coor + fs->base[i] * 2, coor[i], (size_t)n_kp[i] * 2 * sizeof(double),
+                          cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(fs->d_count, fs->h_count.data(), n_images * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // sources are pageable host memory
+  if (e != cudaSuccess) { rc = ctx_cuda(ctx, e, "featureset upload"); featureset_release(fs); return rc; }
+  fs->counts_on_host = true;
+  *out = fs;
+  return PANO_OK;
+}
+
+int pano_featureset_num_images(const pano_featureset* fs) { return fs ? fs->n_images : PANO_ERR_INVALID; }
+
+int pano_featureset_count(pano_featureset* fs, int image) {
+  if (!fs || image < 0 || image >= fs->n_images) return PANO_ERR_INVALID;
+  int rc = featureset_sync_counts(fs);
+  if (rc) return rc;
+  return fs->h_count[image];
+}
+
+int pano_featureset_download(pano_featureset* fs, int image, double* coor_xy, float* desc) {
+  if (!fs || image < 0 || image >= fs->n_images) return PANO_ERR_INVALID;
+  int rc = featureset_sync_counts(fs);
+  if (rc) return rc;
+  pano_ctx* ctx = fs->ctx;
+  int n = fs->h_count[image];
+  if (n == 0) return PANO_OK;
+  if (desc) PANO_CUDA(ctx, cudaMemcpyAsync(desc, fs->d_desc + fs->base[image] * 128, (size_t)n * 128 * sizeof(float),
+                                           cudaMemcpyDeviceToHost, ctx->stream));
+  if (coor_xy) {
+    if (!fs->d_coor) return ctx_fail(ctx, PANO_ERR_INVALID, "featureset has no coordinates");
+    PANO_CUDA(ctx, cudaMemcpyAsync(coor_xy, fs->d_coor + fs->base[image] * 2, (size_t)n * 2 * sizeof(double),
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  PANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PANO_OK;
+}
+
+void pano_featureset_free(pano_featureset* fs) { featureset_release(fs); }
+
+// ---------------------------------------------------------------- stage inspection
+
+struct pano_sift_trace {
+  pano_ctx* ctx;
+  SiftWork* wk;
+  pano_featureset* fs;
+  float* d_img;
+};
+
+int pano_sift_trace_run(pano_ctx* ctx, const float* rgb, int w, int h, const pano_params* p, pano_sift_trace** out) {
+  if (!ctx || !rgb || !p || !out) return PANO_ERR_INVALID;
+  *out = nullptr;
+  std::vector<float*> d_imgs;
+  float* d_block = nullptr;
+  int rc = upload_images(ctx, 1, &rgb, &w, &h, d_imgs, &d_block);
+  if (rc) { ctx_free(ctx, d_block); return rc; }
+  pano_featureset* fs = new pano_featureset;
+  fs->ctx = ctx;
+  SiftWork* wk = nullptr;
+  rc = sift_run_batch(ctx, 1, d_imgs.data(), &w, &h, p, fs, &wk);
+  if (rc) { featureset_release(fs); ctx_free(ctx, d_block); return rc; }
+  rc = featureset_sync_counts(fs);
+  if (rc) { sift_work_free(ctx, wk); featureset_release(fs); ctx_free(ctx, d_block); return rc; }
+  pano_sift_trace* t = new pano_sift_trace{ctx, wk, fs, d_block};
+  *out = t;
+  return PANO_OK;
+}
+
+int pano_sift_trace_working_size(const pano_sift_trace* t, int* w0, int* h0) {
+  *w0 = t->wk->h_img[0].w0; *h0 = t->wk->h_img[0].h0;
+  return PANO_OK;
+}
+
+int pano_sift_trace_octave_size(const pano_sift_trace* t, int o, int* w, int* h) {
+  if (o < 0 || o >= t->wk->n_oct) return PANO_ERR_INVALID;
+  *w = t->wk->h_oct[o].w; *h = t->wk->h_oct[o].h;
+  return PANO_OK;
+}
+
+int pano_sift_trace_plane(pano_sift_trace* t, int kind, int o, int level, float* out) {
+  pano_ctx* ctx = t->ctx;
+  SiftWork* wk = t->wk;
+  if (kind == 0) {
+    const ImgMeta& im = wk->h_img[0];
+    return pano_dev_download(ctx, out, wk->arena + im.work_off, (size_t)im.w0 * im.h0 * 3 * sizeof(float));
+  }
+  if (o < 0 || o >= wk->n_oct) return PANO_ERR_INVALID;
+  const OctMeta& om = wk->h_oct[o];
+  size_t bytes = (size_t)om.w * om.h * sizeof(float);
+  if (kind == 1 && level >= 0 && level < wk->n_scale)
+    return pano_dev_download(ctx, out, wk->arena + om.gauss_off + (size_t)level * om.plane, bytes);
+  if (kind == 2 && level >= 0 && level < wk->n_scale - 1)
+    return pano_dev_download(ctx, out, wk->arena + om.dog_off + (size_t)level * om.plane, bytes);
+  // mag/ort are never materialised by the engine (recomputed inside the
+  // orientation/descriptor kernels); not available as planes.
+  return PANO_ERR_INVALID;
+}
+
+int pano_sift_trace_points(pano_sift_trace* t, int stage, int cap, pano_sspoint* out) {
+  pano_ctx* ctx = t->ctx;
+  SiftWork* wk = t->wk;
+  int n_raw = 0, n_desc = t->fs->h_count[0];
+  if (pano_dev_download(ctx, &n_raw, wk->cand_count, sizeof(int))) return PANO_ERR_CUDA;
+  n_raw = std::min(n_raw, SIFT_CAND_CAP);
+  if (stage == 0) {
+    std::vector<uint32_t> keys(std::max(n_raw, 1));
+    if (n_raw && pano_dev_download(ctx, keys.data(), wk->sorted_keys, n_raw * sizeof(uint32_t))) return PANO_ERR_CUDA;
+    for (int i = 0; i < n_raw && i < cap; ++i) {
+      memset(&out[i], 0, sizeof(pano_sspoint));
+      out[i].pyr_id = keys[i] >> 29; out[i].scale_id = (keys[i] >> 26) & 7;
+      out[i].y = (keys[i] >> 13) & 8191; out[i].x = keys[i] & 8191;
+    }
+    return n_raw;
+  }
+  std::vector<pano_sspoint> pts(std::max(n_raw, 1));
+  std::vector<unsigned char> valid(std::max(n_raw, 1));
+  if (n_raw) {
+    if (pano_dev_download(ctx, pts.data(), wk->refined, n_raw * sizeof(pano_sspoint))) return PANO_ERR_CUDA;
+    if (pano_dev_download(ctx, valid.data(), wk->kp_valid, n_raw)) return PANO_ERR_CUDA;
+  }
+  if (stage == 1) {
+    int k = 0;
+    for (int i = 0; i < n_raw; ++i)
+      if (valid[i]) { if (k < cap) out[k] = pts[i]; ++k; }
+    return k;
+  }
+  if (stage == 2) {
+    std::vector<int> dc(std::max(n_desc, 1));
+    std::vector<float> dd(std::max(n_desc, 1));
+    if (n_desc) {
+      if (pano_dev_download(ctx, dc.data(), wk->desc_cand, n_desc * sizeof(int))) return PANO_ERR_CUDA;
+      if (pano_dev_download(ctx, dd.data(), wk->desc_dir, n_desc * sizeof(float))) return PANO_ERR_CUDA;
+    }
+    for (int i = 0; i < n_desc && i < cap; ++i) { out[i] = pts[dc[i]]; out[i].dir = dd[i]; }
+    return n_desc;
+  }
+  return PANO_ERR_INVALID;
+}
+
+int pano_sift_trace_descriptors(pano_sift_trace* t, int cap, double* coor_xy, float* desc) {
+  int n = t->fs->h_count[0];
+  if (n <= cap && n > 0) {
+    int rc = pano_featureset_download(t->fs, 0, coor_xy, desc);
+    if (rc) return rc;
+  }
+  return n;
+}
+
+void pano_sift_trace_free(pano_sift_trace* t) {
+  if (!t) return;
+  sift_work_free(t->ctx, t->wk);
+  featureset_release(t->fs);
+  ctx_free(t->ctx, t->d_img);
+  delete t;
+}
+
+}  // extern "C"

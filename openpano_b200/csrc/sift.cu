@@ -1,0 +1,921 @@
+// sift.cu — batched SIFT on sm_100a: working resize, octave grey, fused
+// 6-sigma separable blur + |DoG|, extrema scan + ordered compaction, sub-pixel
+// refinement, orientation assignment and 128-D RootSIFT descriptors.
+//
+// Replaces (reference paths relative to src/): feature/feature.cc:20-47,
+// feature/dog.cc:42-143, feature/gaussian.hh:29-90, feature/extrema.cc:36-216,
+// feature/orientation.cc:22-100, feature/sift.cc:15-152, lib/imgproc.cc:22-80,
+// :237-249.  One launch per stage covers every image and octave of the batch.
+#include "sift.cuh"
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+
+// ============================================================ K1a working resize
+// lib/imgproc.cc:22-80 resize_bilinear; the reference's per-row/col tables are
+// recomputed per thread with the same float expressions.
+__device__ __forceinline__ void bilinear_coef(int d, float inv, int src_n, int* s, float* frac) {
+  float r = ((float)d + 0.5f) * inv - 0.5f;
+  int si = (int)floorf(r);
+  r -= (float)si;
+  if (si < 0) { si = 0; r = 0.f; }
+  else if (si + 1 >= src_n) { si = src_n - 2; r = 1.f; }
+  *s = si; *frac = r;
+}
+
+__global__ void k_working_resize(const ImgMeta* __restrict__ imgs, float* __restrict__ arena) {
+  const ImgMeta im = imgs[blockIdx.z];
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (c >= im.w0 || r >= im.h0) return;
+  int sx, sy; float rx, ry;
+  bilinear_coef(r, im.ifx, im.in_h, &sx, &rx);
+  bilinear_coef(c, im.ify, im.in_w, &sy, &ry);
+  float irx = 1.0f - rx, iry = 1.0f - ry;
+  const float* p0 = im.src + ((size_t)sx * im.in_w + sy) * 3;
+  const float* p1 = p0 + (size_t)im.in_w * 3;
+  float* dst = arena + im.work_off + ((size_t)r * im.w0 + c) * 3;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float p00 = __ldg(p0 + ch), p01 = __ldg(p0 + 3 + ch), p10 = __ldg(p1 + ch), p11 = __ldg(p1 + 3 + ch);
+    dst[ch] = rx * (p11 * ry + p10 * iry) + irx * (p01 * ry + p00 * iry);
+  }
+}
+
+// ============================================================ K1b octave grey
+// feature/dog.cc:96-114 (octave o>0 resized from the WORKING image) +
+// lib/imgproc.cc:237-249 rgb2grey.
+__global__ void k_octave_grey(const ImgMeta* __restrict__ imgs, const OctMeta* __restrict__ octs,
+                              float* __restrict__ arena) {
+  const OctMeta om = octs[blockIdx.z];
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = blockIdx.y * blockDim.y + threadIdx.y;
+  if (c >= om.w || r >= om.h) return;
+  const ImgMeta im = imgs[om.img];
+  const float* work = arena + im.work_off;
+  float v0, v1, v2;
+  if (om.oct == 0) {
+    const float* p = work + ((size_t)r * im.w0 + c) * 3;
+    v0 = p[0]; v1 = p[1]; v2 = p[2];
+  } else {
+    int sx, sy; float rx, ry;
+    bilinear_coef(r, om.ifx, im.h0, &sx, &rx);
+    bilinear_coef(c, om.ify, im.w0, &sy, &ry);
+    float irx = 1.0f - rx, iry = 1.0f - ry;
+    const float* p0 = work + ((size_t)sx * im.w0 + sy) * 3;
+    const float* p1 = p0 + (size_t)im.w0 * 3;
+    v0 = rx * (p1[3] * ry + p1[0] * iry) + irx * (p0[3] * ry + p0[0] * iry);
+    v1 = rx * (p1[4] * ry + p1[1] * iry) + irx * (p0[4] * ry + p0[1] * iry);
+    v2 = rx * (p1[5] * ry + p1[2] * iry) + irx * (p0[5] * ry + p0[2] * iry);
+  }
+  arena[om.gauss_off + (size_t)r * om.w + c] = (v0 + v1 + v2) / 3.f;
+}
+
+// ============================================================ K2 blur + |DoG|
+// feature/gaussian.hh:29-90 (column pass, then row pass over the column result,
+// replicate border, ascending-k mul-then-add), every level from level 0
+// (feature/dog.cc:54-57), and DOGSpace::diff (dog.cc:116-129) fused: the grey
+// tile is staged once in shared memory and all nlev sigmas are produced from it.
+#define BT_W 64
+#define BT_H 32
+#define BT_THREADS 256
+
+__global__ void __launch_bounds__(BT_THREADS)
+k_blur_dog(const OctMeta* __restrict__ octs, const BlurTile* __restrict__ tiles,
+           float* __restrict__ arena, const __grid_constant__ GaussTable gt) {
+  extern __shared__ float smem[];
+  const BlurTile tl = tiles[blockIdx.x];
+  const OctMeta om = octs[tl.om];
+  const int R = gt.rmax;
+  const int GW = BT_W + 2 * R;           // grey tile width
+  const int GH = BT_H + 2 * R;
+  float* grey = smem;                    // [GH][GW]
+  float* colbuf = smem + GH * GW;        // [BT_H][GW]
+  const int x0 = tl.tx * BT_W, y0 = tl.ty * BT_H;
+  const float* g0 = arena + om.gauss_off;
+  const int tid = threadIdx.x;
+
+  for (int i = tid; i < GH * GW; i += BT_THREADS) {
+    int yy = i / GW, xx = i - yy * GW;
+    int gy = min(max(y0 + yy - R, 0), om.h - 1);
+    int gx = min(max(x0 + xx - R, 0), om.w - 1);
+    grey[i] = __ldg(g0 + (size_t)gy * om.w + gx);
+  }
+  __syncthreads();
+
+  const int tx = tid & (BT_W - 1), ty = tid / BT_W;   // 64 x 4
+  float prev[BT_H / 4];
+#pragma unroll
+  for (int i = 0; i < BT_H / 4; ++i) prev[i] = grey[(ty + 4 * i + R) * GW + tx + R];
+
+  for (int s = 0; s < gt.nlev; ++s) {
+    const int c = gt.center[s];
+    const float* taps = gt.taps[s];      // taps[k + c], k = -c..c
+    const int cw = BT_W + 2 * c;         // columns needed by the row pass
+    // column pass
+    for (int i = tid; i < BT_H * cw; i += BT_THREADS) {
+      int y = i / cw, xx = i - y * cw;
+      const float* col = grey + (y + R - c) * GW + (xx + R - c);
+      float tmp = 0.f;
+      for (int k = 0; k <= 2 * c; ++k) tmp += col[k * GW] * taps[k];
+      colbuf[y * GW + xx] = tmp;
+    }
+    __syncthreads();
+    // row pass + DoG
+    float* lvl = arena + om.gauss_off + (size_t)(s + 1) * om.plane;
+    float* dog = arena + om.dog_off + (size_t)s * om.plane;
+#pragma unroll
+    for (int i = 0; i < BT_H / 4; ++i) {
+      int y = ty + 4 * i;
+      const float* row = colbuf + y * GW + tx;
+      float tmp = 0.f;
+      for (int k = 0; k <= 2 * c; ++k) tmp += row[k] * taps[k];
+      int gx = x0 + tx, gy = y0 + y;
+      if (gx < om.w && gy < om.h) {
+        size_t o = (size_t)gy * om.w + gx;
+        lvl[o] = tmp;
+        dog[o] = fabsf(prev[i] - tmp);
+      }
+      prev[i] = tmp;
+    }
+    __syncthreads();
+  }
+}
+
+// ============================================================ K3 extrema scan
+// feature/extrema.cc:170-216.  Candidates are appended unordered (one atomic per
+// hit) with a key that encodes the canonical order octave -> scale -> raster.
+__device__ __forceinline__ uint32_t make_key(int oct, int scale, int y, int x) {
+  return ((uint32_t)oct << 29) | ((uint32_t)scale << 26) | ((uint32_t)y << 13) | (uint32_t)x;
+}
+
+__global__ void k_extrema_scan(const OctMeta* __restrict__ octs, const float* __restrict__ arena,
+                               int nscale, float pre_color_thres, float diff_thres,
+                               int* __restrict__ cand_count, uint32_t* __restrict__ cand_keys) {
+  const OctMeta om = octs[blockIdx.z];
+  int c = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  int r = blockIdx.y * blockDim.y + threadIdx.y + 1;
+  if (c >= om.w - 1 || r >= om.h - 1) return;
+  const float* dog = arena + om.dog_off;
+  const size_t o = (size_t)r * om.w + c;
+  for (int j = 1; j < nscale - 2; ++j) {
+    const float* now = dog + (size_t)j * om.plane;
+    float center = __ldg(now + o);
+    if (center < pre_color_thres) continue;
+    float cmp1 = center - diff_thres, cmp2 = center + diff_thres;
+    bool mx = true, mn = true;
+#pragma unroll
+    for (int ds = -1; ds <= 1; ++ds) {
+      const float* pl = now + (ptrdiff_t)ds * om.plane;
+#pragma unroll
+      for (int di = -1; di <= 1; ++di)
+#pragma unroll
+        for (int dj = -1; dj <= 1; ++dj) {
+          if (ds == 0 && di == 0 && dj == 0) continue;
+          float v = __ldg(pl + o + (ptrdiff_t)di * om.w + dj);
+          if (v >= cmp1) mx = false;
+          if (v <= cmp2) mn = false;
+        }
+    }
+    if (mx || mn) {
+      int slot = atomicAdd(&cand_count[om.img], 1);
+      if (slot < SIFT_CAND_CAP) cand_keys[(size_t)om.img * SIFT_CAND_CAP + slot] = make_key(om.oct, j, r, c);
+    }
+  }
+}
+
+// ============================================================ K3b ordered compaction
+// Rank sort per image: keys are unique, rank = #keys smaller.
+__global__ void k_rank_sort(const int* __restrict__ cand_count, const uint32_t* __restrict__ keys,
+                            uint32_t* __restrict__ sorted) {
+  __shared__ uint32_t sk[1024];
+  const int img = blockIdx.y;
+  const int n = min(cand_count[img], SIFT_CAND_CAP);
+  const uint32_t* k = keys + (size_t)img * SIFT_CAND_CAP;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (blockIdx.x * blockDim.x >= n) return;
+  uint32_t mine = i < n ? k[i] : 0xffffffffu;
+  int rank = 0;
+  for (int base = 0; base < n; base += 1024) {
+    int m = min(1024, n - base);
+    for (int t = threadIdx.x; t < m; t += blockDim.x) sk[t] = k[base + t];
+    __syncthreads();
+    for (int t = 0; t < m; ++t) rank += sk[t] < mine;
+    __syncthreads();
+  }
+  if (i < n) sorted[(size_t)img * SIFT_CAND_CAP + rank] = mine;
+}
+
+// ============================================================ K4 refinement
+// Same arithmetic as oracle/small_linalg.h (Eigen FullPivLU restated).
+__device__ bool lu3_inverse(const double* a_in, double* inv) {
+  double a[9];
+  int rowperm[3] = {0, 1, 2}, colperm[3] = {0, 1, 2};
+  int nonzero = 3, rank = 0;
+  double maxpivot = 0.0;
+  for (int i = 0; i < 9; ++i) a[i] = a_in[i];
+  for (int k = 0; k < 3; ++k) {
+    int br = k, bc = k;
+    double big = -1.0;
+    for (int i = k; i < 3; ++i)
+      for (int j = k; j < 3; ++j) {
+        double v = fabs(a[i * 3 + j]);
+        if (v > big) { big = v; br = i; bc = j; }
+      }
+    if (big == 0.0) { nonzero = k; break; }
+    if (big > maxpivot) maxpivot = big;
+    if (br != k) {
+      for (int j = 0; j < 3; ++j) { double w = a[k * 3 + j]; a[k * 3 + j] = a[br * 3 + j]; a[br * 3 + j] = w; }
+      int t = rowperm[k]; rowperm[k] = rowperm[br]; rowperm[br] = t;
+    }
+    if (bc != k) {
+      for (int i = 0; i < 3; ++i) { double w = a[i * 3 + k]; a[i * 3 + k] = a[i * 3 + bc]; a[i * 3 + bc] = w; }
+      int t = colperm[k]; colperm[k] = colperm[bc]; colperm[bc] = t;
+    }
+    for (int i = k + 1; i < 3; ++i) a[i * 3 + k] /= a[k * 3 + k];
+    for (int i = k + 1; i < 3; ++i)
+      for (int j = k + 1; j < 3; ++j) a[i * 3 + j] -= a[i * 3 + k] * a[k * 3 + j];
+  }
+  double thr = 2.2204460492503131e-16 * 3.0 * maxpivot;
+  for (int k = 0; k < nonzero; ++k) if (fabs(a[k * 3 + k]) > thr) ++rank;
+  if (rank < 3) return false;
+  for (int col = 0; col < 3; ++col) {
+    double c[3];
+    for (int i = 0; i < 3; ++i) c[i] = rowperm[i] == col ? 1.0 : 0.0;
+    c[1] -= a[3] * c[0];
+    c[2] -= a[6] * c[0];
+    c[2] -= a[7] * c[1];
+    c[2] /= a[8];
+    c[1] -= a[5] * c[2];
+    c[0] -= a[2] * c[2];
+    c[1] /= a[4];
+    c[0] -= a[1] * c[1];
+    c[0] /= a[0];
+    for (int i = 0; i < 3; ++i) inv[colperm[i] * 3 + col] = c[i];
+  }
+  return true;
+}
+
+__device__ void sym3_pinv(const double* a_in, double* out) {
+  double a[9], v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) a[i] = a_in[i];
+  for (int sweep = 0; sweep < 32; ++sweep) {
+    double off = fabs(a[1]) + fabs(a[2]) + fabs(a[5]);
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double apq = a[p * 3 + q];
+        if (apq == 0.0) continue;
+        double theta = (a[q * 3 + q] - a[p * 3 + p]) / (2.0 * apq);
+        double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        double c = 1.0 / sqrt(t * t + 1.0);
+        double s = t * c;
+        for (int k = 0; k < 3; ++k) {
+          double akp = a[k * 3 + p], akq = a[k * 3 + q];
+          a[k * 3 + p] = c * akp - s * akq;
+          a[k * 3 + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {
+          double apk = a[p * 3 + k], aqk = a[q * 3 + k];
+          a[p * 3 + k] = c * apk - s * aqk;
+          a[q * 3 + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {
+          double vkp = v[k * 3 + p], vkq = v[k * 3 + q];
+          v[k * 3 + p] = c * vkp - s * vkq;
+          v[k * 3 + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < 3; ++k) {
+        double l = a[k * 3 + k];
+        if (fabs(l) > 1e-6) acc += v[i * 3 + k] * (1.0 / l) * v[j * 3 + k];
+      }
+      out[i * 3 + j] = acc;
+    }
+}
+
+struct RefineParams {
+  int nscale, depth;
+  float offset_thres, contrast_thres, edge_ratio, gauss_sigma, scale_factor;
+};
+
+// feature/extrema.cc:63-168: calc_kp_offset(+_iter) and is_edge_response.
+__global__ void k_refine(const OctMeta* __restrict__ octs, const float* __restrict__ arena, int n_oct,
+                         const int* __restrict__ cand_count, const uint32_t* __restrict__ sorted,
+                         RefineParams rp, pano_sspoint* __restrict__ out, unsigned char* __restrict__ valid) {
+  const int img = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(cand_count[img], SIFT_CAND_CAP);
+  if (i >= n) return;
+  const size_t slot = (size_t)img * SIFT_CAND_CAP + i;
+  uint32_t key = sorted[slot];
+  int oct = key >> 29, s0 = (key >> 26) & 7, y0 = (key >> 13) & 8191, x0 = key & 8191;
+  const OctMeta om = octs[img * n_oct + oct];
+  const float* dog = arena + om.dog_off;
+  const int w = om.w, h = om.h;
+#define DG(xx, yy, ss) __ldg(dog + (size_t)(ss) * om.plane + (size_t)(yy) * w + (xx))
+  pano_sspoint sp;
+  sp.x = x0; sp.y = y0; sp.pyr_id = oct; sp.scale_id = s0;
+  sp.real_x = 0; sp.real_y = 0; sp.dir = 0; sp.scale_factor = 0;
+  bool ok = true;
+  int nowx = x0, nowy = y0, nows = s0, niter = 0;
+  double offset[3] = {0, 0, 0}, delta[3] = {0, 0, 0};
+  for (; niter < rp.depth; ++niter) {
+    if (!DBETWEEN(nowx, 1, w - 1) || !DBETWEEN(nowy, 1, h - 1) || !DBETWEEN(nows, 1, rp.nscale - 2)) {
+      ok = false; break;
+    }
+    const int x = nowx, y = nowy, s = nows;
+    float val = DG(x, y, s);
+    delta[0] = (double)((DG(x + 1, y, s) - DG(x - 1, y, s)) / 2);
+    delta[1] = (double)((DG(x, y + 1, s) - DG(x, y - 1, s)) / 2);
+    delta[2] = (double)((DG(x, y, s + 1) - DG(x, y, s - 1)) / 2);
+    double dxx = (double)(DG(x + 1, y, s) + DG(x - 1, y, s) - val - val);
+    double dyy = (double)(DG(x, y + 1, s) + DG(x, y - 1, s) - val - val);
+    double dss = (double)(DG(x, y, s + 1) + DG(x, y, s - 1) - val - val);
+    double dxy = (double)((DG(x + 1, y + 1, s) - DG(x + 1, y - 1, s) - DG(x - 1, y + 1, s) + DG(x - 1, y - 1, s)) / 4);
+    double dys = (double)((DG(x, y + 1, s + 1) - DG(x, y - 1, s + 1) - DG(x, y + 1, s - 1) + DG(x, y - 1, s - 1)) / 4);
+    double dsx = (double)((DG(x + 1, y, s + 1) - DG(x - 1, y, s + 1) - DG(x + 1, y, s - 1) + DG(x - 1, y, s - 1)) / 4);
+    double m[9] = {dxx, dxy, dsx, dxy, dyy, dys, dsx, dys, dss}, inv[9];
+    if (!lu3_inverse(m, inv)) sym3_pinv(m, inv);
+    for (int q = 0; q < 3; ++q) {
+      double acc = inv[q * 3] * delta[0];
+      acc += inv[q * 3 + 1] * delta[1];
+      acc += inv[q * 3 + 2] * delta[2];
+      offset[q] = acc;
+    }
+    double am = fmax(fabs(offset[0]), fmax(fabs(offset[1]), fabs(offset[2])));
+    if (am < (double)rp.offset_thres) break;
+    nowx = (int)((double)nowx + round(offset[0]));
+    nowy = (int)((double)nowy + round(offset[1]));
+    nows = (int)((double)nows + round(offset[2]));
+  }
+  if (ok && niter == rp.depth) ok = false;
+  if (ok) {
+    double dextr = offset[0] * delta[0] + offset[1] * delta[1] + offset[2] * delta[2];
+    dextr = (double)DG(nowx, nowy, nows) + dextr / 2;
+    if (dextr < (double)rp.contrast_thres) ok = false;
+  }
+  if (ok) {
+    sp.x = nowx; sp.y = nowy; sp.scale_id = nows;
+    sp.scale_factor = (float)((double)rp.gauss_sigma *
+                              pow((double)rp.scale_factor, ((double)nows + offset[2]) / rp.nscale));
+    sp.real_x = ((double)nowx + offset[0]) / w;
+    sp.real_y = ((double)nowy + offset[1]) / h;
+    // is_edge_response on dog[scale_id] at the refined integer position
+    const int x = nowx, y = nowy, s = nows;
+    float val = DG(x, y, s);
+    float dxx = DG(x + 1, y, s) + DG(x - 1, y, s) - val - val;
+    float dyy = DG(x, y + 1, s) + DG(x, y - 1, s) - val - val;
+    float dxy = (DG(x + 1, y + 1, s) + DG(x - 1, y - 1, s) - DG(x - 1, y + 1, s) - DG(x + 1, y - 1, s)) / 4;
+    float det = dxx * dyy - dxy * dxy;
+    if (det <= 0) ok = false;
+    else {
+      float tr2 = (dxx + dyy) * (dxx + dyy);
+      float lim = ((rp.edge_ratio + 1) * (rp.edge_ratio + 1)) / rp.edge_ratio;
+      if (!(tr2 / det < lim)) ok = false;
+    }
+  }
+#undef DG
+  out[slot] = sp;
+  valid[slot] = ok ? 1 : 0;
+}
+
+// ============================================================ K5 orientation
+// feature/orientation.cc:34-100.  One warp per keypoint.  Histogram bins are
+// accumulated in the reference's scan order (xx outer, yy inner) so the float
+// sums are bit-identical: lanes first evaluate (bin, weight*mag) for a chunk of
+// window positions in parallel, then lane b replays the chunk in order for bin b.
+#define ORI_BINS 36
+#define ORI_CHUNK 256
+#define ORI_WARPS 4
+
+__global__ void __launch_bounds__(ORI_WARPS * 32)
+k_orientation(const OctMeta* __restrict__ octs, const float* __restrict__ arena, int n_oct,
+              const int* __restrict__ cand_count, const pano_sspoint* __restrict__ pts,
+              const unsigned char* __restrict__ valid, float ori_radius, int smooth_count,
+              int* __restrict__ npeaks, float* __restrict__ dirs) {
+  __shared__ signed char s_bin[ORI_WARPS][ORI_CHUNK];
+  __shared__ float s_val[ORI_WARPS][ORI_CHUNK];
+  __shared__ float s_hist[ORI_WARPS][ORI_BINS + 4];
+  const int img = blockIdx.y;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * ORI_WARPS + wid;
+  const int n = min(cand_count[img], SIFT_CAND_CAP);
+  if (i >= n) return;
+  const size_t slot = (size_t)img * SIFT_CAND_CAP + i;
+  if (!valid[slot]) { if (lane == 0) npeaks[slot] = 0; return; }
+  const pano_sspoint p = pts[slot];
+  const OctMeta om = octs[img * n_oct + p.pyr_id];
+  const float* lvl = arena + om.gauss_off + (size_t)p.scale_id * om.plane;
+  const float halfipi = (float)(0.5 / PANO_PI);   // 0.5f / M_PI evaluated in double
+  const float gws = p.scale_factor * 1.5f;
+  const int rad = (int)roundf(p.scale_factor * ori_radius);
+  const float exp_denom = 2 * (gws * gws);
+  const int side = 2 * rad, total = side * side;
+  float h0 = 0.f, h1 = 0.f;  // bins lane and lane+32
+  for (int base = 0; base < total; base += ORI_CHUNK) {
+    int m = min(ORI_CHUNK, total - base);
+    for (int t = lane; t < m; t += 32) {
+      int pos = base + t;
+      int xx = pos / side - rad, yy = pos % side - rad;
+      int newx = p.x + xx, newy = p.y + yy;
+      signed char bin = -1;
+      float val = 0.f;
+      if (DBETWEEN(newx, 1, om.w - 1) && DBETWEEN(newy, 1, om.h - 1)) {
+        float fx = (float)xx, fy = (float)yy, fr = (float)rad;
+        float d2 = fx * fx + fy * fy;
+        if (!(d2 > fr * fr)) {
+          float mag, ort;
+          mag_ort_at(lvl, om.w, newx, newy, &mag, &ort);
+          int b = (int)roundf((float)ORI_BINS * halfipi * ort);
+          if (b == ORI_BINS) b = 0;
+          float weight = glibc_expf(-d2 / exp_denom);
+          bin = (signed char)b;
+          val = weight * mag;
+        }
+      }
+      s_bin[wid][t] = bin;
+      s_val[wid][t] = val;
+    }
+    __syncwarp();
+    for (int t = 0; t < m; ++t) {
+      int b = s_bin[wid][t];
+      float v = s_val[wid][t];
+      if (b == lane) h0 += v;
+      if (b == lane + 32) h1 += v;
+    }
+    __syncwarp();
+  }
+  s_hist[wid][lane] = h0;
+  if (lane < ORI_BINS - 32) s_hist[wid][lane + 32] = h1;
+  __syncwarp();
+  if (lane == 0) {  // in-place sequential smoothing (orientation.cc:70-75)
+    float* hist = s_hist[wid];
+    for (int K = smooth_count; K--;)
+      for (int b = 0; b < ORI_BINS; ++b) {
+        float prev = hist[b == 0 ? ORI_BINS - 1 : b - 1];
+        float next = hist[b == ORI_BINS - 1 ? 0 : b + 1];
+        hist[b] = (float)((double)hist[b] * 0.5 + (double)(prev + next) * 0.25);
+      }
+  }
+  __syncwarp();
+  const float* hist = s_hist[wid];
+  float mx = 0.f;
+  for (int b = 0; b < ORI_BINS; ++b) if (mx < hist[b]) mx = hist[b];
+  const float thres = mx * 0.8f;
+  int count = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    int b = lane + 32 * pass;
+    bool peak = false;
+    float dir = 0.f;
+    if (b < ORI_BINS) {
+      float hb = hist[b];
+      float prev = hist[b == 0 ? ORI_BINS - 1 : b - 1];
+      float next = hist[b == ORI_BINS - 1 ? 0 : b + 1];
+      if (hb > thres && hb > (prev < next ? next : prev)) {
+        peak = true;
+        double newbin = (double)(float)b - 0.5 + (double)((hb - prev) / (prev + next - 2 * hb));
+        if (newbin < 0) newbin += ORI_BINS;
+        else if (newbin >= ORI_BINS) newbin -= ORI_BINS;
+        dir = (float)(newbin / ORI_BINS * 2 * PANO_PI);
+      }
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, peak);
+    if (peak) {
+      int k = count + __popc(mask & ((1u << lane) - 1));
+      if (k < SIFT_MAX_PEAKS) dirs[slot * SIFT_MAX_PEAKS + k] = dir;
+    }
+    count += __popc(mask);
+  }
+  if (lane == 0) npeaks[slot] = min(count, SIFT_MAX_PEAKS);
+}
+
+// ============================================================ K5b expansion scan
+// OrientationAssign::work (orientation.cc:22-32): keypoint order is preserved,
+// peaks ascending.  One block per image: exclusive scan of npeaks.
+#define SCAN_THREADS 1024
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_expand_scan(const int* __restrict__ cand_count, const unsigned char* __restrict__ valid,
+              const int* __restrict__ npeaks, const float* __restrict__ dirs,
+              int* __restrict__ n_desc, int* __restrict__ n_refined,
+              int* __restrict__ desc_cand, float* __restrict__ desc_dir) {
+  __shared__ int s_warp[32];
+  __shared__ int s_warp2[32];
+  const int img = blockIdx.x;
+  const int n = min(cand_count[img], SIFT_CAND_CAP);
+  const int per = (SIFT_CAND_CAP + SCAN_THREADS - 1) / SCAN_THREADS;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const size_t base = (size_t)img * SIFT_CAND_CAP;
+  int local = 0, nval = 0;
+  for (int k = 0; k < per; ++k) {
+    int i = tid * per + k;
+    if (i < n && valid[base + i]) { local += npeaks[base + i]; nval++; }
+  }
+  int incl = local, incl2 = nval;
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, d);
+    int t2 = __shfl_up_sync(0xffffffffu, incl2, d);
+    if (lane >= d) { incl += t; incl2 += t2; }
+  }
+  if (lane == 31) { s_warp[wid] = incl; s_warp2[wid] = incl2; }
+  __syncthreads();
+  if (wid == 0) {
+    int v = s_warp[lane], v2 = s_warp2[lane];
+    int a = v, a2 = v2;
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, a, d);
+      int t2 = __shfl_up_sync(0xffffffffu, a2, d);
+      if (lane >= d) { a += t; a2 += t2; }
+    }
+    s_warp[lane] = a - v;   // exclusive
+    s_warp2[lane] = a2;     // inclusive (only the last is used)
+  }
+  __syncthreads();
+  int off = s_warp[wid] + incl - local;
+  for (int k = 0; k < per; ++k) {
+    int i = tid * per + k;
+    if (i < n && valid[base + i]) {
+      int np = npeaks[base + i];
+      for (int q = 0; q < np; ++q) {
+        int d = off + q;
+        if (d < SIFT_DESC_CAP) {
+          desc_cand[(size_t)img * SIFT_DESC_CAP + d] = i;
+          desc_dir[(size_t)img * SIFT_DESC_CAP + d] = dirs[(base + i) * SIFT_MAX_PEAKS + q];
+        }
+      }
+      off += np;
+    }
+  }
+  if (tid == SCAN_THREADS - 1) { n_desc[img] = off; n_refined[img] = s_warp2[31]; }
+}
+
+// ============================================================ K6 descriptor
+// feature/sift.cc:87-152 calc_descriptor, :48-67 trilinear_interpolate, :15-46
+// hist_to_descriptor (RootSIFT).  One 128-thread block per oriented keypoint,
+// thread t owns histogram bin t.  Phase 1 evaluates every window position in
+// parallel into shared-memory records; phase 2 lets each bin replay, in the
+// reference's scan order, only the positions inside the bounding box of its
+// 2x2-cell footprint, so every bin's float sum is bit-identical to the serial
+// loop without 128 threads scanning the whole window.
+#define DESC_THREADS 128
+#define DESC_REC_CAP 1600
+#define DESC_SKIP 0xffffffffu
+
+struct DescParams { int hist_scale_factor; int int_factor; };
+
+__global__ void __launch_bounds__(DESC_THREADS)
+k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
+             const float* __restrict__ arena, int n_oct, int n_img,
+             const pano_sspoint* __restrict__ pts, const int* __restrict__ n_desc,
+             const int* __restrict__ desc_cand, const float* __restrict__ desc_dir,
+             DescParams dp, float* __restrict__ out_desc, double* __restrict__ out_coor) {
+  __shared__ float r_w[DESC_REC_CAP], r_yd[DESC_REC_CAP], r_xd[DESC_REC_CAP], r_hd[DESC_REC_CAP];
+  __shared__ uint32_t r_pk[DESC_REC_CAP];
+  __shared__ float s_hist[128];
+  __shared__ float s_sum;
+  const int tid = threadIdx.x;
+  const float pi2 = (float)(2 * PANO_PI);
+  const float nbin_per_rad = 8 / pi2;
+  for (int img = 0; img < n_img; ++img) {
+    const int nd = min(n_desc[img], SIFT_DESC_CAP);
+    const ImgMeta im = imgs[img];
+    for (int d = blockIdx.x; d < nd; d += gridDim.x) {
+      const size_t dslot = (size_t)img * SIFT_DESC_CAP + d;
+      const pano_sspoint p = pts[(size_t)img * SIFT_CAND_CAP + desc_cand[dslot]];
+      const float ort = desc_dir[dslot];
+      const OctMeta om = octs[img * n_oct + p.pyr_id];
+      const float* lvl = arena + om.gauss_off + (size_t)p.scale_id * om.plane;
+      const int w = om.w, h = om.h;
+      const float hist_w = p.scale_factor * (float)dp.hist_scale_factor;
+      const float exp_denom = 2 * (4.f * 4.f);
+      const int radius = (int)round(PANO_SQRT1_2 * (double)hist_w * (4 + 1));
+      float sinort, cosort;
+      glibc_sincosf(ort, &sinort, &cosort);
+      const int side = 2 * radius + 1;
+      const int cols_per_chunk = max(1, DESC_REC_CAP / side);
+
+      // this thread's bin and its bounding box in window offsets
+      const int cell = tid >> 3, bh = tid & 7, by = cell >> 2, bx = cell & 3;
+      int bx_lo, bx_hi, by_lo, by_hi;
+      {
+        // cell footprint in rotated bin units: x_rot in [bx-2.5, bx-0.5), same for y
+        float xr0 = (float)bx - 2.5f, xr1 = (float)bx - 0.5f;
+        float yr0 = (float)by - 2.5f, yr1 = (float)by - 0.5f;
+        float xmin = 1e30f, xmax = -1e30f, ymin = 1e30f, ymax = -1e30f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float xr = (q & 1) ? xr1 : xr0, yr = (q & 2) ? yr1 : yr0;
+          float px = hist_w * (xr * cosort - yr * sinort);
+          float py = hist_w * (xr * sinort + yr * cosort);
+          xmin = fminf(xmin, px); xmax = fmaxf(xmax, px);
+          ymin = fminf(ymin, py); ymax = fmaxf(ymax, py);
+        }
+        bx_lo = max(-radius, (int)floorf(xmin) - 2); bx_hi = min(radius, (int)ceilf(xmax) + 2);
+        by_lo = max(-radius, (int)floorf(ymin) - 2); by_hi = min(radius, (int)ceilf(ymax) + 2);
+      }
+      float acc = 0.f;
+
+      for (int cx0 = -radius; cx0 <= radius; cx0 += cols_per_chunk) {
+        const int cx1 = min(radius, cx0 + cols_per_chunk - 1);
+        const int nrec = (cx1 - cx0 + 1) * side;
+        // phase 1
+        for (int t = tid; t < nrec; t += DESC_THREADS) {
+          int xx = cx0 + t / side, yy = t % side - radius;
+          int nowx = p.x + xx, nowy = p.y + yy;
+          uint32_t pk = DESC_SKIP;
+          float wgt = 0.f, ybind = 0.f, xbind = 0.f, hbind = 0.f;
+          if (DBETWEEN(nowx, 1, w - 1) && DBETWEEN(nowy, 1, h - 1)) {
+            float fx = (float)xx, fy = (float)yy, fr = (float)radius;
+            if (!(fx * fx + fy * fy > fr * fr)) {
+              float y_rot = ((float)(-xx) * sinort + fy * cosort) / hist_w;
+              float x_rot = (fx * cosort + fy * sinort) / hist_w;
+              float ybin = (float)((double)(y_rot + 2.f) - 0.5);
+              float xbin = (float)((double)(x_rot + 2.f) - 0.5);
+              if (ybin >= -1.f && ybin <= 3.f && xbin >= -1.f && xbin <= 3.f) {
+                float now_mag, now_ort;
+                mag_ort_at(lvl, w, nowx, nowy, &now_mag, &now_ort);
+                float weight = glibc_expf(-(x_rot * x_rot + y_rot * y_rot) / exp_denom);
+                weight = weight * now_mag;
+                now_ort -= ort;
+                if (now_ort < 0) now_ort += pi2;
+                if (now_ort > pi2) now_ort -= pi2;
+                float hbin = now_ort * nbin_per_rad;
+                int ybinf = (int)floorf(ybin), xbinf = (int)floorf(xbin), hbinf = (int)floorf(hbin);
+                ybind = ybin - (float)ybinf;
+                xbind = xbin - (float)xbinf;
+                hbind = hbin - (float)hbinf;
+                wgt = weight;
+                pk = (uint32_t)(ybinf + 2) | ((uint32_t)(xbinf + 2) << 8) | ((uint32_t)hbinf << 16);
+              }
+            }
+          }
+          r_pk[t] = pk; r_w[t] = wgt; r_yd[t] = ybind; r_xd[t] = xbind; r_hd[t] = hbind;
+        }
+        __syncthreads();
+        // phase 2
+        {
+          int xa = max(cx0, bx_lo), xb = min(cx1, bx_hi);
+          for (int xx = xa; xx <= xb; ++xx) {
+            const int rb = (xx - cx0) * side + radius;
+            for (int yy = by_lo; yy <= by_hi; ++yy) {
+              const int t = rb + yy;
+              uint32_t pk = r_pk[t];
+              if (pk == DESC_SKIP) continue;
+              int dy = by - ((int)(pk & 0xff) - 2);
+              int dx = bx - ((int)((pk >> 8) & 0xff) - 2);
+              if ((unsigned)dy > 1u || (unsigned)dx > 1u) continue;
+              int hbinf = (int)(pk >> 16);
+              int ho;
+              if ((hbinf & 7) == bh) ho = 0;
+              else if (((hbinf + 1) & 7) == bh) ho = 1;
+              else continue;
+              float yd = r_yd[t], xd = r_xd[t], hd = r_hd[t];
+              float w_y = r_w[t] * (dy ? yd : 1 - yd);
+              float w_x = w_y * (dx ? xd : 1 - xd);
+              acc += w_x * (ho ? hd : 1 - hd);
+            }
+          }
+        }
+        __syncthreads();
+      }
+      // RootSIFT: L1 normalise (sequential sum), sqrt, * DESC_INT_FACTOR
+      s_hist[tid] = acc;
+      __syncthreads();
+      if (tid == 0) {
+        float sum = 0.f;
+        for (int q = 0; q < 128; ++q) sum += s_hist[q];
+        s_sum = sum;
+      }
+      __syncthreads();
+      float v = acc / s_sum;
+      out_desc[dslot * 128 + tid] = sqrtf(v) * (float)dp.int_factor;
+      if (tid == 0) {
+        out_coor[dslot * 2] = (p.real_x - 0.5) * im.in_w;
+        out_coor[dslot * 2 + 1] = (p.real_y - 0.5) * im.in_h;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ============================================================ host driver
+
+int host_gauss_kernel(float sigma, int window_factor, float* taps, int cap) {
+  // feature/gaussian.cc:17-40 (weights in f32, expf from the host libm: the very
+  // function the reference calls)
+  int kw = (int)(ceil(0.3 * (sigma / 2 - 1) + 0.8) * window_factor);
+  if (kw % 2 == 0) kw++;
+  if (kw > cap) return -kw;
+  const int center = kw / 2;
+  float* k = taps + center;
+  k[0] = 1;
+  float exp_coeff = (float)(-1.0 / (sigma * sigma * 2)), wsum = 1;
+  for (int i = 1; i <= center; i++) {
+    k[i] = expf((float)(i * i) * exp_coeff);
+    wsum += k[i] * 2;
+  }
+  float fac = (float)(1.0 / wsum);
+  k[0] = fac;
+  for (int i = 1; i <= center; i++) { k[i] *= fac; k[-i] = k[i]; }
+  return kw;
+}
+
+void sift_work_free(pano_ctx* ctx, SiftWork* wk) {
+  if (!wk) return;
+  ctx_free(ctx, wk->arena); ctx_free(ctx, wk->d_img); ctx_free(ctx, wk->d_oct); ctx_free(ctx, wk->d_tiles);
+  ctx_free(ctx, wk->cand_count); ctx_free(ctx, wk->cand_keys); ctx_free(ctx, wk->sorted_keys);
+  ctx_free(ctx, wk->refined); ctx_free(ctx, wk->kp_valid); ctx_free(ctx, wk->npeaks);
+  ctx_free(ctx, wk->dirs); ctx_free(ctx, wk->n_refined);
+  ctx_free(ctx, wk->desc_cand); ctx_free(ctx, wk->desc_dir);
+  delete wk;
+}
+
+int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w, const int* h,
+                   const pano_params* p, pano_featureset* fs, SiftWork** keep) {
+  if (n <= 0 || !d_src || !w || !h || !p || !fs) return ctx_fail(ctx, PANO_ERR_INVALID, "sift: bad argument");
+  const int n_oct = p->num_octave, n_scale = p->num_scale;
+  if (n_oct < 1 || n_oct > SIFT_MAX_OCT || n_scale < 4 || n_scale - 1 > SIFT_MAX_LEVELS || n_scale - 2 > 7)
+    return ctx_fail(ctx, PANO_ERR_INVALID, "sift: NUM_OCTAVE/NUM_SCALE out of supported range");
+
+  SiftWork* wk = new SiftWork;
+  wk->n_img = n; wk->n_oct = n_oct; wk->n_scale = n_scale;
+  wk->h_img.resize(n);
+  wk->h_oct.resize((size_t)n * n_oct);
+  size_t off = 0;
+  int max_w0 = 0, max_h0 = 0;
+  std::vector<BlurTile> tiles;
+  for (int i = 0; i < n; ++i) {
+    if (w[i] < 2 || h[i] < 2) { delete wk; return ctx_fail(ctx, PANO_ERR_INVALID, "sift: image too small"); }
+    ImgMeta& im = wk->h_img[i];
+    im.src = d_src[i]; im.in_w = w[i]; im.in_h = h[i];
+    // feature/feature.cc:33-34
+    float ratio = p->sift_working_size * 2.0f / (w[i] + h[i]);
+    im.h0 = (int)(h[i] * ratio); im.w0 = (int)(w[i] * ratio);
+    if (im.w0 < 8 || im.h0 < 8 || im.w0 > 8191 || im.h0 > 8191) {
+      delete wk; return ctx_fail(ctx, PANO_ERR_INVALID, "sift: working size out of range");
+    }
+    float fx = (float)im.h0 / h[i], fy = (float)im.w0 / w[i];
+    im.ifx = 1.f / fx; im.ify = 1.f / fy;
+    im.work_off = (long long)off;
+    off += align_up((size_t)im.w0 * im.h0 * 3, 32);
+    max_w0 = std::max(max_w0, im.w0); max_h0 = std::max(max_h0, im.h0);
+    for (int o = 0; o < n_oct; ++o) {
+      OctMeta& om = wk->h_oct[(size_t)i * n_oct + o];
+      om.img = i; om.oct = o;
+      if (o == 0) { om.w = im.w0; om.h = im.h0; om.ifx = om.ify = 1.f; }
+      else {  // feature/dog.cc:105-107
+        float factor = (float)pow((double)p->scale_factor, (double)-o);
+        om.w = (int)ceilf(im.w0 * factor); om.h = (int)ceilf(im.h0 * factor);
+        if (om.w <= 5 || om.h <= 5) { delete wk; return ctx_fail(ctx, PANO_ERR_INVALID, "sift: octave too small"); }
+        float ofx = (float)om.h / im.h0, ofy = (float)om.w / im.w0;
+        om.ifx = 1.f / ofx; om.ify = 1.f / ofy;
+      }
+      om.plane = (long long)align_up((size_t)om.w * om.h, 32);
+      om.gauss_off = (long long)off; off += (size_t)om.plane * n_scale;
+      om.dog_off = (long long)off; off += (size_t)om.plane * (n_scale - 1);
+      for (int ty = 0; ty < ceil_div(om.h, BT_H); ++ty)
+        for (int tx = 0; tx < ceil_div(om.w, BT_W); ++tx)
+          tiles.push_back(BlurTile{i * n_oct + o, tx, ty});
+    }
+  }
+  wk->arena_floats = off;
+  wk->n_tiles = (int)tiles.size();
+
+  GaussTable gt;
+  memset(&gt, 0, sizeof(gt));
+  gt.nlev = n_scale - 1;
+  {
+    float sigma = p->gauss_sigma;  // feature/gaussian.hh:99-102
+    for (int s = 0; s < gt.nlev; ++s) {
+      int kw = host_gauss_kernel(sigma, p->gauss_window_factor, gt.taps[s], SIFT_MAX_TAPS);
+      if (kw < 0) { delete wk; return ctx_fail(ctx, PANO_ERR_INVALID, "sift: gaussian window %d too wide", -kw); }
+      gt.center[s] = kw / 2;
+      gt.rmax = std::max(gt.rmax, kw / 2);
+      sigma *= p->scale_factor;
+    }
+  }
+
+#define SIFT_TRY(call) do { int _rc = (call); if (_rc != 0) { sift_work_free(ctx, wk); return _rc; } } while (0)
+#define SIFT_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { int _rc = ctx_cuda(ctx, _e, #call); sift_work_free(ctx, wk); return _rc; } } while (0)
+
+  const size_t ncand = (size_t)n * SIFT_CAND_CAP, ndesc = (size_t)n * SIFT_DESC_CAP;
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->arena, off * sizeof(float)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_img, n * sizeof(ImgMeta)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_oct, wk->h_oct.size() * sizeof(OctMeta)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_tiles, tiles.size() * sizeof(BlurTile)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->cand_count, n * sizeof(int)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->cand_keys, ncand * sizeof(uint32_t)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->sorted_keys, ncand * sizeof(uint32_t)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->refined, ncand * sizeof(pano_sspoint)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->kp_valid, ncand));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->npeaks, ncand * sizeof(int)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->dirs, ncand * SIFT_MAX_PEAKS * sizeof(float)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->n_refined, n * sizeof(int)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->desc_cand, ndesc * sizeof(int)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->desc_dir, ndesc * sizeof(float)));
+
+  // featureset outputs (fixed per-image capacity; compact on download)
+  fs->ctx = ctx; fs->n_images = n;
+  SIFT_TRY(ctx_alloc(ctx, (void**)&fs->d_desc, ndesc * 128 * sizeof(float)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&fs->d_coor, ndesc * 2 * sizeof(double)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&fs->d_count, n * sizeof(int)));
+  fs->base.resize(n);
+  for (int i = 0; i < n; ++i) fs->base[i] = (long long)i * SIFT_DESC_CAP;
+
+  // metadata upload through the pinned staging buffer
+  {
+    size_t b_img = n * sizeof(ImgMeta), b_oct = wk->h_oct.size() * sizeof(OctMeta), b_t = tiles.size() * sizeof(BlurTile);
+    char* st = (char*)ctx_pinned2(ctx, b_img + b_oct + b_t);
+    if (!st) { sift_work_free(ctx, wk); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned alloc failed"); }
+    memcpy(st, wk->h_img.data(), b_img);
+    memcpy(st + b_img, wk->h_oct.data(), b_oct);
+    memcpy(st + b_img + b_oct, tiles.data(), b_t);
+    SIFT_CUDA(cudaMemcpyAsync(wk->d_img, st, b_img, cudaMemcpyHostToDevice, ctx->stream));
+    SIFT_CUDA(cudaMemcpyAsync(wk->d_oct, st + b_img, b_oct, cudaMemcpyHostToDevice, ctx->stream));
+    SIFT_CUDA(cudaMemcpyAsync(wk->d_tiles, st + b_img + b_oct, b_t, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  SIFT_CUDA(cudaMemsetAsync(wk->cand_count, 0, n * sizeof(int), ctx->stream));
+
+#define SIFT_LAUNCH(name, kernel, grid, block, smem, ...)                                   \
+  do {                                                                                      \
+    ctx->launches++;                                                                        \
+    if (ctx->profiling) ctx_prof_begin(ctx, name);                                          \
+    kernel<<<(grid), (block), (smem), ctx->stream>>>(__VA_ARGS__);                          \
+    if (ctx->profiling) ctx_prof_end(ctx);                                                  \
+    SIFT_CUDA(cudaGetLastError());                                                          \
+  } while (0)
+
+  {
+    dim3 b(32, 8), g(ceil_div(max_w0, 32), ceil_div(max_h0, 8), n);
+    SIFT_LAUNCH("k_working_resize", k_working_resize, g, b, 0, wk->d_img, wk->arena);
+    dim3 g2(ceil_div(max_w0, 32), ceil_div(max_h0, 8), n * n_oct);
+    SIFT_LAUNCH("k_octave_grey", k_octave_grey, g2, b, 0, wk->d_img, wk->d_oct, wk->arena);
+  }
+  {
+    const int R = gt.rmax;
+    size_t smem = ((size_t)(BT_H + 2 * R) * (BT_W + 2 * R) + (size_t)BT_H * (BT_W + 2 * R)) * sizeof(float);
+    if (smem > 200 * 1024) { sift_work_free(ctx, wk); return ctx_fail(ctx, PANO_ERR_INVALID, "sift: blur halo too large"); }
+    if (smem > 48 * 1024)
+      SIFT_CUDA(cudaFuncSetAttribute(k_blur_dog, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SIFT_LAUNCH("k_blur_dog", k_blur_dog, wk->n_tiles, BT_THREADS, smem, wk->d_oct, wk->d_tiles, wk->arena, gt);
+  }
+  {
+    dim3 b(32, 8), g(ceil_div(max_w0 - 2, 32), ceil_div(max_h0 - 2, 8), n * n_oct);
+    SIFT_LAUNCH("k_extrema_scan", k_extrema_scan, g, b, 0, wk->d_oct, wk->arena, n_scale, p->pre_color_thres,
+                p->judge_extrema_diff_thres, wk->cand_count, wk->cand_keys);
+  }
+  {
+    dim3 g(SIFT_CAND_CAP / 256, n);
+    SIFT_LAUNCH("k_rank_sort", k_rank_sort, g, 256, 0, wk->cand_count, wk->cand_keys, wk->sorted_keys);
+    RefineParams rp{n_scale, p->calc_offset_depth, p->offset_thres, p->contrast_thres, p->edge_ratio,
+                    p->gauss_sigma, p->scale_factor};
+    dim3 g4(SIFT_CAND_CAP / 128, n);
+    SIFT_LAUNCH("k_refine", k_refine, g4, 128, 0, wk->d_oct, wk->arena, n_oct, wk->cand_count, wk->sorted_keys, rp,
+                wk->refined, wk->kp_valid);
+    dim3 g5(SIFT_CAND_CAP / ORI_WARPS, n);
+    SIFT_LAUNCH("k_orientation", k_orientation, g5, ORI_WARPS * 32, 0, wk->d_oct, wk->arena, n_oct, wk->cand_count,
+                wk->refined, wk->kp_valid, p->ori_radius, p->ori_hist_smooth_count, wk->npeaks, wk->dirs);
+    SIFT_LAUNCH("k_expand_scan", k_expand_scan, n, SCAN_THREADS, 0, wk->cand_count, wk->kp_valid, wk->npeaks,
+                wk->dirs, fs->d_count, wk->n_refined, wk->desc_cand, wk->desc_dir);
+    DescParams dp{p->desc_hist_scale_factor, p->desc_int_factor};
+    int grid = ctx->num_sms * 8;
+    SIFT_LAUNCH("k_descriptor", k_descriptor, grid, DESC_THREADS, 0, wk->d_oct, wk->d_img, wk->arena, n_oct, n,
+                wk->refined, fs->d_count, wk->desc_cand, wk->desc_dir, dp, fs->d_desc, fs->d_coor);
+  }
+  wk->n_desc = fs->d_count;
+
+  // counts to the host (pinned, async); consumers wait on counts_ready
+  if (!fs->h_count_pinned) SIFT_CUDA(cudaMallocHost((void**)&fs->h_count_pinned, (size_t)2 * n * sizeof(int)));
+  SIFT_CUDA(cudaMemcpyAsync(fs->h_count_pinned, fs->d_count, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  SIFT_CUDA(cudaMemcpyAsync(fs->h_count_pinned + n, wk->cand_count, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!fs->counts_ready) SIFT_CUDA(cudaEventCreateWithFlags(&fs->counts_ready, cudaEventDisableTiming));
+  SIFT_CUDA(cudaEventRecord(fs->counts_ready, ctx->stream));
+  fs->counts_on_host = false;
+
+  if (keep) *keep = wk;
+  else sift_work_free(ctx, wk);
+  return PANO_OK;
+}
+
+int featureset_sync_counts(pano_featureset* fs) {
+  if (fs->counts_on_host) return PANO_OK;
+  pano_ctx* ctx = fs->ctx;
+  if (fs->counts_ready) {
+    PANO_CUDA(ctx, cudaEventSynchronize(fs->counts_ready));
+    fs->h_count.assign(fs->h_count_pinned, fs->h_count_pinned + fs->n_images);
+    for (int i = 0; i < fs->n_images; ++i) {
+      if (fs->h_count_pinned[fs->n_images + i] > SIFT_CAND_CAP)
+        return ctx_fail(ctx, PANO_ERR_CAPACITY, "image %d: %d raw extrema exceed capacity %d", i,
+                        fs->h_count_pinned[fs->n_images + i], SIFT_CAND_CAP);
+      if (fs->h_count[i] > SIFT_DESC_CAP)
+        return ctx_fail(ctx, PANO_ERR_CAPACITY, "image %d: %d descriptors exceed capacity %d", i, fs->h_count[i],
+                        SIFT_DESC_CAP);
+    }
+  }
+  fs->counts_on_host = true;
+  return PANO_OK;
+}

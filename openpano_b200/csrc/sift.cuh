@@ -1,0 +1,80 @@
+// sift.cuh — host-visible structures of the batched SIFT pipeline.
+#pragma once
+#include "common.cuh"
+
+#define SIFT_MAX_OCT 8
+#define SIFT_MAX_LEVELS 8        // nscale-1 blurred levels
+#define SIFT_MAX_TAPS 32         // kw <= 31
+#define SIFT_CAND_CAP 8192       // raw extrema per image
+#define SIFT_DESC_CAP 8192       // descriptors per image
+#define SIFT_MAX_PEAKS 18        // a peak needs two lower neighbours: <= 36/2
+
+struct ImgMeta {
+  const float* src;   // input RGB (device)
+  int in_w, in_h;
+  int w0, h0;         // working size
+  float ifx, ify;     // 1/fx (rows), 1/fy (cols) of the working resize
+  long long work_off; // working RGB offset in the arena (floats)
+};
+
+struct OctMeta {
+  int img, oct;
+  int w, h;
+  float ifx, ify;       // octave resize from the working image (oct > 0)
+  long long gauss_off;  // nscale planes: grey + blurred levels
+  long long dog_off;    // nscale-1 planes
+  long long plane;      // floats per plane (padded to 32)
+};
+
+struct BlurTile { int om; int tx, ty; };
+
+struct GaussTable {
+  int nlev;
+  int rmax;
+  int center[SIFT_MAX_LEVELS];
+  float taps[SIFT_MAX_LEVELS][SIFT_MAX_TAPS];
+};
+
+// All device state of one batched SIFT run.  Kept alive by pano_sift_trace for
+// stage inspection; freed right after the run otherwise.
+struct SiftWork {
+  int n_img = 0, n_oct = 0, n_scale = 0;
+  std::vector<ImgMeta> h_img;
+  std::vector<OctMeta> h_oct;     // n_img * n_oct
+  float* arena = nullptr;
+  size_t arena_floats = 0;
+  ImgMeta* d_img = nullptr;
+  OctMeta* d_oct = nullptr;
+  BlurTile* d_tiles = nullptr;
+  int n_tiles = 0;
+  // keypoint state, all [n_img * SIFT_CAND_CAP] unless noted
+  int* cand_count = nullptr;      // [n_img]
+  uint32_t* cand_keys = nullptr;
+  uint32_t* sorted_keys = nullptr;
+  pano_sspoint* refined = nullptr;  // valid flag in .dir < 0 ? no: see kp_valid
+  unsigned char* kp_valid = nullptr;
+  int* npeaks = nullptr;
+  float* dirs = nullptr;            // [n_img * CAP * SIFT_MAX_PEAKS]
+  int* n_desc = nullptr;            // [n_img]
+  int* n_refined = nullptr;         // [n_img] (for traces)
+  int* desc_cand = nullptr;         // [n_img * DESC_CAP] candidate index of descriptor
+  float* desc_dir = nullptr;        // [n_img * DESC_CAP]
+};
+
+struct pano_featureset {
+  pano_ctx* ctx = nullptr;
+  int n_images = 0;
+  float* d_desc = nullptr;    // rows of 128 f32
+  double* d_coor = nullptr;   // rows of 2 f64 (may be null for uploaded sets)
+  int* d_count = nullptr;     // [n_images]
+  std::vector<long long> base;  // first row of image i
+  std::vector<int> h_count;
+  bool counts_on_host = false;
+  cudaEvent_t counts_ready = nullptr;
+  int* h_count_pinned = nullptr;
+};
+
+int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w, const int* h,
+                   const pano_params* p, pano_featureset* fs, SiftWork** keep);
+void sift_work_free(pano_ctx* ctx, SiftWork* wk);
+int featureset_sync_counts(pano_featureset* fs);

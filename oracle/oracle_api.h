@@ -43,6 +43,16 @@ extern "C" {
                     double* kpts_xy, int n_kpts);                                      \
   int  P##_blend(int n, const pano_blend_image* imgs, const pano_blend_geom* g,        \
                  int bands, const pano_params* p, float* out_hwc, int out_w, int out_h);\
+  /* One pass of the whole hot path as Stitcher::build() drives it (stitcher.cc:32-64  \
+   * minus geometry): calc_feature over n images, n_pairs matches (use_flann: the      \
+   * PairWiseMatcher kd-forest path the reference really runs; else the exact         \
+   * FeatureMatcher), then the blender.  n_feat[n], n_match[n_pairs], seconds[3]       \
+   * (features, match, blend wall time) are outputs. */                               \
+  int  P##_hotpath(int n, const float* const* rgb_hwc, const int* w, const int* h,     \
+                   int n_pairs, const int* image_ij, int use_flann,                    \
+                   const pano_blend_image* bimgs, const pano_blend_geom* g, int bands, \
+                   const pano_params* p, float* out_hwc, int out_w, int out_h,         \
+                   int* n_feat, int* n_match, double* seconds);                        \
   /* number of host threads the library will use (1 for the scalar port) */            \
   int  P##_num_threads(void);
 

@@ -214,3 +214,37 @@ int orc_blend(int n, const pano_blend_image* imgs, const pano_blend_geom* g, int
   if (bands > 0) return multiband_blend(n, imgs, g, bands, P, out, tw, th);
   return linear_blend(n, imgs, g, P, out, tw, th);
 }
+
+#include <time.h> /* clock_gettime: built with -std=gnu11 */
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
+
+/* One pass of the hot path with the restated stages, single thread (see
+ * oracle_api.h).  use_flann is ignored: the port only has the exact matcher. */
+int orc_hotpath(int n, const float* const* rgb, const int* w, const int* h, int n_pairs, const int* ij,
+                int use_flann, const pano_blend_image* bimgs, const pano_blend_geom* g, int bands,
+                const pano_params* P, float* out, int ow, int oh, int* n_feat, int* n_match, double* seconds) {
+  float** desc = (float**)calloc((size_t)n, sizeof(float*));
+  double t = now_s();
+  int k, rc = 0;
+  const int cap = 65536;
+  (void)use_flann;
+  for (k = 0; k < n; ++k) {
+    desc[k] = (float*)malloc(sizeof(float) * 128 * (size_t)cap);
+    n_feat[k] = orc_sift_detect(rgb[k], w[k], h[k], P, cap, NULL, desc[k]);
+    if (n_feat[k] <= 0) rc = -5;
+  }
+  seconds[0] = now_s() - t; t = now_s();
+  for (k = 0; k < n_pairs && !rc; ++k) {
+    int a = ij[2 * k], b = ij[2 * k + 1];
+    int mn = n_feat[a] < n_feat[b] ? n_feat[a] : n_feat[b];
+    int* pairs = (int*)malloc(sizeof(int) * 2 * (size_t)(mn + 1));
+    orc_match(desc[a], n_feat[a], desc[b], n_feat[b], P, pairs, &n_match[k]);
+    free(pairs);
+  }
+  seconds[1] = now_s() - t; t = now_s();
+  if (!rc) rc = orc_blend(n, bimgs, g, bands, P, out, ow, oh);
+  seconds[2] = now_s() - t;
+  for (k = 0; k < n; ++k) free(desc[k]);
+  free(desc);
+  return rc;
+}

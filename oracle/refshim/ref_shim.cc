@@ -17,6 +17,7 @@
 #endif
 
 #include "lib/config.hh"
+#include "lib/timer.hh"
 #include "lib/mat.h"
 #include "lib/imgproc.hh"
 #include "feature/feature.hh"
@@ -296,6 +297,45 @@ int ref_blend(int n, const pano_blend_image* imgs, const pano_blend_geom* g, int
   if (res.width() != ow || res.height() != oh) return -1;
   memcpy(out, res.ptr(), sizeof(float) * (size_t)ow * oh * 3);
   return 0;
+}
+
+
+// The hot path as Stitcher::build() drives it: calc_feature (stitcherbase.cc:9-27,
+// omp over images), linear/pairwise match (stitcher.cc:96-136, omp over pairs, the
+// FLANN PairWiseMatcher unless use_flann == 0), ConnectedImages::blend's blender
+// (stitcher_image.cc:132-154).  RANSAC / camera estimation are host geometry
+// outside the hot path and are replaced by caller-supplied homographies.
+int ref_hotpath(int n, const float* const* rgb, const int* w, const int* h, int n_pairs, const int* ij,
+                int use_flann, const pano_blend_image* bimgs, const pano_blend_geom* g, int bands,
+                const pano_params* p, float* out, int ow, int oh, int* n_feat, int* n_match, double* seconds) {
+  apply_params(p);
+  Timer t0;
+  std::vector<std::vector<Descriptor>> feats(n);
+  std::unique_ptr<FeatureDetector> feature_det(new SIFTDetector);
+#pragma omp parallel for schedule(dynamic)
+  for (int k = 0; k < n; ++k) {
+    Mat32f img = wrap_rgb(rgb[k], w[k], h[k]);
+    feats[k] = feature_det->detect_feature(img);
+  }
+  for (int k = 0; k < n; ++k) { n_feat[k] = (int)feats[k].size(); if (!n_feat[k]) return -5; }
+  seconds[0] = t0.duration();
+  Timer t1;
+  if (use_flann) {
+    PairWiseMatcher pwmatcher(feats);
+#pragma omp parallel for schedule(dynamic)
+    for (int k = 0; k < n_pairs; ++k) n_match[k] = pwmatcher.match(ij[2 * k], ij[2 * k + 1]).size();
+  } else {
+    // FeatureMatcher parallelises internally (matcher.cc:32)
+    for (int k = 0; k < n_pairs; ++k) {
+      FeatureMatcher fm(feats[ij[2 * k]], feats[ij[2 * k + 1]]);
+      n_match[k] = fm.match().size();
+    }
+  }
+  seconds[1] = t1.duration();
+  Timer t2;
+  int rc = ref_blend(n, bimgs, g, bands, p, out, ow, oh);
+  seconds[2] = t2.duration();
+  return rc;
 }
 
 }  // extern "C"

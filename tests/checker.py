@@ -146,6 +146,9 @@ class Checker:
                                    C.c_int, C.c_int, _dp, C.c_int]
         fn("blend").argtypes = [C.c_int, C.POINTER(PanoBlendImage), C.POINTER(PanoBlendGeom),
                                 C.c_int, C.POINTER(PanoParams), _fp, C.c_int, C.c_int]
+        fn("hotpath").argtypes = [C.c_int, C.POINTER(C.c_void_p), _ip, _ip, C.c_int, _ip, C.c_int,
+                                  C.POINTER(PanoBlendImage), C.POINTER(PanoBlendGeom), C.c_int,
+                                  C.POINTER(PanoParams), _fp, C.c_int, C.c_int, _ip, _ip, _dp]
         fn("num_threads").restype = C.c_int
         self._fn = fn
 
@@ -197,6 +200,28 @@ class Checker:
                                   _f(out), ow, oh, _d(k), len(k))
         assert rc == 0
         return out, k
+
+    def hotpath(self, imgs, pairs, items, geom, bands=0, params=None, use_flann=True):
+        """One CPU pass of SIFT + match + blend. Returns (n_feat, n_match, mosaic, seconds[3])."""
+        params = params or default_params()
+        imgs = [np.ascontiguousarray(im, np.float32) for im in imgs]
+        n = len(imgs)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        ws = (C.c_int * n)(*[im.shape[1] for im in imgs])
+        hs = (C.c_int * n)(*[im.shape[0] for im in imgs])
+        pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        arr = make_blend_images(imgs, items)
+        g = make_geom(geom)
+        ow, oh = blend_target_size(items)
+        out = np.empty((oh, ow, 3), np.float32)
+        n_feat = np.zeros(n, np.int32)
+        n_match = np.zeros(max(len(pairs), 1), np.int32)
+        secs = np.zeros(3, np.float64)
+        rc = self._fn("hotpath")(n, ptrs, ws, hs, len(pairs), _i(pairs), 1 if use_flann else 0, arr,
+                                 C.byref(g), bands, C.byref(params), _f(out), ow, oh, _i(n_feat),
+                                 _i(n_match), _d(secs))
+        assert rc == 0, rc
+        return n_feat, n_match[:len(pairs)], out, secs
 
     def blend(self, imgs, items, geom, bands=0, params=None):
         params = params or default_params()

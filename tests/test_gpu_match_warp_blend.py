@@ -1,0 +1,126 @@
+"""GPU parity of matching, cylinder warp and both blenders against the oracle."""
+import numpy as np
+import pytest
+
+from openpano_b200 import synth
+from openpano_b200._abi import default_params
+
+pytestmark = pytest.mark.gpu
+
+
+def test_match_pairs_bit_exact(engine, orc):
+    imgs, _ = synth.make_stack(4, 480, 360, 160, 41)
+    fs = engine.sift_detect_batch(imgs)
+    descs = [fs.download(i)[1] for i in range(4)]
+    pairs = [(0, 1), (1, 0), (1, 2), (2, 3), (0, 3), (3, 1)]
+    got = engine.match_pairs(fs, pairs)
+    for (i, j), m in zip(pairs, got):
+        want = orc.match(descs[i], descs[j])
+        assert np.array_equal(m, want), (i, j, len(m), len(want))
+    assert sum(len(m) for m in got) > 100
+    assert engine.match_pairs_dev(fs, pairs) == sum(len(m) for m in got)
+    fs.free()
+
+
+@pytest.mark.parametrize("n,m,noise", [(700, 600, 6.0), (600, 700, 25.0), (257, 1000, 40.0), (64, 64, 60.0), (1, 5, 1.0), (5, 1, 1.0)])
+def test_match_bruteforce_near_threshold(engine, orc, n, m, noise):
+    rng = np.random.RandomState(n + m)
+    a = synth.rootsift_like(max(n, m), 4)
+    b = a[rng.permutation(len(a))][:m] + rng.randn(m, 128).astype(np.float32) * noise
+    a = a[:n]
+    got = engine.match_bruteforce(a, b)
+    want = orc.match(a, b)
+    assert np.array_equal(got, want), (len(got), len(want))
+
+
+def test_match_duplicates_and_ties(engine, orc):
+    a = synth.rootsift_like(300, 5)
+    b = np.concatenate([a[:100], a[:100], a[200:]])  # exact duplicates -> zero-distance ties
+    assert np.array_equal(engine.match_bruteforce(a, b), orc.match(a, b))
+    assert np.array_equal(engine.match_bruteforce(b, a), orc.match(b, a))
+
+
+def test_match_empty(engine):
+    a = synth.rootsift_like(10, 6)
+    assert len(engine.match_bruteforce(a, np.zeros((0, 128), np.float32))) == 0
+
+
+@pytest.mark.parametrize("w,h,hf", [(600, 400, 1.0), (300, 200, 0.85), (257, 311, 1.2)])
+def test_cyl_warp_bit_exact(engine, orc, w, h, hf):
+    img = synth.make_canvas(h, w, 51)
+    k = np.array([[10.5, -20.25], [-100.0, 50.0], [0.0, 0.0]])
+    assert engine.cyl_warp_shape(w, h, hf) == orc.cyl_warp_shape(w, h, hf)
+    ga, gk = engine.cyl_warp(img, k, hf)
+    oa, ok = orc.cyl_warp(img, k, hf)
+    assert np.array_equal(gk, ok)
+    assert ga.shape == oa.shape
+    assert np.array_equal(ga.view(np.uint32), oa.view(np.uint32)), np.abs(ga - oa).max()
+
+
+def _perspective_items(org, n, projection):
+    import math
+    items = []
+    for k, (x, y) in enumerate(org):
+        if projection == 0:
+            th = 0.002 * (k - 1.5)
+            H = np.array([[math.cos(th), -math.sin(th), x - 150], [math.sin(th), math.cos(th), 3 * k],
+                          [1e-5 * k, -2e-5, 1.0]])
+        else:
+            f = 500.0
+            H = np.array([[1 / f, 0, (x - 150) / f], [0, 1 / f, 0.004 * k], [0, 0, 1]])
+        Hi = np.linalg.inv(H)
+        items.append((k * 100, 0, k * 100 + 300, 210, list(Hi.ravel())))
+    res = 1.0 if projection == 0 else 1 / 500.0
+    pmin = (-150.0, -100.0) if projection == 0 else (-0.35, -0.22)
+    g = dict(projection=projection, res_x=res, res_y=res, proj_min_x=pmin[0], proj_min_y=pmin[1])
+    return items, g
+
+
+@pytest.mark.parametrize("lazy,ordered", [(1, 0), (1, 1), (0, 0), (0, 1)])
+def test_linear_blend_bit_exact(engine, orc, lazy, ordered):
+    imgs, org = synth.make_stack(4, 300, 200, 100, 7)
+    items, geom = synth.translation_blend_setup(org, 300, 200)
+    p = default_params(lazy_read=lazy, ordered_input=ordered)
+    a = engine.blend(imgs, items, geom, 0, p)
+    b = orc.blend(imgs, items, geom, 0, p)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), np.abs(a - b).max()
+
+
+@pytest.mark.parametrize("bands", [1, 2, 5])
+def test_multiband_blend_bit_exact(engine, orc, bands):
+    imgs, org = synth.make_stack(4, 300, 200, 100, 7)
+    items, geom = synth.translation_blend_setup(org, 300, 200)
+    a = engine.blend(imgs, items, geom, bands)
+    b = orc.blend(imgs, items, geom, bands)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), np.abs(a - b).max()
+
+
+@pytest.mark.parametrize("projection", [0, 1, 2])
+@pytest.mark.parametrize("bands", [0, 3])
+def test_blend_projections_bit_exact(engine, orc, projection, bands):
+    imgs, org = synth.make_stack(4, 300, 200, 100, 7)
+    items, geom = _perspective_items(org, 4, projection)
+    a = engine.blend(imgs, items, geom, bands)
+    b = orc.blend(imgs, items, geom, bands)
+    assert (a < 0).mean() < 0.9
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), np.abs(a - b).max()
+
+
+def test_blend_full_size_properties(engine):
+    """At a BASELINE shape (1500x1112 crops) the composite of crops of ONE canvas
+    must reproduce that canvas where covered: linear blend of identical content is
+    the content itself (weights cancel) up to float rounding."""
+    imgs, org = synth.config_stack("ordered_13x1500x1112", n=3)
+    items, geom = synth.translation_blend_setup(org, 1500, 1112)
+    out = engine.blend(imgs, items, geom, 0)
+    canvas = synth.make_canvas(1112, 1500 + 500 * 2, 2)[:out.shape[0], :out.shape[1]]
+    covered = out[..., 0] >= 0
+    assert covered.mean() > 0.95
+    assert np.abs(out[covered] - canvas[covered]).max() < 1e-5
+    mb = engine.blend(imgs, items, geom, 5)
+    cov2 = mb[..., 0] >= 0
+    # multiband blurs ROI-border black into the bands (reference behaviour), so only
+    # the bulk statistics are a property: range, coverage, small mean error
+    assert np.array_equal(cov2, covered)
+    assert mb[cov2].min() >= 0.0 and mb[cov2].max() <= 1.0
+    assert np.abs(mb[cov2] - canvas[cov2]).mean() < 5e-3
