@@ -99,7 +99,13 @@ __constant__ uint64_t c_exp2f_tab[32] = {
     0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
     0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
 
-__device__ __forceinline__ float glibc_expf(float x) {
+// `tab` is a 32-entry copy of c_exp2f_tab in shared memory (see load_exp2f_tab):
+// lanes index it with different k, which constant memory would serialise.
+__device__ __forceinline__ void load_exp2f_tab(uint64_t* s_tab, int tid) {
+  if (tid < 32) s_tab[tid] = c_exp2f_tab[tid];
+}
+
+__device__ __forceinline__ float glibc_expf(float x, const uint64_t* __restrict__ tab) {
   // special ranges of the libm routine (|x| >= 88): only the underflow side can
   // occur here (arguments are -(d^2)/denom <= 0).
   if (x < -0x1.9fe368p6f) return 0.0f;
@@ -112,7 +118,7 @@ __device__ __forceinline__ float glibc_expf(float x) {
   uint64_t ki = (uint64_t)__double_as_longlong(kd);
   kd -= SHIFT;
   double r = z - kd;
-  uint64_t t = c_exp2f_tab[ki & 31];
+  uint64_t t = tab[ki & 31];
   t += ki << 47;
   double s = __longlong_as_double((long long)t);
   z = C0 * r + C1;

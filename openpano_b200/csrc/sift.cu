@@ -142,6 +142,105 @@ k_blur_dog(const OctMeta* __restrict__ octs, const BlurTile* __restrict__ tiles,
   }
 }
 
+// Fast path for the window half-widths the reference's defaults produce (kw = 7
+// and 13): both passes keep a sliding window in registers so one
+// shared-memory load feeds up to 2C+1 taps, 8 outputs per thread per pass.
+//   column pass: lane <-> column, thread = 8 consecutive rows
+//   row pass   : lane <-> row (odd row stride => conflict-free), thread = 8
+//                consecutive columns, results staged transposed-safe in `outT`
+//   store      : lane <-> column, coalesced level + |DoG| writes
+// The arithmetic per output is unchanged: tmp = 0; tmp += v[k] * tap[k], k ascending.
+template <int C>
+__device__ __forceinline__ void blur_level(const float* __restrict__ grey, float* __restrict__ colbuf,
+                                           float* __restrict__ outT, const float* __restrict__ taps_g,
+                                           int R, int GW, int CS, int tid) {
+  constexpr int KW = 2 * C + 1;
+  float tap[KW];
+#pragma unroll
+  for (int k = 0; k < KW; ++k) tap[k] = taps_g[k];
+  const int cw = BT_W + 2 * C;
+  // column pass: items = (BT_H/8 row strips) x cw columns
+  for (int item = tid; item < (BT_H / 8) * cw; item += BT_THREADS) {
+    const int strip = item / cw, xx = item - strip * cw;
+    const float* col = grey + (strip * 8 + R - C) * GW + (xx + R - C);
+    float win[8 + 2 * C];
+#pragma unroll
+    for (int j = 0; j < 8 + 2 * C; ++j) win[j] = col[j * GW];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float tmp = 0.f;
+#pragma unroll
+      for (int k = 0; k < KW; ++k) tmp += win[r + k] * tap[k];
+      colbuf[(strip * 8 + r) * CS + xx] = tmp;
+    }
+  }
+  __syncthreads();
+  // row pass: warp <-> 8-column strip, lane <-> row
+  {
+    const int lane = tid & 31, xs = (tid >> 5) * 8;
+    const float* row = colbuf + lane * CS + xs;
+    float win[8 + 2 * C];
+#pragma unroll
+    for (int j = 0; j < 8 + 2 * C; ++j) win[j] = row[j];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float tmp = 0.f;
+#pragma unroll
+      for (int k = 0; k < KW; ++k) tmp += win[r + k] * tap[k];
+      outT[lane * (BT_W + 1) + xs + r] = tmp;
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(BT_THREADS)
+k_blur_dog_fast(const OctMeta* __restrict__ octs, const BlurTile* __restrict__ tiles,
+                float* __restrict__ arena, const __grid_constant__ GaussTable gt) {
+  extern __shared__ float smem[];
+  const BlurTile tl = tiles[blockIdx.x];
+  const OctMeta om = octs[tl.om];
+  const int R = gt.rmax;
+  const int GW = BT_W + 2 * R, GH = BT_H + 2 * R;
+  const int CS = GW | 1;                 // odd stride: row-pass lanes (rows) hit distinct banks
+  float* grey = smem;                    // [GH][GW]
+  float* colbuf = grey + GH * GW;        // [BT_H][CS]
+  float* outT = colbuf + BT_H * CS;      // [BT_H][BT_W+1]
+  const int x0 = tl.tx * BT_W, y0 = tl.ty * BT_H;
+  const float* g0 = arena + om.gauss_off;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < GH * GW; i += BT_THREADS) {
+    int yy = i / GW, xx = i - yy * GW;
+    int gy = min(max(y0 + yy - R, 0), om.h - 1);
+    int gx = min(max(x0 + xx - R, 0), om.w - 1);
+    grey[i] = __ldg(g0 + (size_t)gy * om.w + gx);
+  }
+  __syncthreads();
+  const int tx = tid & (BT_W - 1), ty = tid / BT_W;   // 64 x 4
+  const int gx = x0 + tx;
+  float prev[BT_H / 4];
+#pragma unroll
+  for (int i = 0; i < BT_H / 4; ++i) prev[i] = grey[(ty + 4 * i + R) * GW + tx + R];
+  for (int s = 0; s < gt.nlev; ++s) {
+    if (gt.center[s] == 3) blur_level<3>(grey, colbuf, outT, gt.taps[s], R, GW, CS, tid);
+    else blur_level<6>(grey, colbuf, outT, gt.taps[s], R, GW, CS, tid);
+    float* lvl = arena + om.gauss_off + (size_t)(s + 1) * om.plane;
+    float* dog = arena + om.dog_off + (size_t)s * om.plane;
+#pragma unroll
+    for (int i = 0; i < BT_H / 4; ++i) {
+      const int y = ty + 4 * i, gy = y0 + y;
+      const float v = outT[y * (BT_W + 1) + tx];
+      if (gx < om.w && gy < om.h) {
+        size_t o = (size_t)gy * om.w + gx;
+        lvl[o] = v;
+        dog[o] = fabsf(prev[i] - v);
+      }
+      prev[i] = v;
+    }
+    // no barrier needed here: the next level's column pass touches only grey/colbuf
+    // and its row pass (which rewrites outT) sits behind that pass's barrier
+  }
+}
+
 // ============================================================ K3 extrema scan
 // feature/extrema.cc:170-216.  Candidates are appended unordered (one atomic per
 // hit) with a key that encodes the canonical order octave -> scale -> raster.
@@ -401,6 +500,9 @@ k_orientation(const OctMeta* __restrict__ octs, const float* __restrict__ arena,
   __shared__ signed char s_bin[ORI_WARPS][ORI_CHUNK];
   __shared__ float s_val[ORI_WARPS][ORI_CHUNK];
   __shared__ float s_hist[ORI_WARPS][ORI_BINS + 4];
+  __shared__ uint64_t s_exptab[32];
+  load_exp2f_tab(s_exptab, threadIdx.x);
+  __syncthreads();
   const int img = blockIdx.y;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * ORI_WARPS + wid;
@@ -433,7 +535,7 @@ k_orientation(const OctMeta* __restrict__ octs, const float* __restrict__ arena,
           mag_ort_at(lvl, om.w, newx, newy, &mag, &ort);
           int b = (int)roundf((float)ORI_BINS * halfipi * ort);
           if (b == ORI_BINS) b = 0;
-          float weight = glibc_expf(-d2 / exp_denom);
+          float weight = glibc_expf(-d2 / exp_denom, s_exptab);
           bin = (signed char)b;
           val = weight * mag;
         }
@@ -555,17 +657,34 @@ k_expand_scan(const int* __restrict__ cand_count, const unsigned char* __restric
 
 // ============================================================ K6 descriptor
 // feature/sift.cc:87-152 calc_descriptor, :48-67 trilinear_interpolate, :15-46
-// hist_to_descriptor (RootSIFT).  One 128-thread block per oriented keypoint,
-// thread t owns histogram bin t.  Phase 1 evaluates every window position in
-// parallel into shared-memory records; phase 2 lets each bin replay, in the
-// reference's scan order, only the positions inside the bounding box of its
-// 2x2-cell footprint, so every bin's float sum is bit-identical to the serial
-// loop without 128 threads scanning the whole window.
-#define DESC_THREADS 128
-#define DESC_REC_CAP 1600
+// hist_to_descriptor (RootSIFT).  ONE WARP per oriented keypoint.  Every bin's
+// float sum must run in the reference's scan order (xx outer, yy inner):
+//   A  lanes test 32 window positions at a time against a cheap conservative
+//      bound; survivors are compacted IN ORDER (ballot + popc) into a staging
+//      ring;
+//   B  each full group of 32 survivors gets the exact test and the heavy math
+//      (mag/ort from the blurred level, glibc expf) -> shared-memory records, and
+//      one ballot word per spatial cell says which of the 32 records touch it;
+//   D  lane = (cell, role): the two lanes of a cell walk the set bits of that
+//      cell's words — ascending bit order is the scan order — and add the
+//      record's two orientation contributions (bins hbinf and hbinf+1) to
+//      shared-memory accumulators.  Different cells never share a bin, so the 16
+//      lane pairs advance independently and nearly every lane does useful work.
+#define DESC_WARPS 4
+#define DESC_THREADS (DESC_WARPS * 32)
+#define DESC_REC_CAP 640                 // records per flush; more simply flushes twice
+#define DESC_CHUNKS (DESC_REC_CAP / 32)
 #define DESC_SKIP 0xffffffffu
 
 struct DescParams { int hist_scale_factor; int int_factor; };
+
+struct __align__(16) DescWarpSmem {
+  float r_w[DESC_REC_CAP], r_yd[DESC_REC_CAP], r_xd[DESC_REC_CAP], r_hd[DESC_REC_CAP];
+  uint32_t r_pk[DESC_REC_CAP];
+  uint32_t mask[16][DESC_CHUNKS];
+  uint32_t stage[64];                    // packed (xx+128)<<8 | (yy+128), in scan order
+  float acc[128];
+};
 
 __global__ void __launch_bounds__(DESC_THREADS)
 k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
@@ -573,17 +692,22 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
              const pano_sspoint* __restrict__ pts, const int* __restrict__ n_desc,
              const int* __restrict__ desc_cand, const float* __restrict__ desc_dir,
              DescParams dp, float* __restrict__ out_desc, double* __restrict__ out_coor) {
-  __shared__ float r_w[DESC_REC_CAP], r_yd[DESC_REC_CAP], r_xd[DESC_REC_CAP], r_hd[DESC_REC_CAP];
-  __shared__ uint32_t r_pk[DESC_REC_CAP];
-  __shared__ float s_hist[128];
-  __shared__ float s_sum;
-  const int tid = threadIdx.x;
+  extern __shared__ __align__(16) unsigned char desc_smem_raw[];
+  __shared__ uint64_t s_exptab[32];
+  load_exp2f_tab(s_exptab, threadIdx.x);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  DescWarpSmem& S = reinterpret_cast<DescWarpSmem*>(desc_smem_raw)[wid];
   const float pi2 = (float)(2 * PANO_PI);
   const float nbin_per_rad = 8 / pi2;
+  const int cell = lane >> 1, role = lane & 1, by = cell >> 2, bx = cell & 3;
+  const unsigned pair_mask = 3u << (lane & ~1);
+  const int warp_global = blockIdx.x * DESC_WARPS + wid, warp_stride = gridDim.x * DESC_WARPS;
+
   for (int img = 0; img < n_img; ++img) {
     const int nd = min(n_desc[img], SIFT_DESC_CAP);
     const ImgMeta im = imgs[img];
-    for (int d = blockIdx.x; d < nd; d += gridDim.x) {
+    for (int d = warp_global; d < nd; d += warp_stride) {
       const size_t dslot = (size_t)img * SIFT_DESC_CAP + d;
       const pano_sspoint p = pts[(size_t)img * SIFT_CAND_CAP + desc_cand[dslot]];
       const float ort = desc_dir[dslot];
@@ -596,108 +720,147 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
       float sinort, cosort;
       glibc_sincosf(ort, &sinort, &cosort);
       const int side = 2 * radius + 1;
-      const int cols_per_chunk = max(1, DESC_REC_CAP / side);
-
-      // this thread's bin and its bounding box in window offsets
-      const int cell = tid >> 3, bh = tid & 7, by = cell >> 2, bx = cell & 3;
-      int bx_lo, bx_hi, by_lo, by_hi;
-      {
-        // cell footprint in rotated bin units: x_rot in [bx-2.5, bx-0.5), same for y
-        float xr0 = (float)bx - 2.5f, xr1 = (float)bx - 0.5f;
-        float yr0 = (float)by - 2.5f, yr1 = (float)by - 0.5f;
-        float xmin = 1e30f, xmax = -1e30f, ymin = 1e30f, ymax = -1e30f;
+      // conservative bounds on the un-normalised rotated coordinates:
+      // bin in [-1,3]  <=>  rot in [-2.5, 1.5] * hist_w (the exact test is in phase B)
+      const float lo = -2.5f * hist_w - 0.02f * hist_w - 1e-3f, hi = 1.5f * hist_w + 0.02f * hist_w + 1e-3f;
+      const float fr2 = (float)radius * (float)radius;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float xr = (q & 1) ? xr1 : xr0, yr = (q & 2) ? yr1 : yr0;
-          float px = hist_w * (xr * cosort - yr * sinort);
-          float py = hist_w * (xr * sinort + yr * cosort);
-          xmin = fminf(xmin, px); xmax = fmaxf(xmax, px);
-          ymin = fminf(ymin, py); ymax = fmaxf(ymax, py);
-        }
-        bx_lo = max(-radius, (int)floorf(xmin) - 2); bx_hi = min(radius, (int)ceilf(xmax) + 2);
-        by_lo = max(-radius, (int)floorf(ymin) - 2); by_hi = min(radius, (int)ceilf(ymax) + 2);
-      }
-      float acc = 0.f;
+      for (int q = 0; q < 4; ++q) S.acc[lane + 32 * q] = 0.f;
+      __syncwarp();
 
-      for (int cx0 = -radius; cx0 <= radius; cx0 += cols_per_chunk) {
-        const int cx1 = min(radius, cx0 + cols_per_chunk - 1);
-        const int nrec = (cx1 - cx0 + 1) * side;
-        // phase 1
-        for (int t = tid; t < nrec; t += DESC_THREADS) {
-          int xx = cx0 + t / side, yy = t % side - radius;
-          int nowx = p.x + xx, nowy = p.y + yy;
-          uint32_t pk = DESC_SKIP;
-          float wgt = 0.f, ybind = 0.f, xbind = 0.f, hbind = 0.f;
+      int nstage = 0;   // survivors waiting in S.stage (warp-uniform)
+      int nrec = 0;     // records in S.r_* (warp-uniform, multiple of 32 except after the tail)
+
+      // phase D for the current record set, then reset it
+      auto flush_records = [&]() {
+        const int nchunk = (nrec + 31) >> 5;
+        __syncwarp();
+        volatile float* acc = S.acc;
+        int ci = 0;
+        uint32_t word = nchunk > 0 ? S.mask[cell][0] : 0u;
+        while (true) {
+          while (word == 0u && ++ci < nchunk) word = S.mask[cell][ci];
+          if (ci >= nchunk) break;
+          const int b = __ffs(word) - 1;
+          word &= word - 1;
+          const int t = ci * 32 + b;
+          const uint32_t pk = S.r_pk[t];
+          const int hbinf = (int)(pk >> 16);
+          const int dy = by - ((int)(pk & 0xff) - 2);
+          const int dx = bx - ((int)((pk >> 8) & 0xff) - 2);
+          const float yd = S.r_yd[t], xd = S.r_xd[t], hd = S.r_hd[t];
+          const float w_y = S.r_w[t] * (dy ? yd : 1 - yd);
+          const float w_x = w_y * (dx ? xd : 1 - xd);
+          const float v = w_x * (role ? hd : 1 - hd);
+          const int bin = cell * 8 + ((hbinf + role) & 7);
+          __syncwarp(pair_mask);          // the pair's previous read-modify-write is complete
+          acc[bin] = acc[bin] + v;
+        }
+        __syncwarp();
+        nrec = 0;
+      };
+
+      // phase B on the first 32 staged survivors (or the tail when final)
+      auto consume_stage = [&](int count) {
+        uint32_t pk = DESC_SKIP;
+        float wgt = 0.f, ybind = 0.f, xbind = 0.f, hbind = 0.f;
+        int ybinf = -100, xbinf = -100;
+        if (lane < count) {
+          const uint32_t packed = S.stage[lane];
+          const int xx = (int)(packed >> 8) - 128, yy = (int)(packed & 0xff) - 128;
+          const float fx = (float)xx, fy = (float)yy;
+          const float y_rot = ((float)(-xx) * sinort + fy * cosort) / hist_w;
+          const float x_rot = (fx * cosort + fy * sinort) / hist_w;
+          const float ybin = (float)((double)(y_rot + 2.f) - 0.5);
+          const float xbin = (float)((double)(x_rot + 2.f) - 0.5);
+          if (ybin >= -1.f && ybin <= 3.f && xbin >= -1.f && xbin <= 3.f) {
+            float now_mag, now_ort;
+            mag_ort_at(lvl, w, p.x + xx, p.y + yy, &now_mag, &now_ort);
+            float weight = glibc_expf(-(x_rot * x_rot + y_rot * y_rot) / exp_denom, s_exptab);
+            weight = weight * now_mag;
+            now_ort -= ort;
+            if (now_ort < 0) now_ort += pi2;
+            if (now_ort > pi2) now_ort -= pi2;
+            const float hbin = now_ort * nbin_per_rad;
+            ybinf = (int)floorf(ybin); xbinf = (int)floorf(xbin);
+            const int hbinf = (int)floorf(hbin);
+            ybind = ybin - (float)ybinf;
+            xbind = xbin - (float)xbinf;
+            hbind = hbin - (float)hbinf;
+            wgt = weight;
+            pk = (uint32_t)(ybinf + 2) | ((uint32_t)(xbinf + 2) << 8) | ((uint32_t)hbinf << 16);
+          }
+        }
+        const int t = nrec + lane;
+        S.r_pk[t] = pk; S.r_w[t] = wgt; S.r_yd[t] = ybind; S.r_xd[t] = xbind; S.r_hd[t] = hbind;
+        const int ci = nrec >> 5;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int cy = c >> 2, cxx = c & 3;
+          const bool touch = (unsigned)(cy - ybinf) <= 1u && (unsigned)(cxx - xbinf) <= 1u;
+          const unsigned m = __ballot_sync(0xffffffffu, touch);
+          if (lane == 0) S.mask[c][ci] = m;
+        }
+        nrec += 32;
+        // shift the ring: survivors 32.. move to the front
+        __syncwarp();
+        const uint32_t carry = S.stage[32 + lane];
+        __syncwarp();
+        S.stage[lane] = carry;
+        nstage = max(nstage - 32, 0);
+        __syncwarp();
+        if (nrec == DESC_REC_CAP) flush_records();
+      };
+
+      // ---- phase A: ordered compaction of candidate positions
+      const int npos = side * side;
+      int xx = -radius, yy = -radius + lane;      // position = base + lane, kept as (xx, yy)
+      while (yy > radius) { yy -= side; ++xx; }
+      for (int base = 0; base < npos; base += 32) {
+        bool keep = false;
+        uint32_t packed = 0;
+        if (base + lane < npos) {
+          const int nowx = p.x + xx, nowy = p.y + yy;
           if (DBETWEEN(nowx, 1, w - 1) && DBETWEEN(nowy, 1, h - 1)) {
-            float fx = (float)xx, fy = (float)yy, fr = (float)radius;
-            if (!(fx * fx + fy * fy > fr * fr)) {
-              float y_rot = ((float)(-xx) * sinort + fy * cosort) / hist_w;
-              float x_rot = (fx * cosort + fy * sinort) / hist_w;
-              float ybin = (float)((double)(y_rot + 2.f) - 0.5);
-              float xbin = (float)((double)(x_rot + 2.f) - 0.5);
-              if (ybin >= -1.f && ybin <= 3.f && xbin >= -1.f && xbin <= 3.f) {
-                float now_mag, now_ort;
-                mag_ort_at(lvl, w, nowx, nowy, &now_mag, &now_ort);
-                float weight = glibc_expf(-(x_rot * x_rot + y_rot * y_rot) / exp_denom);
-                weight = weight * now_mag;
-                now_ort -= ort;
-                if (now_ort < 0) now_ort += pi2;
-                if (now_ort > pi2) now_ort -= pi2;
-                float hbin = now_ort * nbin_per_rad;
-                int ybinf = (int)floorf(ybin), xbinf = (int)floorf(xbin), hbinf = (int)floorf(hbin);
-                ybind = ybin - (float)ybinf;
-                xbind = xbin - (float)xbinf;
-                hbind = hbin - (float)hbinf;
-                wgt = weight;
-                pk = (uint32_t)(ybinf + 2) | ((uint32_t)(xbinf + 2) << 8) | ((uint32_t)hbinf << 16);
-              }
-            }
-          }
-          r_pk[t] = pk; r_w[t] = wgt; r_yd[t] = ybind; r_xd[t] = xbind; r_hd[t] = hbind;
-        }
-        __syncthreads();
-        // phase 2
-        {
-          int xa = max(cx0, bx_lo), xb = min(cx1, bx_hi);
-          for (int xx = xa; xx <= xb; ++xx) {
-            const int rb = (xx - cx0) * side + radius;
-            for (int yy = by_lo; yy <= by_hi; ++yy) {
-              const int t = rb + yy;
-              uint32_t pk = r_pk[t];
-              if (pk == DESC_SKIP) continue;
-              int dy = by - ((int)(pk & 0xff) - 2);
-              int dx = bx - ((int)((pk >> 8) & 0xff) - 2);
-              if ((unsigned)dy > 1u || (unsigned)dx > 1u) continue;
-              int hbinf = (int)(pk >> 16);
-              int ho;
-              if ((hbinf & 7) == bh) ho = 0;
-              else if (((hbinf + 1) & 7) == bh) ho = 1;
-              else continue;
-              float yd = r_yd[t], xd = r_xd[t], hd = r_hd[t];
-              float w_y = r_w[t] * (dy ? yd : 1 - yd);
-              float w_x = w_y * (dx ? xd : 1 - xd);
-              acc += w_x * (ho ? hd : 1 - hd);
+            const float fx = (float)xx, fy = (float)yy;
+            if (!(fx * fx + fy * fy > fr2)) {
+              const float yr = (float)(-xx) * sinort + fy * cosort;
+              const float xr = fx * cosort + fy * sinort;
+              keep = yr >= lo && yr <= hi && xr >= lo && xr <= hi;
+              packed = ((uint32_t)(xx + 128) << 8) | (uint32_t)(yy + 128);
             }
           }
         }
-        __syncthreads();
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) S.stage[nstage + __popc(bal & ((1u << lane) - 1))] = packed;
+        nstage += __popc(bal);
+        __syncwarp();
+        if (nstage >= 32) consume_stage(32);
+        // advance this lane's position by 32
+        yy += 32;
+        while (yy > radius) { yy -= side; ++xx; }
       }
+      if (nstage > 0) consume_stage(nstage);
+      if (nrec > 0) flush_records();
+
       // RootSIFT: L1 normalise (sequential sum), sqrt, * DESC_INT_FACTOR
-      s_hist[tid] = acc;
-      __syncthreads();
-      if (tid == 0) {
-        float sum = 0.f;
-        for (int q = 0; q < 128; ++q) sum += s_hist[q];
-        s_sum = sum;
+      float sum = 0.f;
+      if (lane == 0) {
+#pragma unroll 16
+        for (int q = 0; q < 128; ++q) sum += S.acc[q];
       }
-      __syncthreads();
-      float v = acc / s_sum;
-      out_desc[dslot * 128 + tid] = sqrtf(v) * (float)dp.int_factor;
-      if (tid == 0) {
+      sum = __shfl_sync(0xffffffffu, sum, 0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int b = lane + 32 * q;
+        const float v = S.acc[b] / sum;
+        out_desc[dslot * 128 + b] = sqrtf(v) * (float)dp.int_factor;
+      }
+      if (lane == 0) {
         out_coor[dslot * 2] = (p.real_x - 0.5) * im.in_w;
         out_coor[dslot * 2 + 1] = (p.real_y - 0.5) * im.in_h;
       }
-      __syncthreads();
+      __syncwarp();
     }
   }
 }
@@ -859,9 +1022,17 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     const int R = gt.rmax;
     size_t smem = ((size_t)(BT_H + 2 * R) * (BT_W + 2 * R) + (size_t)BT_H * (BT_W + 2 * R)) * sizeof(float);
     if (smem > 200 * 1024) { sift_work_free(ctx, wk); return ctx_fail(ctx, PANO_ERR_INVALID, "sift: blur halo too large"); }
-    if (smem > 48 * 1024)
-      SIFT_CUDA(cudaFuncSetAttribute(k_blur_dog, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SIFT_LAUNCH("k_blur_dog", k_blur_dog, wk->n_tiles, BT_THREADS, smem, wk->d_oct, wk->d_tiles, wk->arena, gt);
+    bool fast = true;
+    for (int s = 0; s < gt.nlev; ++s) fast = fast && (gt.center[s] == 3 || gt.center[s] == 6);
+    if (fast) {
+      const int GW = BT_W + 2 * R, GH = BT_H + 2 * R, CS = GW | 1;
+      size_t smf = ((size_t)GH * GW + (size_t)BT_H * CS + (size_t)BT_H * (BT_W + 1)) * sizeof(float);
+      SIFT_LAUNCH("k_blur_dog", k_blur_dog_fast, wk->n_tiles, BT_THREADS, smf, wk->d_oct, wk->d_tiles, wk->arena, gt);
+    } else {
+      if (smem > 48 * 1024)
+        SIFT_CUDA(cudaFuncSetAttribute(k_blur_dog, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SIFT_LAUNCH("k_blur_dog_generic", k_blur_dog, wk->n_tiles, BT_THREADS, smem, wk->d_oct, wk->d_tiles, wk->arena, gt);
+    }
   }
   {
     dim3 b(32, 8), g(ceil_div(max_w0 - 2, 32), ceil_div(max_h0 - 2, 8), n * n_oct);
@@ -882,8 +1053,10 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     SIFT_LAUNCH("k_expand_scan", k_expand_scan, n, SCAN_THREADS, 0, wk->cand_count, wk->kp_valid, wk->npeaks,
                 wk->dirs, fs->d_count, wk->n_refined, wk->desc_cand, wk->desc_dir);
     DescParams dp{p->desc_hist_scale_factor, p->desc_int_factor};
-    int grid = ctx->num_sms * 8;
-    SIFT_LAUNCH("k_descriptor", k_descriptor, grid, DESC_THREADS, 0, wk->d_oct, wk->d_img, wk->arena, n_oct, n,
+    const size_t dsm = sizeof(DescWarpSmem) * DESC_WARPS;
+    SIFT_CUDA(cudaFuncSetAttribute(k_descriptor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+    int grid = ctx->num_sms * 3;
+    SIFT_LAUNCH("k_descriptor", k_descriptor, grid, DESC_THREADS, dsm, wk->d_oct, wk->d_img, wk->arena, n_oct, n,
                 wk->refined, fs->d_count, wk->desc_cand, wk->desc_dir, dp, fs->d_desc, fs->d_coor);
   }
   wk->n_desc = fs->d_count;
