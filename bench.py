@@ -284,6 +284,7 @@ def main():
         barrier()
         launches = eng.launch_count() - l0
         clocks = sampler.stop() if rank == 0 else None
+        exact_rows = eng.match_last_exact_rows()
         ms = e0.elapsed_time(e1)
         t_dev = torch.tensor([ms], device="cuda")
         if world > 1:
@@ -384,7 +385,8 @@ def main():
                        "pairs": len(pairs), "bands": args.bands, "blend": "linear" if args.bands == 0 else "multiband",
                        "geometry": "generator-known homographies (flat projection)", "parallelism": f"dp{world}",
                        "l2_policy": "inputs_exceed_l2 (260 MB of images + 0.9 GB pyramid arena per step)",
-                       "features": int(sum(counts)), "matches": int(n_matches)},
+                       "features": int(sum(counts)), "matches": int(n_matches),
+                       "match_rows_rescanned_exactly": int(exact_rows)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_per_step * 1e3},

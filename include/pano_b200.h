@@ -104,6 +104,9 @@ int  pano_profile_reset(pano_ctx* ctx);
 int  pano_profile_read(pano_ctx* ctx, int cap, char* names, int* launches, double* total_ms);
 /* Total number of kernels this ctx has launched since creation. */
 long long pano_launch_count(const pano_ctx* ctx);
+/* Diagnostics: how many descriptor rows the last pano_match_pairs_dev call had to
+ * re-scan exactly because the tensor-core nomination was not certain. */
+int pano_match_last_exact_rows(const pano_ctx* ctx);
 
 /* ---------------------------------------------------------------- features
  * Replaces FeatureDetector::detect_feature / SIFTDetector::do_detect_feature

@@ -35,6 +35,7 @@ struct pano_ctx {
   std::vector<cudaEvent_t> event_pool;
   std::map<std::string, std::pair<int, double>> prof_acc;  // name -> (launches, ms)
   long long launches = 0;
+  int last_match_exact_rows = 0;   // rows the last match call had to re-scan exactly
   int num_sms = 148;
   // pinned host staging (grown on demand)
   void* pinned = nullptr;

@@ -179,6 +179,7 @@ int pano_profile_read(pano_ctx* ctx, int cap, char* names, int* launches, double
 }
 
 long long pano_launch_count(const pano_ctx* ctx) { return ctx->launches; }
+int pano_match_last_exact_rows(const pano_ctx* ctx) { return ctx->last_match_exact_rows; }
 
 // ---------------------------------------------------------------- device utilities
 int pano_dev_alloc(pano_ctx* ctx, size_t bytes, void** d_ptr) { return ctx_alloc(ctx, d_ptr, bytes); }
@@ -210,6 +211,7 @@ static void featureset_release(pano_featureset* fs) {
   pano_ctx* ctx = fs->ctx;
   if (ctx) {
     ctx_free(ctx, fs->d_desc); ctx_free(ctx, fs->d_coor); ctx_free(ctx, fs->d_count);
+    tc_release(ctx, &fs->tc);
   }
   if (fs->counts_ready) cudaEventDestroy(fs->counts_ready);
   if (fs->h_count_pinned) cudaFreeHost(fs->h_count_pinned);

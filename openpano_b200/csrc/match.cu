@@ -7,14 +7,47 @@
 // FMA.  The reference's rule
 //     loop k over the smaller set: exact top-2 of row k (lowest index wins);
 //     reject if min > R*next; next = min(next, min_{kk!=k} d(best, kk)); reject again
-// is evaluated as two symmetric top-2 reductions (rows of A over B, rows of B over
-// A) followed by a per-row decision: min_{kk!=k} d(j, kk) is column j's second
-// minimum when its argmin is k, and its minimum otherwise.
+// is evaluated from two symmetric top-2 reductions (rows of A over B, rows of B
+// over A): min_{kk!=k} d(j, kk) is column j's second minimum when its argmin is
+// k, and its minimum otherwise.
+//
+// Two ways to get those reductions:
+//  * tensor path (default): match_tc.cu nominates (approx best, argmin, approx
+//    second) per row on the tcgen05 tensor cores; here every row gets its exact
+//    fp32 best distance, a certified interval for its second-best (the fp16
+//    quantisation bound), and rows whose argmin or accept/reject decision is not
+//    certain within those intervals are re-scanned exactly (k_exact_rows).  The
+//    outcome is the reference's, bit for bit; the tensor cores only decide how
+//    little exact work is left.
+//  * exact path (PANO_MATCH_PATH=exact): both reductions in fp32 on the CUDA
+//    cores (k_match_top2), kept as the in-engine cross-check.
 #include "sift.cuh"
+#include "match_tc.cuh"
 #include <float.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 
+// feature/dist.cc:22-57 (SSE lane order); a and b are 16-byte aligned rows of 128 floats
+__device__ __forceinline__ float exact_dist(const float* __restrict__ a, const float* __restrict__ b) {
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+  const float4* pa = (const float4*)a;
+  const float4* pb = (const float4*)b;
+#pragma unroll 8
+  for (int k = 0; k < 32; ++k) {
+    float4 x = __ldg(pa + k), y = __ldg(pb + k);
+    float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+    l0 += d0 * d0; l1 += d1 * d1; l2 += d2 * d2; l3 += d3 * d3;
+  }
+  return (l0 + l1) + (l2 + l3);
+}
+
+__device__ __forceinline__ void top2_merge(float& mn, int& idx, float& sec, float m2, int i2, float s2) {
+  if (m2 < mn || (m2 == mn && i2 < idx)) { sec = fminf(mn, s2); mn = m2; idx = i2; }
+  else sec = fminf(sec, m2);
+}
+
+// ============================================================ exact path (fp32 CUDA cores)
 #define MT 64            // rows of the query tile and of the target tile
 #define MT_STRIDE 132    // padded row stride in floats (conflict-free float4 reads)
 #define MT_THREADS 256
@@ -26,15 +59,13 @@ struct MatchTask {       // one top-2 reduction: rows [q_row0, q_row0+MT) of Q a
   long long res_off;     // where this query set's results start
 };
 
-struct Top2 { float mn; float second; int idx; int pad; };
-
-__device__ __forceinline__ void top2_merge(float& mn, int& idx, float& sec, float m2, int i2, float s2) {
-  if (m2 < mn || (m2 == mn && i2 < idx)) { sec = fminf(mn, s2); mn = m2; idx = i2; }
-  else sec = fminf(sec, m2);
-}
+// Per-row knowledge, as certified intervals.  state bit 1: argmin certain (then
+// mn == mn_hi is the exact fp32 distance to idx); bit 0: second-best exact
+// (sec_lo == sec_hi).  With an uncertain argmin only the bounds are valid.
+struct RowInfo { float mn, mn_hi; int idx; float sec_lo, sec_hi; int state; int requested; int pad; };
 
 __global__ void __launch_bounds__(MT_THREADS)
-k_match_top2(const float* __restrict__ desc, const MatchTask* __restrict__ tasks, Top2* __restrict__ res) {
+k_match_top2(const float* __restrict__ desc, const MatchTask* __restrict__ tasks, RowInfo* __restrict__ res) {
   extern __shared__ float sm[];
   float* sq = sm;                       // [MT][MT_STRIDE]
   float* st = sm + MT * MT_STRIDE;      // [MT][MT_STRIDE]
@@ -116,112 +147,319 @@ k_match_top2(const float* __restrict__ desc, const MatchTask* __restrict__ tasks
     }
     int row = tk.q_row0 + ty + 16 * i;
     if (tx == 0 && row < tk.q_n) {
-      Top2 o; o.mn = mn; o.second = sec; o.idx = idx; o.pad = 0;
+      RowInfo o; o.mn = mn; o.mn_hi = mn; o.idx = idx; o.sec_lo = sec; o.sec_hi = sec; o.state = 3; o.requested = 0; o.pad = 0;
       res[tk.res_off + row] = o;
     }
   }
 }
 
+// ============================================================ tensor path: certification
+
+struct SideMeta {        // one query set of one pair
+  long long q_base, t_base;   // descriptor rows in the featureset
+  int q_n, t_n;
+  long long res_off;          // RowInfo / TcTop2 offset of this side
+};
+
+// Bound on |approx d^2 - exact fp32 d^2| for a query of squared norm nq against
+// targets of squared norm <= nmax: fp16 rounding of both operands (2 * 2^-11
+// relative on every product, doubled by the -2ab term) plus the packed-key
+// mantissa truncation, the hi/lo norm split and accumulation slack.
+__device__ __forceinline__ float tc_eps(float nq, float nmax) {
+  return 0.00215f * sqrtf(nq * nmax) + 0.0005f * nmax + 1.0f;
+}
+
+__global__ void k_refine(const float* __restrict__ desc, const float* __restrict__ norms,
+                         const unsigned* __restrict__ maxnorm_bits, const SideMeta* __restrict__ sides,
+                         const TcTop2* __restrict__ approx, RowInfo* __restrict__ info) {
+  const int side = blockIdx.y;
+  const SideMeta sm = sides[side];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= sm.q_n) return;
+  const TcTop2 ap = approx[sm.res_off + r];
+  const float nmax = __uint_as_float(*maxnorm_bits);
+  const float eps = tc_eps(norms[sm.q_base + r], nmax);
+  RowInfo o;
+  o.requested = 0; o.pad = 0;
+  const bool idx_ok = ap.idx >= 0 && ap.idx < sm.t_n;
+  o.idx = idx_ok ? ap.idx : 0;
+  const bool single = ap.m2 == FLT_MAX;                 // only one real target
+  const bool certain = idx_ok && (single || (ap.m2 - ap.m1 > 2.f * eps));
+  if (sm.t_n <= 0) { o.mn = FLT_MAX; o.mn_hi = FLT_MAX; o.sec_lo = FLT_MAX; o.sec_hi = FLT_MAX; o.state = 3; }
+  else if (certain) {
+    // the argmin is certain: its exact fp32 distance is the row minimum
+    o.mn = exact_dist(desc + (size_t)(sm.q_base + r) * 128, desc + (size_t)(sm.t_base + o.idx) * 128);
+    o.mn_hi = o.mn;
+    if (single) { o.sec_lo = FLT_MAX; o.sec_hi = FLT_MAX; o.state = 3; }
+    else { o.sec_lo = fmaxf(ap.m2 - eps, o.mn); o.sec_hi = fmaxf(ap.m2 + eps, o.mn); o.state = 2; }
+  } else {
+    // two or more targets within the error band of the best: only bounds are known
+    o.mn = fmaxf(ap.m1 - eps, 0.f); o.mn_hi = ap.m1 + eps;
+    o.sec_lo = fmaxf(ap.m2 - eps, 0.f); o.sec_hi = ap.m2 + eps;
+    o.state = 0;
+  }
+  info[sm.res_off + r] = o;
+}
+
+// Exact re-scan of listed rows: one warp per row, lanes stride over the targets.
+__global__ void __launch_bounds__(256)
+k_exact_rows(const float* __restrict__ desc, const SideMeta* __restrict__ sides, const int2* __restrict__ list,
+             const int* __restrict__ list_count, RowInfo* __restrict__ info) {
+  __shared__ __align__(16) float sq[8][128];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int n = *list_count;
+  for (int e = blockIdx.x * 8 + wid; e < n; e += gridDim.x * 8) {
+    const int2 it = list[e];
+    const SideMeta sm = sides[it.x];
+    const float* q = desc + (size_t)(sm.q_base + it.y) * 128;
+    __syncwarp();
+    *(float4*)(&sq[wid][lane * 4]) = __ldg((const float4*)q + lane);
+    __syncwarp();
+    float mn = FLT_MAX, sec = FLT_MAX;
+    int idx = 0x7fffffff;
+    for (int c = lane; c < sm.t_n; c += 32) {
+      const float4* pb = (const float4*)(desc + (size_t)(sm.t_base + c) * 128);
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < 32; ++k) {
+        float4 x = *(const float4*)(&sq[wid][k * 4]), y = __ldg(pb + k);
+        float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+        l0 += d0 * d0; l1 += d1 * d1; l2 += d2 * d2; l3 += d3 * d3;
+      }
+      float d = (l0 + l1) + (l2 + l3);
+      if (d < mn) { sec = mn; mn = d; idx = c; }
+      else if (d < sec) sec = d;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      float m2 = __shfl_xor_sync(0xffffffffu, mn, off);
+      float s2 = __shfl_xor_sync(0xffffffffu, sec, off);
+      int i2 = __shfl_xor_sync(0xffffffffu, idx, off);
+      top2_merge(mn, idx, sec, m2, i2, s2);
+    }
+    if (lane == 0) {
+      RowInfo o; o.mn = mn; o.mn_hi = mn; o.idx = idx; o.sec_lo = sec; o.sec_hi = sec; o.state = 3; o.requested = 1; o.pad = 0;
+      info[sm.res_off + it.y] = o;
+    }
+  }
+}
+
 struct PairMeta {
-  long long resA_off, resB_off;  // Top2 of the smaller set's rows / of the larger set's rows
+  int side_small, side_large;    // indices into the side table (small set queries / large set queries)
   int n_small, n_large;
   long long out_off;             // per-row decision of the smaller set
 };
 
-// Decision per row k of the smaller set (matcher.cc:49-66).
-__global__ void k_match_decide(const PairMeta* __restrict__ pairs, const Top2* __restrict__ res,
-                               float ratio_sqr, int* __restrict__ out, int* __restrict__ total) {
+#define OUT_PENDING (-2)
+
+// Decision per row k of the smaller set (matcher.cc:49-66) from certified
+// intervals; rows that cannot be decided request exact re-scans and stay pending.
+__global__ void k_match_decide(const PairMeta* __restrict__ pairs, const SideMeta* __restrict__ sides,
+                               RowInfo* __restrict__ info, float ratio_sqr, int first_round,
+                               int* __restrict__ out, int* __restrict__ total,
+                               int2* __restrict__ list, int* __restrict__ list_count) {
   const PairMeta pm = pairs[blockIdx.y];
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= pm.n_small) return;
-  Top2 r = res[pm.resA_off + k];
+  const size_t oslot = pm.out_off + k;
+  if (!first_round && out[oslot] != OUT_PENDING) return;
   int result = -1;
-  if (pm.n_large > 0 && !(r.mn > ratio_sqr * r.second)) {
-    Top2 c = res[pm.resB_off + r.idx];
-    float colmin = (c.idx == k) ? c.second : c.mn;
-    float next_min = fminf(r.second, colmin);
-    if (!(r.mn > ratio_sqr * next_min)) result = r.idx;
+  if (pm.n_large > 0) {
+    const SideMeta ss = sides[pm.side_small], sl = sides[pm.side_large];
+    const RowInfo r = info[ss.res_off + k];
+    if (!(r.state & 2)) {
+      // argmin not certain: the row test alone (mn > R * second) may already reject
+      if (r.mn > ratio_sqr * r.sec_hi) result = -1;
+      else {
+        result = OUT_PENDING;
+        if (atomicExch(&info[ss.res_off + k].requested, 1) == 0)
+          list[atomicAdd(list_count, 1)] = make_int2(pm.side_small, k);
+      }
+    } else {
+      const RowInfo c = info[sl.res_off + r.idx];
+      float c_lo, c_hi;
+      bool need_c = false;
+      if (c.state & 2) {                                  // column's argmin certain
+        const bool mine = c.idx == k;
+        c_lo = mine ? c.sec_lo : c.mn; c_hi = mine ? c.sec_hi : c.mn_hi;
+        need_c = mine && !(c.state & 1);
+      } else {                                            // min_{kk != k} d(j, kk) lies between its best and second bounds
+        c_lo = c.mn; c_hi = c.sec_hi;
+        need_c = true;
+      }
+      const float nlo = fminf(r.sec_lo, c_lo), nhi = fminf(r.sec_hi, c_hi);
+      if (r.mn > ratio_sqr * nhi) result = -1;               // rejected for every admissible next_min
+      else if (!(r.mn > ratio_sqr * nlo)) result = r.idx;    // accepted for every admissible next_min
+      else {
+        result = OUT_PENDING;
+        if (!(r.state & 1) && atomicExch(&info[ss.res_off + k].requested, 1) == 0)
+          list[atomicAdd(list_count, 1)] = make_int2(pm.side_small, k);
+        if (need_c && atomicExch(&info[sl.res_off + r.idx].requested, 1) == 0)
+          list[atomicAdd(list_count, 1)] = make_int2(pm.side_large, r.idx);
+      }
+    }
   }
-  out[pm.out_off + k] = result;
+  out[oslot] = result;
   if (result >= 0) atomicAdd(total, 1);
 }
 
 // ------------------------------------------------------------------ host driver
 
 struct MatchPlan {
-  std::vector<MatchTask> tasks;
+  std::vector<SideMeta> sides;
   std::vector<PairMeta> pairs;
-  std::vector<char> rev;   // pair was swapped (first image is the larger set)
+  std::vector<MatchTask> exact_tasks;   // exact path
+  std::vector<TcTask> tc_tasks;         // tensor path
+  std::vector<char> rev;                // pair was swapped (first image is the larger set)
   long long res_total = 0, out_total = 0;
+  int max_side_n = 0, max_small = 0;
 };
 
-static void plan_pair(MatchPlan& pl, long long baseA, int nA, long long baseB, int nB) {
-  // matcher.cc:21-29: loop over the smaller one; rev = l1 > l2
-  bool rev = nA > nB;
-  long long bs = rev ? baseB : baseA, bl = rev ? baseA : baseB;
-  int ns = rev ? nB : nA, nl = rev ? nA : nB;
-  PairMeta pm;
-  pm.n_small = ns; pm.n_large = nl;
-  pm.resA_off = pl.res_total; pl.res_total += ns;
-  pm.resB_off = pl.res_total; pl.res_total += nl;
-  pm.out_off = pl.out_total; pl.out_total += ns;
-  for (int r0 = 0; r0 < ns; r0 += MT) pl.tasks.push_back(MatchTask{bs, bl, ns, nl, r0, pm.resA_off});
-  for (int r0 = 0; r0 < nl; r0 += MT) pl.tasks.push_back(MatchTask{bl, bs, nl, ns, r0, pm.resB_off});
-  pl.pairs.push_back(pm);
-  pl.rev.push_back(rev ? 1 : 0);
+static bool use_exact_path() {
+  const char* e = getenv("PANO_MATCH_PATH");
+  return e && strcmp(e, "exact") == 0;
 }
 
-// Runs the plan; leaves per-row decisions in *d_out (caller frees) and the total in *d_total.
-static int run_plan(pano_ctx* ctx, const float* d_desc, const MatchPlan& pl, float ratio, int** d_out, int** d_total) {
-  *d_out = nullptr; *d_total = nullptr;
-  MatchTask* d_tasks = nullptr; PairMeta* d_pairs = nullptr; Top2* d_res = nullptr;
-  int rc = 0;
-  size_t bt = pl.tasks.size() * sizeof(MatchTask), bp = pl.pairs.size() * sizeof(PairMeta);
-  if ((rc = ctx_alloc(ctx, (void**)&d_tasks, bt)) || (rc = ctx_alloc(ctx, (void**)&d_pairs, bp)) ||
-      (rc = ctx_alloc(ctx, (void**)&d_res, std::max<long long>(pl.res_total, 1) * sizeof(Top2))) ||
-      (rc = ctx_alloc(ctx, (void**)d_out, std::max<long long>(pl.out_total, 1) * sizeof(int))) ||
-      (rc = ctx_alloc(ctx, (void**)d_total, sizeof(int)))) {
-    ctx_free(ctx, d_tasks); ctx_free(ctx, d_pairs); ctx_free(ctx, d_res);
-    return rc;
-  }
-  char* stg = (char*)ctx_pinned2(ctx, bt + bp + 16);
-  if (!stg) return ctx_fail(ctx, PANO_ERR_CUDA, "pinned alloc failed");
-  if (bt) memcpy(stg, pl.tasks.data(), bt);
-  if (bp) memcpy(stg + bt, pl.pairs.data(), bp);
-  cudaError_t e = cudaSuccess;
-  if (bt) e = cudaMemcpyAsync(d_tasks, stg, bt, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess && bp) e = cudaMemcpyAsync(d_pairs, stg + bt, bp, cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(*d_total, 0, sizeof(int), ctx->stream);
-  if (e != cudaSuccess) { ctx_free(ctx, d_tasks); ctx_free(ctx, d_pairs); ctx_free(ctx, d_res); return ctx_cuda(ctx, e, "match upload"); }
-  const size_t smem = (size_t)2 * MT * MT_STRIDE * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    e = cudaFuncSetAttribute(k_match_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return ctx_cuda(ctx, e, "cudaFuncSetAttribute(k_match_top2)");
-    attr_set = true;
-  }
-  if (!pl.tasks.empty())
-    PANO_LAUNCH(ctx, "k_match_top2", k_match_top2, (unsigned)pl.tasks.size(), MT_THREADS, smem, d_desc, d_tasks, d_res);
-  int max_small = 0;
-  for (auto& pm : pl.pairs) max_small = std::max(max_small, pm.n_small);
-  if (max_small > 0) {
-    dim3 g(ceil_div(max_small, 256), (unsigned)pl.pairs.size());
-    PANO_LAUNCH(ctx, "k_match_decide", k_match_decide, g, 256, 0, d_pairs, d_res, ratio * ratio, *d_out, *d_total);
-  }
-  ctx_free(ctx, d_tasks); ctx_free(ctx, d_pairs); ctx_free(ctx, d_res);
-  return PANO_OK;
-}
-
-static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int* ij, MatchPlan& pl) {
-  int rc = featureset_sync_counts(fs);
-  if (rc) return rc;
+static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int* ij, MatchPlan& pl,
+                      const std::vector<TcImage>* tcimgs) {
   for (int k = 0; k < n_pairs; ++k) {
     int i = ij[2 * k], j = ij[2 * k + 1];
     if (i < 0 || j < 0 || i >= fs->n_images || j >= fs->n_images)
       return ctx_fail(ctx, PANO_ERR_INVALID, "pair %d: image index out of range", k);
-    plan_pair(pl, fs->base[i], fs->h_count[i], fs->base[j], fs->h_count[j]);
+    // matcher.cc:21-29: loop over the smaller one; rev = l1 > l2
+    const bool rev = fs->h_count[i] > fs->h_count[j];
+    const int is = rev ? j : i, il = rev ? i : j;
+    const int ns = fs->h_count[is], nl = fs->h_count[il];
+    SideMeta a{fs->base[is], fs->base[il], ns, nl, pl.res_total}; pl.res_total += ns;
+    SideMeta b{fs->base[il], fs->base[is], nl, ns, pl.res_total}; pl.res_total += nl;
+    PairMeta pm{(int)pl.sides.size(), (int)pl.sides.size() + 1, ns, nl, pl.out_total};
+    pl.out_total += ns;
+    pl.sides.push_back(a); pl.sides.push_back(b);
+    pl.pairs.push_back(pm);
+    pl.rev.push_back(rev ? 1 : 0);
+    pl.max_side_n = std::max(pl.max_side_n, std::max(ns, nl));
+    pl.max_small = std::max(pl.max_small, ns);
+    if (tcimgs) {
+      const TcImage &ts = (*tcimgs)[is], &tl = (*tcimgs)[il];
+      if (nl > 0)
+        for (int r0 = 0; r0 < ns; r0 += 128)
+          pl.tc_tasks.push_back(TcTask{ts.blk0 + r0 / 128, r0, ns, tl.blk0, tl.n_pad / 128, a.res_off});
+      if (ns > 0)
+        for (int r0 = 0; r0 < nl; r0 += 128)
+          pl.tc_tasks.push_back(TcTask{tl.blk0 + r0 / 128, r0, nl, ts.blk0, ts.n_pad / 128, b.res_off});
+    } else {
+      for (int r0 = 0; r0 < ns; r0 += MT) pl.exact_tasks.push_back(MatchTask{a.q_base, a.t_base, ns, nl, r0, a.res_off});
+      for (int r0 = 0; r0 < nl; r0 += MT) pl.exact_tasks.push_back(MatchTask{b.q_base, b.t_base, nl, ns, r0, b.res_off});
+    }
   }
   return PANO_OK;
+}
+
+struct MatchBuffers {
+  void* tasks = nullptr; PairMeta* pairs = nullptr; SideMeta* sides = nullptr;
+  RowInfo* info = nullptr; TcTop2* approx = nullptr;
+  int2* list = nullptr; int* counters = nullptr;   // [0] total, [1] list1 count, [2] list2 count
+  int* out = nullptr;
+};
+
+static void free_buffers(pano_ctx* ctx, MatchBuffers& b, bool keep_out) {
+  ctx_free(ctx, b.tasks); ctx_free(ctx, b.pairs); ctx_free(ctx, b.sides); ctx_free(ctx, b.info);
+  ctx_free(ctx, b.approx); ctx_free(ctx, b.list);
+  if (!keep_out) { ctx_free(ctx, b.out); ctx_free(ctx, b.counters); b.out = nullptr; b.counters = nullptr; }
+}
+
+// Runs the plan; leaves per-row decisions in b.out and counters in b.counters (caller frees both).
+static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, float ratio, bool tensor,
+                    const TcOperands* ops, MatchBuffers& b) {
+  int rc = 0;
+  const size_t bt = tensor ? pl.tc_tasks.size() * sizeof(TcTask) : pl.exact_tasks.size() * sizeof(MatchTask);
+  const size_t bp = pl.pairs.size() * sizeof(PairMeta), bs = pl.sides.size() * sizeof(SideMeta);
+  const long long nres = std::max<long long>(pl.res_total, 1);
+  if ((rc = ctx_alloc(ctx, &b.tasks, bt)) || (rc = ctx_alloc(ctx, (void**)&b.pairs, bp)) ||
+      (rc = ctx_alloc(ctx, (void**)&b.sides, bs)) || (rc = ctx_alloc(ctx, (void**)&b.info, nres * sizeof(RowInfo))) ||
+      (rc = ctx_alloc(ctx, (void**)&b.approx, nres * sizeof(TcTop2))) ||
+      (rc = ctx_alloc(ctx, (void**)&b.list, nres * sizeof(int2))) ||
+      (rc = ctx_alloc(ctx, (void**)&b.counters, 4 * sizeof(int))) ||
+      (rc = ctx_alloc(ctx, (void**)&b.out, std::max<long long>(pl.out_total, 1) * sizeof(int))))
+    return rc;
+  char* stg = (char*)ctx_pinned2(ctx, bt + bp + bs + 64);
+  if (!stg) return ctx_fail(ctx, PANO_ERR_CUDA, "pinned alloc failed");
+  const void* tsrc = tensor ? (const void*)pl.tc_tasks.data() : (const void*)pl.exact_tasks.data();
+  if (bt) memcpy(stg, tsrc, bt);
+  if (bp) memcpy(stg + bt, pl.pairs.data(), bp);
+  if (bs) memcpy(stg + bt + bp, pl.sides.data(), bs);
+  if (bt) PANO_CUDA(ctx, cudaMemcpyAsync(b.tasks, stg, bt, cudaMemcpyHostToDevice, ctx->stream));
+  if (bp) PANO_CUDA(ctx, cudaMemcpyAsync(b.pairs, stg + bt, bp, cudaMemcpyHostToDevice, ctx->stream));
+  if (bs) PANO_CUDA(ctx, cudaMemcpyAsync(b.sides, stg + bt + bp, bs, cudaMemcpyHostToDevice, ctx->stream));
+  PANO_CUDA(ctx, cudaMemsetAsync(b.counters, 0, 4 * sizeof(int), ctx->stream));
+  if (pl.pairs.empty()) return PANO_OK;
+  const float rs = ratio * ratio;
+  dim3 gd(std::max(1, ceil_div(pl.max_small, 256)), (unsigned)pl.pairs.size());
+  if (!tensor) {
+    const size_t smem = (size_t)2 * MT * MT_STRIDE * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      PANO_CUDA(ctx, cudaFuncSetAttribute(k_match_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+    if (!pl.exact_tasks.empty())
+      PANO_LAUNCH(ctx, "k_match_top2", k_match_top2, (unsigned)pl.exact_tasks.size(), MT_THREADS, smem, fs->d_desc,
+                  (const MatchTask*)b.tasks, b.info);
+    if (pl.max_small > 0)
+      PANO_LAUNCH(ctx, "k_match_decide", k_match_decide, gd, 256, 0, b.pairs, b.sides, b.info, rs, 1, b.out,
+                  b.counters, b.list, b.counters + 1);
+    return PANO_OK;
+  }
+  rc = tc_run_top2(ctx, ops, (const TcTask*)b.tasks, (int)pl.tc_tasks.size(), b.approx);
+  if (rc) return rc;
+  if (pl.max_side_n > 0) {
+    dim3 gr(ceil_div(pl.max_side_n, 128), (unsigned)pl.sides.size());
+    PANO_LAUNCH(ctx, "k_refine", k_refine, gr, 128, 0, fs->d_desc, ops->d_norms, ops->d_maxnorm, b.sides, b.approx,
+                b.info);
+  }
+  if (pl.max_small > 0) {
+    // Up to three decide rounds: a round decides every row it can from the current
+    // intervals and lists the rows it needs exactly; k_exact_rows re-scans those.
+    // Round 1 may need row k itself (argmin uncertain), round 2 then its column.
+    const int eg = ctx->num_sms * 4;
+    for (int round = 0; round < 3; ++round) {
+      int* cnt = b.counters + 1 + round;
+      PANO_LAUNCH(ctx, "k_match_decide", k_match_decide, gd, 256, 0, b.pairs, b.sides, b.info, rs, round == 0 ? 1 : 0,
+                  b.out, b.counters, b.list, cnt);
+      if (round == 2) break;
+      PANO_LAUNCH(ctx, "k_exact_rows", k_exact_rows, eg, 256, 0, fs->d_desc, b.sides, b.list, cnt, b.info);
+    }
+  }
+  return PANO_OK;
+}
+
+static int ensure_tc_operands(pano_ctx* ctx, pano_featureset* fs, std::vector<TcImage>& imgs) {
+  imgs.resize(fs->n_images);
+  int blk = 0;
+  for (int i = 0; i < fs->n_images; ++i) {
+    TcImage& im = imgs[i];
+    im.row0 = fs->base[i]; im.n = fs->h_count[i];
+    im.n_pad = (im.n + 255) / 256 * 256;
+    im.blk0 = blk;
+    blk += im.n_pad / 128;
+  }
+  if (fs->tc_ready) return PANO_OK;
+  int rc = tc_prepare(ctx, fs->d_desc, imgs, &fs->tc);
+  if (rc) return rc;
+  fs->tc_ready = true;
+  return PANO_OK;
+}
+
+static int match_common(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int* ij, const pano_params* p,
+                        MatchPlan& pl, MatchBuffers& b) {
+  int rc = featureset_sync_counts(fs);
+  if (rc) return rc;
+  const bool tensor = !use_exact_path();
+  std::vector<TcImage> tcimgs;
+  if (tensor && (rc = ensure_tc_operands(ctx, fs, tcimgs))) return rc;
+  rc = build_plan(ctx, fs, n_pairs, ij, pl, tensor ? &tcimgs : nullptr);
+  if (rc) return rc;
+  return run_plan(ctx, fs, pl, p->match_reject_next_ratio, tensor, &fs->tc, b);
 }
 
 extern "C" {
@@ -231,15 +469,14 @@ int pano_match_pairs(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int*
   if (!ctx || !fs || !out || n_pairs < 0 || (n_pairs && !ij) || !p) return PANO_ERR_INVALID;
   memset(out, 0, sizeof(*out));
   MatchPlan pl;
-  int rc = build_plan(ctx, fs, n_pairs, ij, pl);
-  if (rc) return rc;
-  int *d_out = nullptr, *d_total = nullptr;
-  rc = run_plan(ctx, fs->d_desc, pl, p->match_reject_next_ratio, &d_out, &d_total);
-  if (rc) { ctx_free(ctx, d_out); ctx_free(ctx, d_total); return rc; }
+  MatchBuffers b;
+  int rc = match_common(ctx, fs, n_pairs, ij, p, pl, b);
+  if (rc) { free_buffers(ctx, b, false); return rc; }
   std::vector<int> h_out(std::max<long long>(pl.out_total, 1));
-  cudaError_t e = cudaMemcpyAsync(h_out.data(), d_out, pl.out_total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaSuccess;
+  if (pl.out_total) e = cudaMemcpyAsync(h_out.data(), b.out, pl.out_total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  ctx_free(ctx, d_out); ctx_free(ctx, d_total);
+  free_buffers(ctx, b, false);
   if (e != cudaSuccess) return ctx_cuda(ctx, e, "match download");
   out->n_pairs = n_pairs;
   out->count = (int*)calloc(std::max(n_pairs, 1), sizeof(int));
@@ -248,7 +485,10 @@ int pano_match_pairs(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int*
   for (int k = 0; k < n_pairs; ++k) {
     const PairMeta& pm = pl.pairs[k];
     int c = 0;
-    for (int r = 0; r < pm.n_small; ++r) c += h_out[pm.out_off + r] >= 0;
+    for (int r = 0; r < pm.n_small; ++r) {
+      if (h_out[pm.out_off + r] == OUT_PENDING) return ctx_fail(ctx, PANO_ERR_CUDA, "match: undecided row (internal error)");
+      c += h_out[pm.out_off + r] >= 0;
+    }
     out->count[k] = c; out->offset[k] = total; total += c;
   }
   out->offset[n_pairs] = total;
@@ -276,15 +516,17 @@ int pano_match_pairs_dev(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const 
                          int* total_matches) {
   if (!ctx || !fs || n_pairs < 0 || (n_pairs && !ij) || !p || !total_matches) return PANO_ERR_INVALID;
   MatchPlan pl;
-  int rc = build_plan(ctx, fs, n_pairs, ij, pl);
-  if (rc) return rc;
-  int *d_out = nullptr, *d_total = nullptr;
-  rc = run_plan(ctx, fs->d_desc, pl, p->match_reject_next_ratio, &d_out, &d_total);
-  if (rc) { ctx_free(ctx, d_out); ctx_free(ctx, d_total); return rc; }
-  cudaError_t e = cudaMemcpyAsync(total_matches, d_total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  MatchBuffers b;
+  int rc = match_common(ctx, fs, n_pairs, ij, p, pl, b);
+  if (rc) { free_buffers(ctx, b, false); return rc; }
+  int h[4] = {0, 0, 0, 0};
+  cudaError_t e = cudaMemcpyAsync(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  ctx_free(ctx, d_out); ctx_free(ctx, d_total);
+  free_buffers(ctx, b, false);
   if (e != cudaSuccess) return ctx_cuda(ctx, e, "match total download");
+  *total_matches = h[0];
+  ctx->last_match_exact_rows = h[1] + h[2];
+  if (h[3] != 0) return ctx_fail(ctx, PANO_ERR_CUDA, "match: %d rows undecided after the exact passes", h[3]);
   return PANO_OK;
 }
 

@@ -1,6 +1,7 @@
 // sift.cuh — host-visible structures of the batched SIFT pipeline.
 #pragma once
 #include "common.cuh"
+#include "match_tc.cuh"
 
 #define SIFT_MAX_OCT 8
 #define SIFT_MAX_LEVELS 8        // nscale-1 blurred levels
@@ -72,6 +73,8 @@ struct pano_featureset {
   bool counts_on_host = false;
   cudaEvent_t counts_ready = nullptr;
   int* h_count_pinned = nullptr;
+  TcOperands tc;              // fp16 tensor-core operands of the descriptors (lazy)
+  bool tc_ready = false;
 };
 
 int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w, const int* h,

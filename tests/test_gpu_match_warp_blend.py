@@ -124,3 +124,21 @@ def test_blend_full_size_properties(engine):
     assert cov2.mean() > 0.95
     assert mb[cov2].min() >= 0.0 and mb[cov2].max() <= 1.0
     assert np.abs(mb[cov2] - canvas[cov2]).mean() < 5e-3
+
+
+def test_match_tensor_path_equals_exact_path(engine, orc, monkeypatch):
+    """The tcgen05 nomination + certified exact decisions must give the same pairs
+    as the all-fp32 CUDA-core path and as the oracle, including near-threshold
+    ratios (heavy noise) where the fp16 scores cannot decide on their own."""
+    rng = np.random.RandomState(77)
+    a = synth.rootsift_like(1500, 8)
+    b = a[rng.permutation(1500)][:1300] + rng.randn(1300, 128).astype(np.float32) * 30.0
+    want = orc.match(a, b)
+    monkeypatch.delenv("PANO_MATCH_PATH", raising=False)
+    got_tc = engine.match_bruteforce(a, b)
+    monkeypatch.setenv("PANO_MATCH_PATH", "exact")
+    got_ex = engine.match_bruteforce(a, b)
+    monkeypatch.delenv("PANO_MATCH_PATH", raising=False)
+    assert np.array_equal(got_ex, want)
+    assert np.array_equal(got_tc, want)
+    assert 50 < len(want) < 1300
