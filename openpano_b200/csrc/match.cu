@@ -201,28 +201,31 @@ __global__ void k_refine(const float* __restrict__ desc, const float* __restrict
   info[sm.res_off + r] = o;
 }
 
-// Exact re-scan of listed rows: one warp per row, lanes stride over the targets.
+// Exact re-scan of listed rows: one 256-thread block per row, every thread strides
+// over the targets (the list is short, so parallelism has to come from the row).
 __global__ void __launch_bounds__(256)
 k_exact_rows(const float* __restrict__ desc, const SideMeta* __restrict__ sides, const int2* __restrict__ list,
              const int* __restrict__ list_count, RowInfo* __restrict__ info) {
-  __shared__ __align__(16) float sq[8][128];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __shared__ __align__(16) float sq[128];
+  __shared__ float s_mn[8], s_sec[8];
+  __shared__ int s_idx[8];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int n = *list_count;
-  for (int e = blockIdx.x * 8 + wid; e < n; e += gridDim.x * 8) {
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
     const int2 it = list[e];
     const SideMeta sm = sides[it.x];
     const float* q = desc + (size_t)(sm.q_base + it.y) * 128;
-    __syncwarp();
-    *(float4*)(&sq[wid][lane * 4]) = __ldg((const float4*)q + lane);
-    __syncwarp();
+    __syncthreads();
+    if (tid < 32) *(float4*)(&sq[tid * 4]) = __ldg((const float4*)q + tid);
+    __syncthreads();
     float mn = FLT_MAX, sec = FLT_MAX;
     int idx = 0x7fffffff;
-    for (int c = lane; c < sm.t_n; c += 32) {
+    for (int c = tid; c < sm.t_n; c += 256) {
       const float4* pb = (const float4*)(desc + (size_t)(sm.t_base + c) * 128);
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll 8
       for (int k = 0; k < 32; ++k) {
-        float4 x = *(const float4*)(&sq[wid][k * 4]), y = __ldg(pb + k);
+        float4 x = *(const float4*)(&sq[k * 4]), y = __ldg(pb + k);
         float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
         l0 += d0 * d0; l1 += d1 * d1; l2 += d2 * d2; l3 += d3 * d3;
       }
@@ -237,7 +240,10 @@ k_exact_rows(const float* __restrict__ desc, const SideMeta* __restrict__ sides,
       int i2 = __shfl_xor_sync(0xffffffffu, idx, off);
       top2_merge(mn, idx, sec, m2, i2, s2);
     }
-    if (lane == 0) {
+    if (lane == 0) { s_mn[wid] = mn; s_sec[wid] = sec; s_idx[wid] = idx; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int wdx = 1; wdx < 8; ++wdx) top2_merge(mn, idx, sec, s_mn[wdx], s_idx[wdx], s_sec[wdx]);
       RowInfo o; o.mn = mn; o.mn_hi = mn; o.idx = idx; o.sec_lo = sec; o.sec_hi = sec; o.state = 3; o.requested = 1; o.pad = 0;
       info[sm.res_off + it.y] = o;
     }

@@ -672,7 +672,7 @@ k_expand_scan(const int* __restrict__ cand_count, const unsigned char* __restric
 //      lane pairs advance independently and nearly every lane does useful work.
 #define DESC_WARPS 4
 #define DESC_THREADS (DESC_WARPS * 32)
-#define DESC_REC_CAP 640                 // records per flush; more simply flushes twice
+#define DESC_REC_CAP 384                 // records per flush (more records simply flush again)
 #define DESC_CHUNKS (DESC_REC_CAP / 32)
 #define DESC_SKIP 0xffffffffu
 
@@ -1055,7 +1055,7 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     DescParams dp{p->desc_hist_scale_factor, p->desc_int_factor};
     const size_t dsm = sizeof(DescWarpSmem) * DESC_WARPS;
     SIFT_CUDA(cudaFuncSetAttribute(k_descriptor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-    int grid = ctx->num_sms * 3;
+    int grid = ctx->num_sms * 6;
     SIFT_LAUNCH("k_descriptor", k_descriptor, grid, DESC_THREADS, dsm, wk->d_oct, wk->d_img, wk->arena, n_oct, n,
                 wk->refined, fs->d_count, wk->desc_cand, wk->desc_dir, dp, fs->d_desc, fs->d_coor);
   }
