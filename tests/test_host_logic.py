@@ -1,0 +1,69 @@
+"""CPU: host-side logic around the kernels (synthetic inputs, geometry set-up,
+byte model of bench.py)."""
+import numpy as np
+
+from openpano_b200 import synth
+from openpano_b200._abi import default_params
+
+
+def test_synth_is_deterministic_and_textured():
+    a = synth.make_canvas(120, 160, 5)
+    b = synth.make_canvas(120, 160, 5)
+    assert a.dtype == np.float32 and a.shape == (120, 160, 3)
+    assert np.array_equal(a, b)
+    assert a.min() >= 0 and a.max() <= 1 and a.std() > 0.1
+    assert not np.array_equal(a, synth.make_canvas(120, 160, 6))
+
+
+def test_stack_views_are_crops_of_one_canvas():
+    imgs, org = synth.make_stack(4, 100, 80, 30, 9)
+    assert org == [(0, 0), (30, 0), (60, 0), (90, 0)]
+    assert np.array_equal(imgs[0][:, 30:], imgs[1][:, :70])
+    imgs2, org2 = synth.make_stack(6, 50, 40, 20, 3, rows=2, step_y=15)
+    assert len(imgs2) == 6 and org2[3][1] == 15                 # serpentine second row
+
+
+def test_baseline_config_shapes():
+    for name, cfg in synth.CONFIGS.items():
+        assert cfg["n"] > 0 and cfg["w"] > 0 and cfg["h"] > 0
+    c = synth.CONFIGS["ordered_13x1500x1112"]
+    assert (c["n"], c["w"], c["h"]) == (13, 1500, 1112)
+
+
+def test_translation_blend_setup_matches_reference_convention(orc):
+    """The closed-form inverse map must send target pixel t to image pixel t - origin."""
+    imgs, org = synth.make_stack(3, 90, 60, 30, 11)
+    items, geom = synth.translation_blend_setup(org, 90, 60)
+    assert [it[:4] for it in items] == [(0, 0, 90, 60), (30, 0, 120, 60), (60, 0, 150, 60)]
+    out = orc.blend(imgs, items, geom, 0, default_params(lazy_read=0))
+    canvas = synth.make_canvas(60, 150, 11)
+    cov = out[..., 0] >= 0
+    assert cov.mean() > 0.9 and np.abs(out[cov] - canvas[:out.shape[0], :out.shape[1]][cov]).max() < 1e-5
+
+
+def test_octave_dims_match_the_oracle(orc):
+    import bench
+    for (w, h) in ((600, 400), (1500, 1112), (1300, 867), (4000, 3000), (333, 517)):
+        img = np.zeros((h, w, 3), np.float32)
+        tr = orc.sift_trace(img)
+        want = [tr.octave_size(o) for o in range(4)]
+        tr.close()
+        assert bench.octave_dims(w, h, default_params()) == want, (w, h)
+
+
+def test_survey_octave_sizes():
+    """exact working/octave sizes of the BASELINE configs."""
+    import bench
+    assert bench.octave_dims(1500, 1112, default_params()) == [(918, 681), (650, 482), (459, 341), (325, 241)]
+    assert bench.octave_dims(600, 400, default_params()) == [(960, 640), (679, 453), (480, 320), (340, 227)]
+
+
+def test_algorithmic_bytes_follow_survey_formula():
+    import bench
+    imgs = [np.zeros((1112, 1500, 3), np.float32)]
+    items = [(0, 0, 1500, 1112, [1, 0, 0, 0, 1, 0, 0, 0, 1])]
+    ab = bench.algorithmic_bytes(imgs, items, default_params(), [1800])
+    sp = 918 * 681 + 650 * 482 + 459 * 341 + 325 * 241
+    assert ab["k_blur_dog"] == sp * 4 * 13                      # grey in, 6 levels + 6 |DoG| out
+    assert ab["k_extrema_scan"] == sp * 24
+    assert ab["k_descriptor"] == 1800 * 528

@@ -1,0 +1,93 @@
+"""CPU: the plain-C oracle against the reference's own translation units
+(oracle/_ref, compiled from /root/reference/src) on inputs beyond the committed
+fixtures: other shapes, up-sampling, edge cases.  Skipped when oracle/_ref was
+not built (it needs the reference tree)."""
+import numpy as np
+import pytest
+
+from openpano_b200 import synth
+from openpano_b200._abi import default_params
+from tests import golden_util as gu
+
+
+def _same_trace(a, b, noct=4, nscale=7):
+    assert a.working_size() == b.working_size()
+    assert gu.same_bits(a.plane(0), b.plane(0))
+    for o in range(noct):
+        assert a.octave_size(o) == b.octave_size(o)
+        for l in range(nscale):
+            assert gu.same_bits(a.plane(1, o, l), b.plane(1, o, l)), (o, l)
+        for l in range(nscale - 1):
+            assert gu.same_bits(a.plane(2, o, l), b.plane(2, o, l)), (o, l)
+        for l in range(1, nscale):
+            assert gu.same_bits(a.plane(3, o, l), b.plane(3, o, l)), ("mag", o, l)
+            assert gu.same_bits(a.plane(4, o, l), b.plane(4, o, l)), ("ort", o, l)
+    for st in range(3):
+        assert a.points(st).tobytes() == b.points(st).tobytes(), st
+    ca, da = a.descriptors()
+    cb, db = b.descriptors()
+    assert gu.same_bits(ca, cb) and gu.same_bits(da, db)
+    return len(da)
+
+
+@pytest.mark.parametrize("w,h,seed", [(300, 200, 7), (200, 300, 8), (157, 211, 9)])
+def test_sift_every_stage(orc, ref, w, h, seed):
+    img = synth.make_canvas(h, w, seed)
+    a, b = orc.sift_trace(img), ref.sift_trace(img)
+    assert _same_trace(a, b) > 20
+    a.close(); b.close()
+
+
+def test_sift_other_params(orc, ref):
+    img = synth.make_canvas(180, 260, 31)
+    p = default_params(num_octave=3, num_scale=6, contrast_thres=3e-2, edge_ratio=10.0, sift_working_size=300)
+    a, b = orc.sift_trace(img, p), ref.sift_trace(img, p)
+    _same_trace(a, b, noct=3, nscale=6)
+    a.close(); b.close()
+
+
+def test_sift_flat_image(orc, ref):
+    img = np.full((120, 160, 3), 0.25, np.float32)
+    assert len(orc.sift_detect(img)[1]) == 0 and len(ref.sift_detect(img)[1]) == 0
+
+
+def test_match_ragged_and_ties(orc, ref):
+    rng = np.random.RandomState(3)
+    a = synth.rootsift_like(260, 5)
+    b = np.concatenate([a[:80], a[:80], a[150:]])                   # exact duplicates: zero-distance ties
+    noisy = (a[rng.permutation(260)][:200] + rng.randn(200, 128).astype(np.float32) * 36).astype(np.float32)
+    for x, y in ((a, b), (b, a), (a, noisy), (noisy, a), (a[:1], b), (b, a[:1]), (a[:2], a[:2])):
+        assert np.array_equal(orc.match(x, y), ref.match(x, y))
+
+
+@pytest.mark.parametrize("w,h,hf", [(200, 140, 1.0), (141, 173, 0.8), (160, 120, 1.3)])
+def test_cyl_warp(orc, ref, w, h, hf):
+    img = synth.make_canvas(h, w, 61)
+    k = np.array([[3.5, -2.25], [-60.0, 40.0]])
+    assert orc.cyl_warp_shape(w, h, hf) == ref.cyl_warp_shape(w, h, hf)
+    oa, ka = orc.cyl_warp(img, k, hf)
+    ob, kb = ref.cyl_warp(img, k, hf)
+    assert gu.same_bits(oa, ob) and gu.same_bits(ka, kb)
+
+
+@pytest.mark.parametrize("projection", [0, 1, 2])
+@pytest.mark.parametrize("bands", [0, 2])
+def test_blend_projections(orc, ref, projection, bands, capfd):
+    import math
+    imgs, org = synth.make_stack(3, 160, 110, 60, 71)
+    items = []
+    for k, (x, y) in enumerate(org):
+        if projection == 0:
+            th = 0.003 * (k - 1)
+            H = np.array([[math.cos(th), -math.sin(th), x - 80], [math.sin(th), math.cos(th), 2 * k], [1e-5 * k, -2e-5, 1.0]])
+        else:
+            f = 300.0
+            H = np.array([[1 / f, 0, (x - 80) / f], [0, 1 / f, 0.004 * k], [0, 0, 1]])
+        items.append((k * 60, 0, k * 60 + 160, 115, list(np.linalg.inv(H).ravel())))
+    res = 1.0 if projection == 0 else 1 / 300.0
+    pmin = (-80.0, -55.0) if projection == 0 else (-0.3, -0.2)
+    geom = dict(projection=projection, res_x=res, res_y=res, proj_min_x=pmin[0], proj_min_y=pmin[1])
+    a = orc.blend(imgs, items, geom, bands)
+    b = ref.blend(imgs, items, geom, bands)
+    assert (a >= 0).mean() > 0.3
+    assert gu.same_bits(a, b)
