@@ -114,29 +114,46 @@ class ClockSampler:
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
         self.samples = []
-        self._stop = threading.Event()
+        self._proc = None
         self._thr = None
+        self._t0 = self._t1 = None
 
     def _run(self):
-        while not self._stop.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
-            except Exception:
-                pass
-            self._stop.wait(0.15)
+        # one long-lived `nvidia-smi -lms 25` (a fresh process per sample costs > 100 ms)
+        for line in self._proc.stdout:
+            parts = [p.strip() for p in line.strip().split(",")]
+            if len(parts) >= 7:
+                self.samples.append((time.perf_counter(), parts))
+
+    def launch(self):
+        """Start the sampler process ahead of time; mark() / stop() bracket the timed region."""
+        try:
+            self._proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}",
+                                           "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE,
+                                          stderr=subprocess.DEVNULL, text=True)
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        except Exception:
+            self._proc = None
 
     def start(self):
-        self._thr = threading.Thread(target=self._run, daemon=True)
-        self._thr.start()
+        if self._proc is None:
+            self.launch()
+        self._t0 = time.perf_counter()
 
     def stop(self):
-        self._stop.set()
+        self._t1 = time.perf_counter()
+        time.sleep(0.05)
+        if self._proc is not None:
+            self._proc.terminate()
+            try:
+                self._proc.wait(timeout=3)
+            except Exception:
+                self._proc.kill()
         if self._thr:
-            self._thr.join(timeout=6)
+            self._thr.join(timeout=3)
+        inside = [p for (t, p) in self.samples if self._t0 <= t <= self._t1 + 0.03]
+        self.samples = inside if inside else [p for (_, p) in self.samples[-3:]]
         sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
         mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
         reasons = set()
@@ -204,7 +221,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bands", type=int, default=0, help="0 = LinearBlender (reference default), k = MultiBandBlender{k}")
@@ -273,6 +290,8 @@ def main():
         barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
+            sampler.launch()
+            time.sleep(0.3)                      # let nvidia-smi start sampling
             sampler.start()
         l0 = eng.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -293,7 +312,8 @@ def main():
         ms_per_step = ms_total / args.steps
         value = world * mpx / (ms_per_step / 1e3)
 
-        # ---- e2e: pinned host images in, host mosaic + matches out, every step
+        # ---- e2e: pinned host images in, host mosaic + matches out, every step.
+        # (a) one job at a time: Stitcher.build() — the latency of a single stitch
         d2h_bytes = out_w * out_h * 3 * 4
         for _ in range(2):
             st.build(host_ptrs, shapes, pairs, items, geom, host_out.data_ptr(), args.bands)
@@ -301,18 +321,48 @@ def main():
         barrier()
         t0 = time.perf_counter()
         nm_e2e = 0
-        for _ in range(args.steps):
+        n_lat = max(3, min(args.steps, 10))
+        for _ in range(n_lat):
             m = st.build(host_ptrs, shapes, pairs, items, geom, host_out.data_ptr(), args.bands)
             nm_e2e = sum(len(x) for x in m)
         torch.cuda.synchronize()
+        e2e_latency = (time.perf_counter() - t0) / n_lat
+        d2h_bytes += nm_e2e * 8 + len(imgs) * 8
+        assert float(host_out[out_h // 2, out_w // 2, 0]) >= 0.0      # the mosaic really came back
+        # (b) throughput: consecutive jobs pipelined (PipelinedStitcher): job i+1's H2D and
+        # job i-1's D2H overlap job i's kernels; every step still uploads its own inputs
+        # from pinned host memory and downloads its own mosaic + match lists.
+        from openpano_b200.stitcher import PipelinedStitcher
+        ps = PipelinedStitcher(local_rank, params, depth=3)
+        host_outs = [host_out, torch.empty_like(host_out).pin_memory(), torch.empty_like(host_out).pin_memory()]
+
+        def pipelined(n_jobs):
+            slot = ps.stage(host_ptrs, shapes, (out_w, out_h))
+            pending, total = None, 0
+            for i in range(n_jobs):
+                nxt = ps.stage(host_ptrs, shapes, (out_w, out_h)) if i + 1 < n_jobs else None
+                job = ps.run(slot, pairs, items, geom, host_outs[i % 3].data_ptr(), args.bands)
+                if pending is not None:
+                    total += sum(len(x) for x in ps.wait(pending))
+                pending, slot = job, nxt
+            total += sum(len(x) for x in ps.wait(pending))
+            return total
+
+        pipelined(3)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        nm_pipe = pipelined(args.steps)
+        torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
+        assert nm_pipe == args.steps * nm_e2e, (nm_pipe, nm_e2e)      # every job returned the same matches
+        assert float(host_outs[(args.steps - 1) % 3][out_h // 2, out_w // 2, 0]) >= 0.0
+        ps.close()
         t_e2e = torch.tensor([e2e_s], device="cuda")
         if world > 1:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         e2e_per_step = float(t_e2e.item()) / args.steps
         e2e_value = world * mpx / e2e_per_step
-        d2h_bytes += nm_e2e * 8 + len(imgs) * 8
-        assert float(host_out[out_h // 2, out_w // 2, 0]) >= 0.0      # the mosaic really came back
 
         # ---- roofline of the dominant kernel (event-timed per launch, separate untimed pass)
         roof = None
@@ -389,7 +439,10 @@ def main():
                        "match_rows_rescanned_exactly": int(exact_rows)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_per_step * 1e3},
+                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_per_step * 1e3,
+                    "mode": "PipelinedStitcher: consecutive jobs overlap H2D / kernels / D2H (depth 3)",
+                    "single_job_latency_ms": e2e_latency * 1e3,
+                    "single_job_value": world * mpx / e2e_latency},
             "gpu_launches": int(launches * world),
             "roofline": roof,
             "cpu_baseline": cpu,

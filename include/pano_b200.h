@@ -230,6 +230,22 @@ int pano_dev_download(pano_ctx* ctx, void* h_dst, const void* d_src, size_t byte
 int pano_dev_upload_async(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 int pano_dev_download_async(pano_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 
+/* Page-locked host memory (cudaHostAlloc) for buffers handed to the async copies
+ * and to pano_sift_detect_batch. */
+int pano_host_alloc(size_t bytes, void** h_ptr);
+int pano_host_free(void* h_ptr);
+
+/* Cross-context ordering.  Several contexts on one device (e.g. an upload ctx, a
+ * compute ctx and a download ctx, each with its own stream) can overlap copies
+ * with kernels: an event recorded on one ctx's stream can be waited for by
+ * another ctx's stream (device-side) or by the host. */
+typedef struct pano_event pano_event;
+int  pano_event_create(pano_ctx* ctx, pano_event** out);
+int  pano_event_record(pano_ctx* ctx, pano_event* ev);        /* on ctx's stream */
+int  pano_event_wait(pano_ctx* ctx, pano_event* ev);          /* ctx's stream waits (no host block) */
+int  pano_event_sync(pano_event* ev);                         /* host blocks until the event completed */
+void pano_event_destroy(pano_event* ev);
+
 /* ------------------------------------------------------ stage inspection
  * Parity-test hooks: run the SIFT chain on ONE host image and keep every
  * intermediate on the device so tests can compare each stage with the oracle

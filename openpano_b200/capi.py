@@ -77,6 +77,13 @@ def _load():
         "pano_dev_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
         "pano_dev_upload_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
         "pano_dev_download_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+        "pano_host_alloc": (C.c_int, [C.c_size_t, _vpp]),
+        "pano_host_free": (C.c_int, [C.c_void_p]),
+        "pano_event_create": (C.c_int, [C.c_void_p, _vpp]),
+        "pano_event_record": (C.c_int, [C.c_void_p, C.c_void_p]),
+        "pano_event_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
+        "pano_event_sync": (C.c_int, [C.c_void_p]),
+        "pano_event_destroy": (None, [C.c_void_p]),
         "pano_sift_trace_run": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, P, _vpp]),
         "pano_sift_trace_working_size": (C.c_int, [C.c_void_p, _ip, _ip]),
         "pano_sift_trace_octave_size": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip]),
@@ -281,6 +288,38 @@ class Engine:
 
     def dev_download_async(self, h_ptr, d_ptr, nbytes):
         self._check(LIB.pano_dev_download_async(self._h, C.c_void_p(h_ptr), C.c_void_p(d_ptr), nbytes))
+
+    @staticmethod
+    def host_alloc(nbytes):
+        p = C.c_void_p()
+        if LIB.pano_host_alloc(nbytes, C.byref(p)) != 0:
+            raise PanoError(-1, "pano_host_alloc failed")
+        return p.value
+
+    @staticmethod
+    def host_free(ptr):
+        LIB.pano_host_free(C.c_void_p(ptr))
+
+    # -- events (cross-context ordering)
+    def event_create(self):
+        e = C.c_void_p()
+        self._check(LIB.pano_event_create(self._h, C.byref(e)))
+        return e
+
+    def event_record(self, ev):
+        self._check(LIB.pano_event_record(self._h, ev))
+
+    def event_wait(self, ev):
+        self._check(LIB.pano_event_wait(self._h, ev))
+
+    @staticmethod
+    def event_sync(ev):
+        if LIB.pano_event_sync(ev) != 0:
+            raise PanoError(-1, "pano_event_sync failed")
+
+    @staticmethod
+    def event_destroy(ev):
+        LIB.pano_event_destroy(ev)
 
     # -- features
     def sift_detect_batch(self, imgs, params=None) -> FeatureSet:

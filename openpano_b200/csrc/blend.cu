@@ -276,11 +276,8 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
   cudaError_t e;
   if ((rc = ctx_alloc(ctx, (void**)&d_imgs, n * sizeof(BlendImg)))) goto done;
   if ((rc = ctx_alloc(ctx, (void**)&d_tab, std::max<size_t>(tab.size(), 1) * sizeof(double)))) goto done;
-  e = cudaMemcpyAsync(d_imgs, job.imgs.data(), n * sizeof(BlendImg), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess && !tab.empty())
-    e = cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
-  // job.imgs / tab are pageable: the copies above are staged synchronously by the runtime
-  if (e != cudaSuccess) { rc = ctx_cuda(ctx, e, "blend upload"); goto done; }
+  if ((rc = ctx_put(ctx, d_imgs, job.imgs.data(), n * sizeof(BlendImg)))) goto done;
+  if (!tab.empty() && (rc = ctx_put(ctx, d_tab, tab.data(), tab.size() * sizeof(double)))) goto done;
   job.g.projection = g->projection; job.g.res_x = g->res_x; job.g.res_y = g->res_y;
   job.g.min_x = g->proj_min_x; job.g.min_y = g->proj_min_y;
   job.g.col_sin = d_tab; job.g.col_cos = d_tab + ncol; job.g.row_tan = d_tab + 2 * ncol;
@@ -295,8 +292,7 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
       if ((rc = ctx_alloc(ctx, (void**)&d_tmp, roi * sizeof(float4)))) goto done;
       if ((rc = ctx_alloc(ctx, (void**)&d_mask, roi))) goto done;
       if ((rc = ctx_alloc(ctx, (void**)&d_tmask, (size_t)tw * th))) goto done;
-      e = cudaMemsetAsync(d_tmask, 0, (size_t)tw * th, ctx->stream);
-      if (e != cudaSuccess) { rc = ctx_cuda(ctx, e, "memset"); goto done; }
+      if ((rc = ctx_zero(ctx, d_tmask, (size_t)tw * th))) goto done;
       dim3 gr(ceil_div(job.max_rw, 32), ceil_div(job.max_rh, 8), n);
       BL_LAUNCH(ctx, "k_mb_first_level", k_mb_first_level, gr, b, d_imgs, job.g, d_cur, d_mask);
       BL_LAUNCH(ctx, "k_mb_weight_argmax", k_mb_weight_argmax, gt, b, d_imgs, n, d_cur, tw, th);

@@ -42,6 +42,13 @@ struct pano_ctx {
   size_t pinned_bytes = 0;
   void* pinned2 = nullptr;
   size_t pinned2_bytes = 0;
+  // pinned + device-mapped ring for small host<->device moves done by SM kernels
+  char* ring = nullptr;
+  size_t ring_cap = 0, ring_off = 0;
+  // recycled pinned blocks for per-featureset count read-backs (cudaHostAlloc / cudaFreeHost
+  // are slow and cudaFreeHost synchronises the whole device)
+  std::vector<std::pair<void*, size_t>> small_pinned;
+  std::vector<cudaEvent_t> sync_events;
 };
 
 int  ctx_fail(pano_ctx* ctx, int code, const char* fmt, ...);
@@ -51,6 +58,22 @@ int  ctx_alloc(pano_ctx* ctx, void** p, size_t bytes);
 void ctx_free(pano_ctx* ctx, void* p);
 void* ctx_pinned(pano_ctx* ctx, size_t bytes);   // staging buffer A (inputs)
 void* ctx_pinned2(pano_ctx* ctx, size_t bytes);  // staging buffer B (results)
+// Small host<->device moves that stay OFF the copy engines: a big image upload or
+// mosaic download queued on another stream of the same device would otherwise
+// delay every tiny metadata copy queued behind it on the same engine, and with it
+// the kernels that depend on it.  ctx_ring reserves space in a pinned, device-
+// mapped ring (valid until the ring wraps, which synchronises the stream);
+// ctx_fetch / ctx_store move words with a small kernel that addresses the host
+// memory directly (UVA); ctx_put = ring + memcpy + fetch; ctx_zero fills zeros.
+void* ctx_ring(pano_ctx* ctx, size_t bytes);
+void* ctx_small_pinned_get(pano_ctx* ctx, size_t bytes, size_t* cap);
+void ctx_small_pinned_put(pano_ctx* ctx, void* p, size_t cap);
+cudaEvent_t ctx_sync_event_get(pano_ctx* ctx);
+void ctx_sync_event_put(pano_ctx* ctx, cudaEvent_t e);
+int  ctx_fetch(pano_ctx* ctx, void* d_dst, const void* h_pinned_src, size_t bytes);
+int  ctx_store(pano_ctx* ctx, void* h_pinned_dst, const void* d_src, size_t bytes);
+int  ctx_put(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int  ctx_zero(pano_ctx* ctx, void* d_dst, size_t bytes);
 void ctx_prof_begin(pano_ctx* ctx, const char* name);
 void ctx_prof_end(pano_ctx* ctx);
 

@@ -24,6 +24,7 @@ int ctx_cuda(pano_ctx* ctx, cudaError_t e, const char* what) {
 
 int ctx_alloc(pano_ctx* ctx, void** p, size_t bytes) {
   *p = nullptr;
+  bytes = (bytes + 15) / 16 * 16;      // word-granular helper kernels may touch the padding
   if (bytes == 0) bytes = 16;
   cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
   if (e != cudaSuccess) return ctx_cuda(ctx, e, "cudaMallocAsync");
@@ -49,6 +50,81 @@ void* ctx_pinned2(pano_ctx* ctx, size_t bytes) {
   // metadata staging is reused across calls: wait for earlier async copies
   if (ctx->pinned2) cudaStreamSynchronize(ctx->stream);
   return grow_pinned(&ctx->pinned2, &ctx->pinned2_bytes, bytes);
+}
+
+// ---- copy-engine-free small moves
+__global__ void k_copy_u32(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void k_zero_u32(uint32_t* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = 0u;
+}
+
+void* ctx_ring(pano_ctx* ctx, size_t bytes) {
+  bytes = (bytes + 63) / 64 * 64;
+  if (!ctx->ring || bytes > ctx->ring_cap) {
+    if (ctx->ring) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->ring); ctx->ring = nullptr; }
+    size_t cap = std::max(bytes * 2, (size_t)8 << 20);
+    if (cudaHostAlloc((void**)&ctx->ring, cap, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { ctx->ring = nullptr; ctx->ring_cap = 0; return nullptr; }
+    ctx->ring_cap = cap; ctx->ring_off = 0;
+  }
+  if (ctx->ring_off + bytes > ctx->ring_cap) {   // wrap: everything queued so far must have consumed its slice
+    cudaStreamSynchronize(ctx->stream);
+    ctx->ring_off = 0;
+  }
+  void* p = ctx->ring + ctx->ring_off;
+  ctx->ring_off += bytes;
+  return p;
+}
+
+void* ctx_small_pinned_get(pano_ctx* ctx, size_t bytes, size_t* cap) {
+  for (size_t i = 0; i < ctx->small_pinned.size(); ++i)
+    if (ctx->small_pinned[i].second >= bytes) {
+      void* p = ctx->small_pinned[i].first; *cap = ctx->small_pinned[i].second;
+      ctx->small_pinned.erase(ctx->small_pinned.begin() + i);
+      return p;
+    }
+  void* p = nullptr;
+  size_t want = std::max<size_t>((bytes + 255) / 256 * 256, 1024);
+  if (cudaHostAlloc(&p, want, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+  *cap = want;
+  return p;
+}
+void ctx_small_pinned_put(pano_ctx* ctx, void* p, size_t cap) { if (p) ctx->small_pinned.emplace_back(p, cap); }
+cudaEvent_t ctx_sync_event_get(pano_ctx* ctx) {
+  if (!ctx->sync_events.empty()) { cudaEvent_t e = ctx->sync_events.back(); ctx->sync_events.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  return e;
+}
+void ctx_sync_event_put(pano_ctx* ctx, cudaEvent_t e) { if (e) ctx->sync_events.push_back(e); }
+
+static unsigned small_grid(size_t words) { return (unsigned)std::min<size_t>(std::max<size_t>((words + 255) / 256, 1), 256); }
+
+int ctx_fetch(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  if (!bytes) return PANO_OK;
+  const size_t words = (bytes + 3) / 4;
+  PANO_LAUNCH(ctx, "k_copy_u32", k_copy_u32, small_grid(words), 256, 0, (uint32_t*)d_dst, (const uint32_t*)h_src, words);
+  return PANO_OK;
+}
+int ctx_store(pano_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  if (!bytes) return PANO_OK;
+  const size_t words = (bytes + 3) / 4;
+  PANO_LAUNCH(ctx, "k_copy_u32", k_copy_u32, small_grid(words), 256, 0, (uint32_t*)h_dst, (const uint32_t*)d_src, words);
+  return PANO_OK;
+}
+int ctx_put(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  if (!bytes) return PANO_OK;
+  void* st = ctx_ring(ctx, bytes + 4);
+  if (!st) return ctx_fail(ctx, PANO_ERR_CUDA, "pinned ring allocation failed");
+  memcpy(st, h_src, bytes);
+  return ctx_fetch(ctx, d_dst, st, bytes);
+}
+int ctx_zero(pano_ctx* ctx, void* d_dst, size_t bytes) {
+  if (!bytes) return PANO_OK;
+  const size_t words = (bytes + 3) / 4;
+  PANO_LAUNCH(ctx, "k_zero_u32", k_zero_u32, small_grid(words), 256, 0, (uint32_t*)d_dst, words);
+  return PANO_OK;
 }
 
 static cudaEvent_t get_event(pano_ctx* ctx) {
@@ -138,6 +214,9 @@ void pano_destroy(pano_ctx* ctx) {
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->pinned2) cudaFreeHost(ctx->pinned2);
+  if (ctx->ring) cudaFreeHost(ctx->ring);
+  for (auto& sp : ctx->small_pinned) cudaFreeHost(sp.first);
+  for (auto e : ctx->sync_events) cudaEventDestroy(e);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -204,6 +283,44 @@ int pano_dev_download_async(pano_ctx* ctx, void* h_dst, const void* d_src, size_
   return PANO_OK;
 }
 
+int pano_host_alloc(size_t bytes, void** h_ptr) {
+  if (!h_ptr) return PANO_ERR_INVALID;
+  *h_ptr = nullptr;
+  return cudaHostAlloc(h_ptr, bytes ? bytes : 16, cudaHostAllocPortable) == cudaSuccess ? PANO_OK : PANO_ERR_CUDA;
+}
+int pano_host_free(void* h_ptr) { return cudaFreeHost(h_ptr) == cudaSuccess ? PANO_OK : PANO_ERR_CUDA; }
+
+struct pano_event { cudaEvent_t ev; int device; };
+
+int pano_event_create(pano_ctx* ctx, pano_event** out) {
+  if (!ctx || !out) return PANO_ERR_INVALID;
+  pano_event* e = new pano_event;
+  e->device = ctx->device;
+  cudaError_t err = cudaEventCreateWithFlags(&e->ev, cudaEventDisableTiming);
+  if (err != cudaSuccess) { delete e; return ctx_cuda(ctx, err, "cudaEventCreate"); }
+  *out = e;
+  return PANO_OK;
+}
+int pano_event_record(pano_ctx* ctx, pano_event* ev) {
+  if (!ctx || !ev) return PANO_ERR_INVALID;
+  PANO_CUDA(ctx, cudaEventRecord(ev->ev, ctx->stream));
+  return PANO_OK;
+}
+int pano_event_wait(pano_ctx* ctx, pano_event* ev) {
+  if (!ctx || !ev) return PANO_ERR_INVALID;
+  PANO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev->ev, 0));
+  return PANO_OK;
+}
+int pano_event_sync(pano_event* ev) {
+  if (!ev) return PANO_ERR_INVALID;
+  return cudaEventSynchronize(ev->ev) == cudaSuccess ? PANO_OK : PANO_ERR_CUDA;
+}
+void pano_event_destroy(pano_event* ev) {
+  if (!ev) return;
+  cudaEventDestroy(ev->ev);
+  delete ev;
+}
+
 // ---------------------------------------------------------------- features
 
 static void featureset_release(pano_featureset* fs) {
@@ -213,8 +330,8 @@ static void featureset_release(pano_featureset* fs) {
     ctx_free(ctx, fs->d_desc); ctx_free(ctx, fs->d_coor); ctx_free(ctx, fs->d_count);
     tc_release(ctx, &fs->tc);
   }
-  if (fs->counts_ready) cudaEventDestroy(fs->counts_ready);
-  if (fs->h_count_pinned) cudaFreeHost(fs->h_count_pinned);
+  if (fs->counts_ready) { if (ctx) ctx_sync_event_put(ctx, fs->counts_ready); else cudaEventDestroy(fs->counts_ready); }
+  if (fs->h_count_pinned) { if (ctx) ctx_small_pinned_put(ctx, fs->h_count_pinned, fs->h_count_cap); else cudaFreeHost(fs->h_count_pinned); }
   delete fs;
 }
 

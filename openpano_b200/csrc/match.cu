@@ -222,10 +222,15 @@ k_exact_rows(const float* __restrict__ desc, const SideMeta* __restrict__ sides,
     int idx = 0x7fffffff;
     for (int c = tid; c < sm.t_n; c += 256) {
       const float4* pb = (const float4*)(desc + (size_t)(sm.t_base + c) * 128);
+      // the whole 512-byte target row is requested before any arithmetic: the kernel
+      // is load-latency bound, so all 32 loads of a row must be in flight together
+      float4 yv[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) yv[k] = __ldg(pb + k);
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll 8
+#pragma unroll
       for (int k = 0; k < 32; ++k) {
-        float4 x = *(const float4*)(&sq[k * 4]), y = __ldg(pb + k);
+        const float4 x = *(const float4*)(&sq[k * 4]), y = yv[k];
         float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
         l0 += d0 * d0; l1 += d1 * d1; l2 += d2 * d2; l3 += d3 * d3;
       }
@@ -388,16 +393,10 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
       (rc = ctx_alloc(ctx, (void**)&b.counters, 4 * sizeof(int))) ||
       (rc = ctx_alloc(ctx, (void**)&b.out, std::max<long long>(pl.out_total, 1) * sizeof(int))))
     return rc;
-  char* stg = (char*)ctx_pinned2(ctx, bt + bp + bs + 64);
-  if (!stg) return ctx_fail(ctx, PANO_ERR_CUDA, "pinned alloc failed");
   const void* tsrc = tensor ? (const void*)pl.tc_tasks.data() : (const void*)pl.exact_tasks.data();
-  if (bt) memcpy(stg, tsrc, bt);
-  if (bp) memcpy(stg + bt, pl.pairs.data(), bp);
-  if (bs) memcpy(stg + bt + bp, pl.sides.data(), bs);
-  if (bt) PANO_CUDA(ctx, cudaMemcpyAsync(b.tasks, stg, bt, cudaMemcpyHostToDevice, ctx->stream));
-  if (bp) PANO_CUDA(ctx, cudaMemcpyAsync(b.pairs, stg + bt, bp, cudaMemcpyHostToDevice, ctx->stream));
-  if (bs) PANO_CUDA(ctx, cudaMemcpyAsync(b.sides, stg + bt + bp, bs, cudaMemcpyHostToDevice, ctx->stream));
-  PANO_CUDA(ctx, cudaMemsetAsync(b.counters, 0, 4 * sizeof(int), ctx->stream));
+  if ((rc = ctx_put(ctx, b.tasks, tsrc, bt)) || (rc = ctx_put(ctx, b.pairs, pl.pairs.data(), bp)) ||
+      (rc = ctx_put(ctx, b.sides, pl.sides.data(), bs)) || (rc = ctx_zero(ctx, b.counters, 4 * sizeof(int))))
+    return rc;
   if (pl.pairs.empty()) return PANO_OK;
   const float rs = ratio * ratio;
   dim3 gd(std::max(1, ceil_div(pl.max_small, 256)), (unsigned)pl.pairs.size());
@@ -479,11 +478,14 @@ int pano_match_pairs(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int*
   int rc = match_common(ctx, fs, n_pairs, ij, p, pl, b);
   if (rc) { free_buffers(ctx, b, false); return rc; }
   std::vector<int> h_out(std::max<long long>(pl.out_total, 1));
-  cudaError_t e = cudaSuccess;
-  if (pl.out_total) e = cudaMemcpyAsync(h_out.data(), b.out, pl.out_total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  int* h_stage = (int*)ctx_ring(ctx, (size_t)std::max<long long>(pl.out_total, 1) * sizeof(int));
+  if (!h_stage) { free_buffers(ctx, b, false); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned ring allocation failed"); }
+  rc = ctx_store(ctx, h_stage, b.out, pl.out_total * sizeof(int));
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
   free_buffers(ctx, b, false);
+  if (rc) return rc;
   if (e != cudaSuccess) return ctx_cuda(ctx, e, "match download");
+  if (pl.out_total) memcpy(h_out.data(), h_stage, pl.out_total * sizeof(int));
   out->n_pairs = n_pairs;
   out->count = (int*)calloc(std::max(n_pairs, 1), sizeof(int));
   out->offset = (int*)calloc(n_pairs + 1, sizeof(int));
@@ -525,10 +527,12 @@ int pano_match_pairs_dev(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const 
   MatchBuffers b;
   int rc = match_common(ctx, fs, n_pairs, ij, p, pl, b);
   if (rc) { free_buffers(ctx, b, false); return rc; }
-  int h[4] = {0, 0, 0, 0};
-  cudaError_t e = cudaMemcpyAsync(h, b.counters, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  int* h = (int*)ctx_ring(ctx, 4 * sizeof(int));
+  if (!h) { free_buffers(ctx, b, false); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned ring allocation failed"); }
+  rc = ctx_store(ctx, h, b.counters, 4 * sizeof(int));
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
   free_buffers(ctx, b, false);
+  if (rc) return rc;
   if (e != cudaSuccess) return ctx_cuda(ctx, e, "match total download");
   *total_matches = h[0];
   ctx->last_match_exact_rows = h[1] + h[2];

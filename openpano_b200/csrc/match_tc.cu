@@ -318,8 +318,8 @@ int tc_prepare(pano_ctx* ctx, const float* d_desc, const std::vector<TcImage>& i
       (rc = ctx_alloc(ctx, (void**)&ops->qbuf, (size_t)std::max<long long>(blocks, 1) * TC_BLOCK_BYTES)) ||
       (rc = ctx_alloc(ctx, (void**)&ops->tbuf, (size_t)std::max<long long>(blocks, 1) * TC_BLOCK_BYTES)))
     return rc;
-  PANO_CUDA(ctx, cudaMemcpyAsync(ops->d_imgs, imgs.data(), n * sizeof(TcImage), cudaMemcpyHostToDevice, ctx->stream));
-  PANO_CUDA(ctx, cudaMemsetAsync(ops->d_maxnorm, 0, sizeof(unsigned), ctx->stream));
+  if ((rc = ctx_put(ctx, ops->d_imgs, imgs.data(), n * sizeof(TcImage)))) return rc;
+  if ((rc = ctx_zero(ctx, ops->d_maxnorm, sizeof(unsigned)))) return rc;
   if (max_pad == 0) return PANO_OK;
   dim3 g1(ceil_div(max_pad, 128), n);
   PANO_LAUNCH(ctx, "k_tc_maxnorm", k_tc_maxnorm, g1, 128, 0, d_desc, ops->d_imgs, n, ops->d_norms, ops->d_maxnorm);

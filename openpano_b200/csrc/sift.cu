@@ -992,16 +992,18 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
   // metadata upload through the pinned staging buffer
   {
     size_t b_img = n * sizeof(ImgMeta), b_oct = wk->h_oct.size() * sizeof(OctMeta), b_t = tiles.size() * sizeof(BlurTile);
-    char* st = (char*)ctx_pinned2(ctx, b_img + b_oct + b_t);
+    char* st = (char*)ctx_ring(ctx, b_img + b_oct + b_t + 192);
     if (!st) { sift_work_free(ctx, wk); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned alloc failed"); }
+    char* st_oct = st + align_up(b_img, 64);
+    char* st_t = st_oct + align_up(b_oct, 64);
     memcpy(st, wk->h_img.data(), b_img);
-    memcpy(st + b_img, wk->h_oct.data(), b_oct);
-    memcpy(st + b_img + b_oct, tiles.data(), b_t);
-    SIFT_CUDA(cudaMemcpyAsync(wk->d_img, st, b_img, cudaMemcpyHostToDevice, ctx->stream));
-    SIFT_CUDA(cudaMemcpyAsync(wk->d_oct, st + b_img, b_oct, cudaMemcpyHostToDevice, ctx->stream));
-    SIFT_CUDA(cudaMemcpyAsync(wk->d_tiles, st + b_img + b_oct, b_t, cudaMemcpyHostToDevice, ctx->stream));
+    memcpy(st_oct, wk->h_oct.data(), b_oct);
+    memcpy(st_t, tiles.data(), b_t);
+    SIFT_TRY(ctx_fetch(ctx, wk->d_img, st, b_img));
+    SIFT_TRY(ctx_fetch(ctx, wk->d_oct, st_oct, b_oct));
+    SIFT_TRY(ctx_fetch(ctx, wk->d_tiles, st_t, b_t));
   }
-  SIFT_CUDA(cudaMemsetAsync(wk->cand_count, 0, n * sizeof(int), ctx->stream));
+  SIFT_TRY(ctx_zero(ctx, wk->cand_count, n * sizeof(int)));
 
 #define SIFT_LAUNCH(name, kernel, grid, block, smem, ...)                                   \
   do {                                                                                      \
@@ -1062,10 +1064,13 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
   wk->n_desc = fs->d_count;
 
   // counts to the host (pinned, async); consumers wait on counts_ready
-  if (!fs->h_count_pinned) SIFT_CUDA(cudaMallocHost((void**)&fs->h_count_pinned, (size_t)2 * n * sizeof(int)));
-  SIFT_CUDA(cudaMemcpyAsync(fs->h_count_pinned, fs->d_count, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  SIFT_CUDA(cudaMemcpyAsync(fs->h_count_pinned + n, wk->cand_count, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  if (!fs->counts_ready) SIFT_CUDA(cudaEventCreateWithFlags(&fs->counts_ready, cudaEventDisableTiming));
+  if (!fs->h_count_pinned) {
+    fs->h_count_pinned = (int*)ctx_small_pinned_get(ctx, (size_t)2 * n * sizeof(int) + 16, &fs->h_count_cap);
+    if (!fs->h_count_pinned) { sift_work_free(ctx, wk); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned allocation failed"); }
+  }
+  SIFT_TRY(ctx_store(ctx, fs->h_count_pinned, fs->d_count, n * sizeof(int)));
+  SIFT_TRY(ctx_store(ctx, fs->h_count_pinned + n, wk->cand_count, n * sizeof(int)));
+  if (!fs->counts_ready) fs->counts_ready = ctx_sync_event_get(ctx);
   SIFT_CUDA(cudaEventRecord(fs->counts_ready, ctx->stream));
   fs->counts_on_host = false;
 

@@ -73,6 +73,7 @@ struct pano_featureset {
   bool counts_on_host = false;
   cudaEvent_t counts_ready = nullptr;
   int* h_count_pinned = nullptr;
+  size_t h_count_cap = 0;
   TcOperands tc;              // fp16 tensor-core operands of the descriptors (lazy)
   bool tc_ready = false;
 };

@@ -114,3 +114,101 @@ class Stitcher:
         m = self.build([im.ctypes.data for im in imgs], [im.shape[:2] for im in imgs], pairs, items, geom,
                        out.ctypes.data, bands)
         return m, out
+
+
+class PipelinedStitcher:
+    """Throughput form of Stitcher.build(): consecutive stitch jobs overlap on the
+    device.  Three contexts share the GPU — upload, compute and download, each with
+    its own stream — ordered by events, so job i+1's images cross PCIe while job i
+    runs SIFT/match/blend and job i-1's mosaic streams back (PCIe is full duplex).
+
+        slot = ps.stage(host_ptrs, shapes, out_wh)     # enqueue the H2D copies
+        job  = ps.run(slot, pairs, items, geom, out_host_ptr)   # compute + enqueue D2H
+        matches = ps.wait(job)                          # host mosaic + matches ready
+
+    Call stage() for the NEXT job before run() of the current one: run() blocks the
+    host while the match lists come back, and that is when the next upload flies.
+    """
+
+    def __init__(self, device: int, params=None, depth: int = 2):
+        self.params = params or default_params()
+        self.up = Engine(device)
+        self.cmp = Engine(device)
+        self.dn = Engine(device)
+        self.depth = depth
+        self.slots = [dict(imgs=None, out=None, shapes=None, offs=None, out_wh=None,
+                           ev_up=self.up.event_create(), ev_cmp=self.cmp.event_create(),
+                           ev_dn=self.dn.event_create(), busy=False) for _ in range(depth)]
+        self._next = 0
+
+    def _ensure(self, s, shapes, out_wh):
+        if s["shapes"] != shapes:
+            if s["imgs"]:
+                self.cmp.dev_free(s["imgs"])
+            offs, total = [], 0
+            for (h, w) in shapes:
+                offs.append(total)
+                total += (h * w * 3 * 4 + 255) // 256 * 256
+            s["imgs"] = self.cmp.dev_alloc(max(total, 256))
+            s["shapes"], s["offs"] = list(shapes), offs
+        if s["out_wh"] != out_wh:
+            if s["out"]:
+                self.cmp.dev_free(s["out"])
+            s["out"] = self.cmp.dev_alloc(max(out_wh[0] * out_wh[1] * 3 * 4, 256))
+            s["out_wh"] = tuple(out_wh)
+            self.cmp.sync()
+
+    def stage(self, host_ptrs, shapes, out_wh) -> int:
+        k = self._next
+        self._next = (self._next + 1) % self.depth
+        s = self.slots[k]
+        if s["busy"]:
+            Engine.event_sync(s["ev_dn"])          # the slot's previous job has fully left the device
+            s["busy"] = False
+        self._ensure(s, list(shapes), tuple(out_wh))
+        self.up.event_wait(s["ev_cmp"])            # its previous compute no longer reads these images
+        for p, o, (h, w) in zip(host_ptrs, s["offs"], shapes):
+            self.up.dev_upload_async(s["imgs"] + o, p, h * w * 3 * 4)
+        self.up.event_record(s["ev_up"])
+        return k
+
+    def run(self, k: int, pairs, items, geom, out_host_ptr, bands: int = 0):
+        s = self.slots[k]
+        shapes = s["shapes"]
+        ptrs = [s["imgs"] + o for o in s["offs"]]
+        self.cmp.event_wait(s["ev_up"])
+        fs = self.cmp.sift_detect_batch_ptr(ptrs, [q[1] for q in shapes], [q[0] for q in shapes], self.params,
+                                            device=True)
+        matches = self.cmp.match_pairs(fs, pairs, self.params)       # host waits here; copies keep flowing
+        self.cmp.event_wait(s["ev_dn"])                               # previous mosaic of this slot is out
+        self.cmp.blend_dev(ptrs, shapes, items, geom, s["out"], s["out_wh"][0], s["out_wh"][1], bands, self.params)
+        self.cmp.event_record(s["ev_cmp"])
+        fs.free()
+        self.dn.event_wait(s["ev_cmp"])
+        self.dn.dev_download_async(out_host_ptr, s["out"], s["out_wh"][0] * s["out_wh"][1] * 3 * 4)
+        self.dn.event_record(s["ev_dn"])
+        s["busy"] = True
+        return (k, matches)
+
+    def wait(self, job):
+        k, matches = job
+        Engine.event_sync(self.slots[k]["ev_dn"])
+        self.slots[k]["busy"] = False
+        return matches
+
+    def close(self):
+        for e in (self.up, self.cmp, self.dn):
+            try:
+                e.sync()
+            except Exception:
+                pass
+        for s in self.slots:
+            if s["imgs"]:
+                self.cmp.dev_free(s["imgs"])
+            if s["out"]:
+                self.cmp.dev_free(s["out"])
+            for key in ("ev_up", "ev_cmp", "ev_dn"):
+                Engine.event_destroy(s[key])
+        self.slots = []
+        for e in (self.up, self.cmp, self.dn):
+            e.close()
