@@ -181,9 +181,37 @@ def load_cpu_checker():
     return get_checker("orc"), "port"
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 when it is unset; the reference's OpenMP
+    path must get every host core (set before libgomp initialises)."""
+    if os.environ.get("OMP_NUM_THREADS", "") in ("", "1") or "TORCHELASTIC_RUN_ID" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+
+
+def bind_to_gpu_numa_node(local_rank: int):
+    """Best effort: run this rank (and allocate its pinned buffers) on the CPUs
+    local to its GPU so H2D/D2H do not cross sockets."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        txt = Path(f"/sys/bus/pci/devices/{bus}/local_cpulist").read_text().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    use_all_host_threads()
     imgs, pairs, items, geom, params, mpx = make_workload(0, args.bands)
     chk, kind = load_cpu_checker()
     devnull = os.open(os.devnull, os.O_WRONLY)
@@ -247,6 +275,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else 0
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -408,6 +437,7 @@ def main():
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             try:
+                use_all_host_threads()
                 chk, kind = load_cpu_checker()
                 devnull = os.open(os.devnull, os.O_WRONLY)
                 saved = os.dup(1)
@@ -433,7 +463,7 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "images": len(imgs), "image_wh": [imgs[0].shape[1], imgs[0].shape[0]],
                        "pairs": len(pairs), "bands": args.bands, "blend": "linear" if args.bands == 0 else "multiband",
-                       "geometry": "generator-known homographies (flat projection)", "parallelism": f"dp{world}",
+                       "geometry": "generator-known homographies (flat projection)", "parallelism": f"dp{world}", "cpu_affinity_cpus": numa_cpus,
                        "l2_policy": "inputs_exceed_l2 (260 MB of images + 0.9 GB pyramid arena per step)",
                        "features": int(sum(counts)), "matches": int(n_matches),
                        "match_rows_rescanned_exactly": int(exact_rows)},
