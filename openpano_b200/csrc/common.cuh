@@ -35,7 +35,8 @@ struct pano_ctx {
   std::vector<cudaEvent_t> event_pool;
   std::map<std::string, std::pair<int, double>> prof_acc;  // name -> (launches, ms)
   long long launches = 0;
-  int last_match_exact_rows = 0;   // rows the last match call had to re-scan exactly
+  int last_match_exact_rows = 0;   // rows the last match call had to decide exactly (gathered pass)
+  int last_match_full_rescans = 0; // of those, rows that needed a scan of every target
   int num_sms = 148;
   // pinned host staging (grown on demand)
   void* pinned = nullptr;

@@ -265,10 +265,18 @@ struct PairMeta {
 
 // Decision per row k of the smaller set (matcher.cc:49-66) from certified
 // intervals; rows that cannot be decided request exact re-scans and stay pending.
+// Requests go to per-side lists (list_rows[side.res_off + slot], side_cnt[side]) so
+// that the gathered second tensor pass can batch the rows of one side together.
+__device__ __forceinline__ void request_row(const SideMeta* __restrict__ sides, RowInfo* __restrict__ info, int side,
+                                            int row, int* __restrict__ list_rows, int* __restrict__ side_cnt) {
+  const long long off = sides[side].res_off;
+  if (atomicExch(&info[off + row].requested, 1) == 0) list_rows[off + atomicAdd(&side_cnt[side], 1)] = row;
+}
+
 __global__ void k_match_decide(const PairMeta* __restrict__ pairs, const SideMeta* __restrict__ sides,
                                RowInfo* __restrict__ info, float ratio_sqr, int first_round,
                                int* __restrict__ out, int* __restrict__ total,
-                               int2* __restrict__ list, int* __restrict__ list_count) {
+                               int* __restrict__ list_rows, int* __restrict__ side_cnt) {
   const PairMeta pm = pairs[blockIdx.y];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= pm.n_small) return;
@@ -283,8 +291,7 @@ __global__ void k_match_decide(const PairMeta* __restrict__ pairs, const SideMet
       if (r.mn > ratio_sqr * r.sec_hi) result = -1;
       else {
         result = OUT_PENDING;
-        if (atomicExch(&info[ss.res_off + k].requested, 1) == 0)
-          list[atomicAdd(list_count, 1)] = make_int2(pm.side_small, k);
+        request_row(sides, info, pm.side_small, k, list_rows, side_cnt);
       }
     } else {
       const RowInfo c = info[sl.res_off + r.idx];
@@ -303,15 +310,81 @@ __global__ void k_match_decide(const PairMeta* __restrict__ pairs, const SideMet
       else if (!(r.mn > ratio_sqr * nlo)) result = r.idx;    // accepted for every admissible next_min
       else {
         result = OUT_PENDING;
-        if (!(r.state & 1) && atomicExch(&info[ss.res_off + k].requested, 1) == 0)
-          list[atomicAdd(list_count, 1)] = make_int2(pm.side_small, k);
-        if (need_c && atomicExch(&info[sl.res_off + r.idx].requested, 1) == 0)
-          list[atomicAdd(list_count, 1)] = make_int2(pm.side_large, r.idx);
+        if (!(r.state & 1)) request_row(sides, info, pm.side_small, k, list_rows, side_cnt);
+        if (need_c) request_row(sides, info, pm.side_large, r.idx, list_rows, side_cnt);
       }
     }
   }
   out[oslot] = result;
   if (result >= 0) atomicAdd(total, 1);
+}
+
+// Plans the gathered second tensor pass: every side with requested rows gets
+// ceil(cnt/128) gather blocks = filter tasks.  A side that does not fit in the
+// block budget sends its rows to the full re-scan list instead.
+__global__ void k_gather_plan(const TcGatherSide* __restrict__ gsides, int n_sides, const int* __restrict__ side_cnt,
+                              const int* __restrict__ list_rows, int block_cap, TcTask* __restrict__ tasks,
+                              int* __restrict__ n_blocks, int2* __restrict__ fb_list, int* __restrict__ fb_cnt) {
+  const int side = blockIdx.x * blockDim.x + threadIdx.x;
+  if (side >= n_sides) return;
+  const int cnt = side_cnt[side];
+  if (cnt == 0) return;
+  const TcGatherSide gs = gsides[side];
+  const int nb = (cnt + 127) / 128;
+  const int b0 = atomicAdd(n_blocks, nb);
+  if (b0 + nb > block_cap) {
+    atomicSub(n_blocks, nb);
+    const int f0 = atomicAdd(fb_cnt, cnt);
+    for (int i = 0; i < cnt; ++i) fb_list[f0 + i] = make_int2(side, list_rows[gs.list_off + i]);
+    return;
+  }
+  for (int i = 0; i < nb; ++i) {
+    TcTask t;
+    t.q_blk = b0 + i; t.q_row0 = (b0 + i) * 128; t.q_n = min(128, cnt - i * 128);
+    t.t_blk0 = gs.t_blk0; t.t_blocks = gs.t_blocks; t.t_n = gs.t_n; t.t_pad = i * 128;
+    t.res_off = side;
+    tasks[b0 + i] = t;
+  }
+}
+
+// Exact decision among the candidate columns the filter pass listed for a row: one
+// warp per gathered row, one lane per candidate.  The candidate set provably holds
+// the true best and second best (every column scoring within 2*eps of the
+// approximate second best is in it); rows that overflowed their slots go to the
+// full re-scan list.
+__global__ void __launch_bounds__(256)
+k_exact_cands(const float* __restrict__ desc, const SideMeta* __restrict__ sides, const int* __restrict__ n_blocks,
+              const int2* __restrict__ g_meta, const int* __restrict__ cand_cnt, const int* __restrict__ cand,
+              RowInfo* __restrict__ info, int2* __restrict__ fb_list, int* __restrict__ fb_cnt) {
+  const int lane = threadIdx.x & 31;
+  const int nrow = *n_blocks * 128;
+  for (int g = blockIdx.x * 8 + (threadIdx.x >> 5); g < nrow; g += gridDim.x * 8) {
+    const int2 me = g_meta[g];
+    if (me.x < 0) continue;
+    const SideMeta sm = sides[me.x];
+    const int cnt = cand_cnt[g];
+    if (cnt > TC_CAND_CAP || cnt < 1 || (cnt < 2 && sm.t_n >= 2)) {
+      if (lane == 0) fb_list[atomicAdd(fb_cnt, 1)] = me;
+      continue;
+    }
+    float mn = FLT_MAX, sec = FLT_MAX;
+    int idx = 0x7fffffff;
+    if (lane < cnt) {
+      idx = cand[(size_t)g * TC_CAND_CAP + lane];
+      mn = exact_dist(desc + (size_t)(sm.q_base + me.y) * 128, desc + (size_t)(sm.t_base + idx) * 128);
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      float m2 = __shfl_xor_sync(0xffffffffu, mn, off);
+      float s2 = __shfl_xor_sync(0xffffffffu, sec, off);
+      int i2 = __shfl_xor_sync(0xffffffffu, idx, off);
+      top2_merge(mn, idx, sec, m2, i2, s2);
+    }
+    if (lane == 0) {
+      RowInfo o; o.mn = mn; o.mn_hi = mn; o.idx = idx; o.sec_lo = sec; o.sec_hi = sec; o.state = 3; o.requested = 1; o.pad = 0;
+      info[sm.res_off + me.y] = o;
+    }
+  }
 }
 
 // ------------------------------------------------------------------ host driver
@@ -321,6 +394,7 @@ struct MatchPlan {
   std::vector<PairMeta> pairs;
   std::vector<MatchTask> exact_tasks;   // exact path
   std::vector<TcTask> tc_tasks;         // tensor path
+  std::vector<TcGatherSide> gsides;     // tensor path: per side, for the gathered second pass
   std::vector<char> rev;                // pair was swapped (first image is the larger set)
   long long res_total = 0, out_total = 0;
   int max_side_n = 0, max_small = 0;
@@ -354,10 +428,12 @@ static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int
       const TcImage &ts = (*tcimgs)[is], &tl = (*tcimgs)[il];
       if (nl > 0)
         for (int r0 = 0; r0 < ns; r0 += 128)
-          pl.tc_tasks.push_back(TcTask{ts.blk0 + r0 / 128, r0, ns, tl.blk0, tl.n_pad / 128, a.res_off});
+          pl.tc_tasks.push_back(TcTask{ts.blk0 + r0 / 128, r0, ns, tl.blk0, tl.n_pad / 128, nl, 0, a.res_off});
       if (ns > 0)
         for (int r0 = 0; r0 < nl; r0 += 128)
-          pl.tc_tasks.push_back(TcTask{tl.blk0 + r0 / 128, r0, nl, ts.blk0, ts.n_pad / 128, b.res_off});
+          pl.tc_tasks.push_back(TcTask{tl.blk0 + r0 / 128, r0, nl, ts.blk0, ts.n_pad / 128, ns, 0, b.res_off});
+      pl.gsides.push_back(TcGatherSide{a.q_base, a.res_off, a.res_off, ts.blk0, tl.blk0, tl.n_pad / 128, nl});
+      pl.gsides.push_back(TcGatherSide{b.q_base, b.res_off, b.res_off, tl.blk0, ts.blk0, ts.n_pad / 128, ns});
     } else {
       for (int r0 = 0; r0 < ns; r0 += MT) pl.exact_tasks.push_back(MatchTask{a.q_base, a.t_base, ns, nl, r0, a.res_off});
       for (int r0 = 0; r0 < nl; r0 += MT) pl.exact_tasks.push_back(MatchTask{b.q_base, b.t_base, nl, ns, r0, b.res_off});
@@ -369,13 +445,21 @@ static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int
 struct MatchBuffers {
   void* tasks = nullptr; PairMeta* pairs = nullptr; SideMeta* sides = nullptr;
   RowInfo* info = nullptr; TcTop2* approx = nullptr;
-  int2* list = nullptr; int* counters = nullptr;   // [0] total, [1] list1 count, [2] list2 count
+  int2* list = nullptr;        // full re-scan (fallback) list
+  int* counters = nullptr;     // [0] matches, [1..3] fallback rows per round, [4..6] gather blocks per round,
+                               // then side_cnt[round][side]
+  int n_counters = 0;
   int* out = nullptr;
+  // gathered second tensor pass
+  TcGatherSide* gsides = nullptr; int* list_rows = nullptr; TcTask* gtasks = nullptr; unsigned char* gq = nullptr;
+  int2* g_meta = nullptr; int* g_thr = nullptr; int* cand_cnt = nullptr; int* cand = nullptr;
 };
 
 static void free_buffers(pano_ctx* ctx, MatchBuffers& b, bool keep_out) {
   ctx_free(ctx, b.tasks); ctx_free(ctx, b.pairs); ctx_free(ctx, b.sides); ctx_free(ctx, b.info);
   ctx_free(ctx, b.approx); ctx_free(ctx, b.list);
+  ctx_free(ctx, b.gsides); ctx_free(ctx, b.list_rows); ctx_free(ctx, b.gtasks); ctx_free(ctx, b.gq);
+  ctx_free(ctx, b.g_meta); ctx_free(ctx, b.g_thr); ctx_free(ctx, b.cand_cnt); ctx_free(ctx, b.cand);
   if (!keep_out) { ctx_free(ctx, b.out); ctx_free(ctx, b.counters); b.out = nullptr; b.counters = nullptr; }
 }
 
@@ -390,12 +474,14 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
       (rc = ctx_alloc(ctx, (void**)&b.sides, bs)) || (rc = ctx_alloc(ctx, (void**)&b.info, nres * sizeof(RowInfo))) ||
       (rc = ctx_alloc(ctx, (void**)&b.approx, nres * sizeof(TcTop2))) ||
       (rc = ctx_alloc(ctx, (void**)&b.list, nres * sizeof(int2))) ||
-      (rc = ctx_alloc(ctx, (void**)&b.counters, 4 * sizeof(int))) ||
       (rc = ctx_alloc(ctx, (void**)&b.out, std::max<long long>(pl.out_total, 1) * sizeof(int))))
     return rc;
+  const int n_sides = (int)pl.sides.size();
+  b.n_counters = 8 + 3 * n_sides;
+  if ((rc = ctx_alloc(ctx, (void**)&b.counters, b.n_counters * sizeof(int)))) return rc;
   const void* tsrc = tensor ? (const void*)pl.tc_tasks.data() : (const void*)pl.exact_tasks.data();
   if ((rc = ctx_put(ctx, b.tasks, tsrc, bt)) || (rc = ctx_put(ctx, b.pairs, pl.pairs.data(), bp)) ||
-      (rc = ctx_put(ctx, b.sides, pl.sides.data(), bs)) || (rc = ctx_zero(ctx, b.counters, 4 * sizeof(int))))
+      (rc = ctx_put(ctx, b.sides, pl.sides.data(), bs)) || (rc = ctx_zero(ctx, b.counters, b.n_counters * sizeof(int))))
     return rc;
   if (pl.pairs.empty()) return PANO_OK;
   const float rs = ratio * ratio;
@@ -410,9 +496,11 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
     if (!pl.exact_tasks.empty())
       PANO_LAUNCH(ctx, "k_match_top2", k_match_top2, (unsigned)pl.exact_tasks.size(), MT_THREADS, smem, fs->d_desc,
                   (const MatchTask*)b.tasks, b.info);
-    if (pl.max_small > 0)
+    if (pl.max_small > 0) {
+      if ((rc = ctx_alloc(ctx, (void**)&b.list_rows, nres * sizeof(int)))) return rc;
       PANO_LAUNCH(ctx, "k_match_decide", k_match_decide, gd, 256, 0, b.pairs, b.sides, b.info, rs, 1, b.out,
-                  b.counters, b.list, b.counters + 1);
+                  b.counters, b.list_rows, b.counters + 8);
+    }
     return PANO_OK;
   }
   rc = tc_run_top2(ctx, ops, (const TcTask*)b.tasks, (int)pl.tc_tasks.size(), b.approx);
@@ -423,16 +511,43 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
                 b.info);
   }
   if (pl.max_small > 0) {
-    // Up to three decide rounds: a round decides every row it can from the current
-    // intervals and lists the rows it needs exactly; k_exact_rows re-scans those.
-    // Round 1 may need row k itself (argmin uncertain), round 2 then its column.
+    // Up to three decide rounds.  A round decides every row it can from the current
+    // intervals and lists, per side, the rows it needs exactly (round 1 may need row k
+    // itself, round 2 then its column).  Listed rows go through a gathered second
+    // tensor pass that enumerates the columns inside each row's error band
+    // (k_tc_filter), k_exact_cands takes exact fp32 distances to just those columns,
+    // and only rows that overflow their candidate slots are re-scanned against every
+    // target (k_exact_rows).
+    const int block_cap = (int)std::min<size_t>(std::max<size_t>(pl.tc_tasks.size(), 1), 4096);
+    const size_t grow = (size_t)block_cap * 128;
+    TcFilter f;
+    if ((rc = ctx_alloc(ctx, (void**)&b.gsides, pl.gsides.size() * sizeof(TcGatherSide))) ||
+        (rc = ctx_put(ctx, b.gsides, pl.gsides.data(), pl.gsides.size() * sizeof(TcGatherSide))) ||
+        (rc = ctx_alloc(ctx, (void**)&b.list_rows, nres * sizeof(int))) ||
+        (rc = ctx_alloc(ctx, (void**)&b.gtasks, (size_t)block_cap * sizeof(TcTask))) ||
+        (rc = ctx_alloc(ctx, (void**)&b.gq, (size_t)block_cap * tc_block_bytes())) ||
+        (rc = ctx_alloc(ctx, (void**)&b.g_meta, grow * sizeof(int2))) ||
+        (rc = ctx_alloc(ctx, (void**)&b.g_thr, grow * sizeof(int))) ||
+        (rc = ctx_alloc(ctx, (void**)&b.cand_cnt, grow * sizeof(int))) ||
+        (rc = ctx_alloc(ctx, (void**)&b.cand, grow * TC_CAND_CAP * sizeof(int))))
+      return rc;
+    f.gq = b.gq; f.tasks = b.gtasks; f.gsides = b.gsides; f.list_rows = b.list_rows; f.approx = b.approx;
+    f.g_meta = b.g_meta; f.g_thr = b.g_thr; f.cand_cnt = b.cand_cnt; f.cand = b.cand;
     const int eg = ctx->num_sms * 4;
     for (int round = 0; round < 3; ++round) {
-      int* cnt = b.counters + 1 + round;
+      int* side_cnt = b.counters + 8 + round * n_sides;
+      int* fb_cnt = b.counters + 1 + round;
+      int* n_blocks = b.counters + 4 + round;
       PANO_LAUNCH(ctx, "k_match_decide", k_match_decide, gd, 256, 0, b.pairs, b.sides, b.info, rs, round == 0 ? 1 : 0,
-                  b.out, b.counters, b.list, cnt);
+                  b.out, b.counters, b.list_rows, side_cnt);
       if (round == 2) break;
-      PANO_LAUNCH(ctx, "k_exact_rows", k_exact_rows, eg, 256, 0, fs->d_desc, b.sides, b.list, cnt, b.info);
+      PANO_LAUNCH(ctx, "k_gather_plan", k_gather_plan, ceil_div(n_sides, 128), 128, 0, b.gsides, n_sides, side_cnt,
+                  b.list_rows, block_cap, b.gtasks, n_blocks, b.list, fb_cnt);
+      f.n_tasks = n_blocks;
+      if ((rc = tc_run_filter(ctx, ops, &f, block_cap))) return rc;
+      PANO_LAUNCH(ctx, "k_exact_cands", k_exact_cands, eg, 256, 0, fs->d_desc, b.sides, n_blocks, b.g_meta, b.cand_cnt,
+                  b.cand, b.info, b.list, fb_cnt);
+      PANO_LAUNCH(ctx, "k_exact_rows", k_exact_rows, eg, 256, 0, fs->d_desc, b.sides, b.list, fb_cnt, b.info);
     }
   }
   return PANO_OK;
@@ -527,16 +642,21 @@ int pano_match_pairs_dev(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const 
   MatchBuffers b;
   int rc = match_common(ctx, fs, n_pairs, ij, p, pl, b);
   if (rc) { free_buffers(ctx, b, false); return rc; }
-  int* h = (int*)ctx_ring(ctx, 4 * sizeof(int));
+  int* h = (int*)ctx_ring(ctx, (size_t)std::max(b.n_counters, 8) * sizeof(int));
   if (!h) { free_buffers(ctx, b, false); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned ring allocation failed"); }
-  rc = ctx_store(ctx, h, b.counters, 4 * sizeof(int));
+  const int n_counters = b.n_counters, n_sides = (int)pl.sides.size();
+  rc = b.counters ? ctx_store(ctx, h, b.counters, (size_t)n_counters * sizeof(int)) : 0;
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   free_buffers(ctx, b, false);
   if (rc) return rc;
   if (e != cudaSuccess) return ctx_cuda(ctx, e, "match total download");
+  if (n_counters < 8) { *total_matches = 0; return PANO_OK; }
+  long long requested = 0, undecided = 0;
+  for (int sidx = 0; sidx < n_sides; ++sidx) { requested += h[8 + sidx] + h[8 + n_sides + sidx]; undecided += h[8 + 2 * n_sides + sidx]; }
+  ctx->last_match_exact_rows = (int)requested;
+  ctx->last_match_full_rescans = h[1] + h[2];
+  if (undecided != 0) return ctx_fail(ctx, PANO_ERR_CUDA, "match: %lld rows undecided after the exact passes", undecided);
   *total_matches = h[0];
-  ctx->last_match_exact_rows = h[1] + h[2];
-  if (h[3] != 0) return ctx_fail(ctx, PANO_ERR_CUDA, "match: %d rows undecided after the exact passes", h[3]);
   return PANO_OK;
 }
 

@@ -29,6 +29,7 @@
 #include "match_tc.cuh"
 #include <cuda_fp16.h>
 #include <float.h>
+#include <algorithm>
 
 #define TC_KC 18                       // 16-byte k-chunks per row: 144 fp16
 #define TC_BLOCK_BYTES (TC_KC * 2048)  // 128 rows x 144 fp16 = 36864 B
@@ -182,31 +183,43 @@ struct __align__(8) TcBarriers {
   uint32_t tmem_base;
 };
 
+// FILTER = false: running top-2 per query row (the nomination pass).
+// FILTER = true : second pass over GATHERED rows only; every column whose score is
+//                 within the row's threshold key is appended to that row's candidate
+//                 slots (the exact kernel then decides among a handful of columns).
+template <bool FILTER>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_tc_top2(const unsigned char* __restrict__ qbuf, const unsigned char* __restrict__ tbuf,
-          const TcTask* __restrict__ tasks, const unsigned* __restrict__ maxnorm_bits, TcTop2* __restrict__ res) {
+k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restrict__ tbuf,
+          const TcTask* __restrict__ tasks, const int* __restrict__ n_tasks_dev,
+          const unsigned* __restrict__ maxnorm_bits, TcTop2* __restrict__ res,
+          const int* __restrict__ g_thr, int* __restrict__ cand_cnt, int* __restrict__ cand) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
+  if (n_tasks_dev && (int)blockIdx.x >= *n_tasks_dev) return;   // uniform per CTA, before any barrier / TMEM use
   unsigned char* sA = tc_smem;                                        // 1 block
   unsigned char* sB = tc_smem + TC_BLOCK_BYTES;                       // TC_STAGES x 2 blocks
   TcBarriers* bars = (TcBarriers*)(sB + (size_t)TC_STAGES * TC_TILE_BLOCKS * TC_BLOCK_BYTES);
-  const TcTask tk = tasks[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // The filter pass is launched with a small persistent grid (its task count lives on
+  // the device); each CTA loops over tasks and re-arms its barriers per task.
+  const int task_end = n_tasks_dev ? *n_tasks_dev : (int)blockIdx.x + 1;
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  uint32_t tmem = 0;
+  for (int task = blockIdx.x; task < task_end; task += gridDim.x) {
+  const TcTask tk = tasks[task];
   const int ntile = tk.t_blocks / TC_TILE_BLOCKS;
-
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bars->acc_full[s]), 1); mbar_init(smem_u32(&bars->acc_empty[s]), 128); }
     mbar_init(smem_u32(&bars->a_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = bars->tmem_base;
+  tmem = bars->tmem_base;
 
   if (warp == 0) {
     // ===== producer
@@ -256,6 +269,8 @@ k_tc_top2(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     int g1 = 0x7f7fff00, g2 = 0x7f7fff00;   // running best / second (value bits, low 8 cleared)
     int gi = 0x7fffffff;
+    const int grow = tk.q_row0 + row;        // FILTER: index of this gathered row
+    const int thr = FILTER ? g_thr[grow] : 0;
     for (int t = 0; t < ntile; ++t) {
       const int as = t & 1;
       mbar_wait(smem_u32(&bars->acc_full[as]), (uint32_t)(t >> 1) & 1u);
@@ -266,22 +281,37 @@ k_tc_top2(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
         uint32_t v[32];
         tmem_ld32(lane_addr + (uint32_t)(as * 256 + c0), v);
         tmem_ld_wait();
+        if (FILTER) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int key = (int)((v[j] & 0xffffff00u) | (uint32_t)(c0 + j));
-          k2 = min(k2, max(k1, key));
-          k1 = min(k1, key);
+          for (int j = 0; j < 32; ++j) {
+            if ((int)(v[j] & 0xffffff00u) <= thr) {
+              const int col = t * 256 + c0 + j;
+              if (col < tk.t_n) {
+                const int slot = atomicAdd(&cand_cnt[grow], 1);
+                if (slot < TC_CAND_CAP) cand[(size_t)grow * TC_CAND_CAP + slot] = col;
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int key = (int)((v[j] & 0xffffff00u) | (uint32_t)(c0 + j));
+            k2 = min(k2, max(k1, key));
+            k1 = min(k1, key);
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->acc_empty[as]));
-      // merge the tile's top-2 into the running top-2
-      const int v1 = k1 & (int)0xffffff00, v2 = k2 & (int)0xffffff00;
-      if (v1 < g1) { g2 = min(g1, v2); g1 = v1; gi = t * 256 + (k1 & 0xff); }
-      else g2 = min(g2, v1);
+      if (!FILTER) {
+        // merge the tile's top-2 into the running top-2
+        const int v1 = k1 & (int)0xffffff00, v2 = k2 & (int)0xffffff00;
+        if (v1 < g1) { g2 = min(g1, v2); g1 = v1; gi = t * 256 + (k1 & 0xff); }
+        else g2 = min(g2, v1);
+      }
     }
     const int qrow = tk.q_row0 + row;
-    if (qrow < tk.q_n) {
+    if (!FILTER && qrow < tk.q_n) {
       const float s = tc_scale_from_maxnorm(__uint_as_float(*maxnorm_bits));
       const float inv = 1.f / (s * s);
       TcTop2 o;
@@ -293,14 +323,30 @@ k_tc_top2(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
     }
   }
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();                 // every role is done with this task's barriers, smem and TMEM
+  if (threadIdx.x == 0 && task + (int)gridDim.x < task_end) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->full[s])) : "memory");
+      asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->empty[s])) : "memory");
+    }
+    for (int s = 0; s < 2; ++s) {
+      asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->acc_full[s])) : "memory");
+      asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->acc_empty[s])) : "memory");
+    }
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->a_full)) : "memory");
+  }
+  }  // task loop
   if (warp == 2) {
+    // a CTA without any task still allocated TMEM above: read the address back directly
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    const uint32_t base = *(volatile uint32_t*)&bars->tmem_base;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512u) : "memory");
   }
 }
 
 // ------------------------------------------------------------------ host side
+
+size_t tc_block_bytes() { return TC_BLOCK_BYTES; }
 
 size_t tc_smem_bytes() {
   return (size_t)TC_BLOCK_BYTES * (1 + TC_STAGES * TC_TILE_BLOCKS) + sizeof(TcBarriers) + 1024;
@@ -338,9 +384,62 @@ int tc_run_top2(pano_ctx* ctx, const TcOperands* ops, const TcTask* d_tasks, int
   const size_t smem = tc_smem_bytes();
   static bool attr_set = false;
   if (!attr_set) {
-    PANO_CUDA(ctx, cudaFuncSetAttribute(k_tc_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PANO_CUDA(ctx, cudaFuncSetAttribute(k_tc_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PANO_CUDA(ctx, cudaFuncSetAttribute(k_tc_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  PANO_LAUNCH(ctx, "k_tc_top2", k_tc_top2, n_tasks, TC_THREADS, smem, ops->qbuf, ops->tbuf, d_tasks, ops->d_maxnorm, d_res);
+  PANO_LAUNCH(ctx, "k_tc_top2", k_tc_pass<false>, n_tasks, TC_THREADS, smem, ops->qbuf, ops->tbuf, d_tasks,
+              (const int*)nullptr, ops->d_maxnorm, d_res, (const int*)nullptr, (int*)nullptr, (int*)nullptr);
+  return PANO_OK;
+}
+
+// ------------------------------------------------------------------ gathered second pass
+
+// Copies the query-form fp16 rows of the listed rows into gather blocks and sets
+// each gathered row's threshold key / bookkeeping.  One CTA per gather block.
+__global__ void __launch_bounds__(128)
+k_tc_gather_rows(const unsigned char* __restrict__ qbuf, unsigned char* __restrict__ gq,
+                 const TcTask* __restrict__ tasks, const int* __restrict__ n_tasks_dev,
+                 const TcGatherSide* __restrict__ gsides, const int* __restrict__ list_rows,
+                 const TcTop2* __restrict__ approx, const float* __restrict__ norms,
+                 const unsigned* __restrict__ maxnorm_bits, int2* __restrict__ g_meta, int* __restrict__ g_thr,
+                 int* __restrict__ cand_cnt) {
+  if ((int)blockIdx.x >= *n_tasks_dev) return;
+  const TcTask tk = tasks[blockIdx.x];
+  const int side = (int)tk.res_off;                 // filter tasks carry the side index here
+  const TcGatherSide gs = gsides[side];
+  const int r = threadIdx.x, g = tk.q_row0 + r;
+  unsigned char* dst = gq + (size_t)tk.q_blk * TC_BLOCK_BYTES + (r / 8) * TC_SBO + (r % 8) * 16;
+  if (r < tk.q_n) {
+    const int row = list_rows[gs.list_off + tk.t_pad + r];      // t_pad = first list slot of this block
+    const unsigned char* src = qbuf + (size_t)(gs.q_blk0 + row / 128) * TC_BLOCK_BYTES + ((row % 128) / 8) * TC_SBO + (row % 8) * 16;
+#pragma unroll
+    for (int kc = 0; kc < TC_KC; ++kc) *(uint4*)(dst + (size_t)kc * TC_LBO) = *(const uint4*)(src + (size_t)kc * TC_LBO);
+    const float nmax = __uint_as_float(*maxnorm_bits);
+    const float s = tc_scale_from_maxnorm(nmax);
+    const float nq = norms[gs.q_base + row];
+    const float eps = 0.00215f * sqrtf(nq * nmax) + 0.0005f * nmax + 1.0f;    // == tc_eps in match.cu
+    const TcTop2 ap = approx[gs.res_off + row];
+    // every column whose exact distance can be the best or the second best scores <= m2~ + 2 eps
+    float thr_v = ap.m2 == FLT_MAX ? FLT_MAX : (ap.m2 + 2.5f * eps) * (s * s) + 1.f;
+    g_thr[g] = (int)(__float_as_uint(thr_v) | 0xffu);
+    g_meta[g] = make_int2(side, row);
+    cand_cnt[g] = 0;
+  } else {
+#pragma unroll
+    for (int kc = 0; kc < TC_KC; ++kc) *(uint4*)(dst + (size_t)kc * TC_LBO) = make_uint4(0, 0, 0, 0);
+    g_thr[g] = -1;
+    g_meta[g] = make_int2(-1, -1);
+    cand_cnt[g] = 0;
+  }
+}
+
+int tc_run_filter(pano_ctx* ctx, const TcOperands* ops, const TcFilter* f, int max_blocks) {
+  if (max_blocks <= 0) return PANO_OK;
+  const size_t smem = tc_smem_bytes();
+  PANO_LAUNCH(ctx, "k_tc_gather_rows", k_tc_gather_rows, max_blocks, 128, 0, ops->qbuf, f->gq, f->tasks, f->n_tasks,
+              f->gsides, f->list_rows, f->approx, ops->d_norms, ops->d_maxnorm, f->g_meta, f->g_thr, f->cand_cnt);
+  PANO_LAUNCH(ctx, "k_tc_filter", k_tc_pass<true>, std::min(max_blocks, ctx->num_sms), TC_THREADS, smem, f->gq, ops->tbuf, f->tasks, f->n_tasks,
+              ops->d_maxnorm, (TcTop2*)nullptr, f->g_thr, f->cand_cnt, f->cand);
   return PANO_OK;
 }

@@ -92,17 +92,26 @@ def config_stack(name: str, n: int | None = None):
     return make_stack(**cfg)
 
 
-def translation_blend_setup(origins, w: int, h: int):
+def translation_blend_setup(origins, w: int, h: int, max_output_size: int | None = None):
     """Generator-known geometry for the blend stage of a crop stack: image k is
-    the canvas translated by its origin, so with the flat projection and unit
-    resolution the inverse homography is a pure translation.
+    the canvas translated by its origin, so with the flat projection the inverse
+    homography is a pure translation.
 
     Returns (list of (x0, y0, x1, y1, homo_inv[9]), geom dict) in the form
     ConnectedImages::blend builds (stitcher_image.cc:116-155): ranges are the
-    projected corner ranges min-shifted by proj_min and truncated to int."""
+    projected corner ranges min-shifted by proj_min, divided by the resolution and
+    truncated to int.  With max_output_size the resolution is raised so that the
+    longer canvas edge is that many pixels (get_final_resolution,
+    stitcher_image.cc:108-111: `resolution *= max_edge / MAX_OUTPUT_SIZE`)."""
     ox = min(o[0] for o in origins)
     oy = min(o[1] for o in origins)
     proj_min = (ox - w / 2.0, oy - h / 2.0)
+    proj_max = (max(o[0] for o in origins) + w / 2.0, max(o[1] for o in origins) + h / 2.0)
+    res = 1.0
+    if max_output_size is not None:
+        max_edge = max(proj_max[0] - proj_min[0], proj_max[1] - proj_min[1])
+        if max_edge > max_output_size:
+            res = float(np.float32(max_edge / max_output_size))      # `float ratio` in the reference
     items = []
     for (x, y) in origins:
         # homo maps image-centred pixel -> canvas-centred coordinate: + (x, y)
@@ -110,12 +119,12 @@ def translation_blend_setup(origins, w: int, h: int):
         homo_inv = [1.0, 0.0, -cx, 0.0, 1.0, -cy, 0.0, 0.0, 1.0]
         rmin = (cx - w / 2.0, cy - h / 2.0)
         rmax = (cx + w / 2.0, cy + h / 2.0)
-        x0 = int(rmin[0] - proj_min[0])
-        y0 = int(rmin[1] - proj_min[1])
-        x1 = int(rmax[0] - proj_min[0])
-        y1 = int(rmax[1] - proj_min[1])
+        x0 = int((rmin[0] - proj_min[0]) / res)
+        y0 = int((rmin[1] - proj_min[1]) / res)
+        x1 = int((rmax[0] - proj_min[0]) / res)
+        y1 = int((rmax[1] - proj_min[1]) / res)
         items.append((x0, y0, x1, y1, homo_inv))
-    geom = dict(projection=0, res_x=1.0, res_y=1.0, proj_min_x=proj_min[0], proj_min_y=proj_min[1])
+    geom = dict(projection=0, res_x=res, res_y=res, proj_min_x=proj_min[0], proj_min_y=proj_min[1])
     return items, geom
 
 
