@@ -119,7 +119,7 @@ class ClockSampler:
         self._t0 = self._t1 = None
 
     def _run(self):
-        # one long-lived `nvidia-smi -lms 25` (a fresh process per sample costs > 100 ms)
+        # one long-lived `nvidia-smi -lms 100` (a fresh process per sample costs > 100 ms)
         for line in self._proc.stdout:
             parts = [p.strip() for p in line.strip().split(",")]
             if len(parts) >= 7:
@@ -129,7 +129,7 @@ class ClockSampler:
         """Start the sampler process ahead of time; mark() / stop() bracket the timed region."""
         try:
             self._proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}",
-                                           "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE,
+                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                           stderr=subprocess.DEVNULL, text=True)
             self._thr = threading.Thread(target=self._run, daemon=True)
             self._thr.start()
@@ -313,6 +313,9 @@ def main():
             f, _ = st.run_device(pairs, items, geom, args.bands, want_matches=False)
             f.free()
 
+        import gc
+        gc.collect()
+        gc.disable()                       # no collector pauses inside the timed regions
         for _ in range(args.warmup):
             step_device()
         torch.cuda.synchronize()

@@ -66,6 +66,11 @@ void* ctx_pinned2(pano_ctx* ctx, size_t bytes);  // staging buffer B (results)
 // mapped ring (valid until the ring wraps, which synchronises the stream);
 // ctx_fetch / ctx_store move words with a small kernel that addresses the host
 // memory directly (UVA); ctx_put = ring + memcpy + fetch; ctx_zero fills zeros.
+// Host waits that SPIN on cudaEventQuery instead of sleeping in the driver: the hot
+// path has two short waits per step (feature counts, match decisions) and a
+// descheduled host thread on a busy machine costs milliseconds.
+cudaError_t ctx_spin_event(cudaEvent_t ev);
+cudaError_t ctx_spin_stream(pano_ctx* ctx);
 void* ctx_ring(pano_ctx* ctx, size_t bytes);
 void* ctx_small_pinned_get(pano_ctx* ctx, size_t bytes, size_t* cap);
 void ctx_small_pinned_put(pano_ctx* ctx, void* p, size_t cap);

@@ -52,6 +52,23 @@ void* ctx_pinned2(pano_ctx* ctx, size_t bytes) {
   return grow_pinned(&ctx->pinned2, &ctx->pinned2_bytes, bytes);
 }
 
+cudaError_t ctx_spin_event(cudaEvent_t ev) {
+  for (;;) {
+    cudaError_t e = cudaEventQuery(ev);
+    if (e != cudaErrorNotReady) return e;
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
+}
+cudaError_t ctx_spin_stream(pano_ctx* ctx) {
+  cudaEvent_t ev = ctx_sync_event_get(ctx);
+  cudaError_t e = cudaEventRecord(ev, ctx->stream);
+  if (e == cudaSuccess) e = ctx_spin_event(ev);
+  ctx_sync_event_put(ctx, ev);
+  return e;
+}
+
 // ---- copy-engine-free small moves
 __global__ void k_copy_u32(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
@@ -313,7 +330,7 @@ int pano_event_wait(pano_ctx* ctx, pano_event* ev) {
 }
 int pano_event_sync(pano_event* ev) {
   if (!ev) return PANO_ERR_INVALID;
-  return cudaEventSynchronize(ev->ev) == cudaSuccess ? PANO_OK : PANO_ERR_CUDA;
+  return ctx_spin_event(ev->ev) == cudaSuccess ? PANO_OK : PANO_ERR_CUDA;
 }
 void pano_event_destroy(pano_event* ev) {
   if (!ev) return;

@@ -596,7 +596,7 @@ int pano_match_pairs(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int*
   int* h_stage = (int*)ctx_ring(ctx, (size_t)std::max<long long>(pl.out_total, 1) * sizeof(int));
   if (!h_stage) { free_buffers(ctx, b, false); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned ring allocation failed"); }
   rc = ctx_store(ctx, h_stage, b.out, pl.out_total * sizeof(int));
-  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = ctx_spin_stream(ctx);
   free_buffers(ctx, b, false);
   if (rc) return rc;
   if (e != cudaSuccess) return ctx_cuda(ctx, e, "match download");
@@ -646,7 +646,7 @@ int pano_match_pairs_dev(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const 
   if (!h) { free_buffers(ctx, b, false); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned ring allocation failed"); }
   const int n_counters = b.n_counters, n_sides = (int)pl.sides.size();
   rc = b.counters ? ctx_store(ctx, h, b.counters, (size_t)n_counters * sizeof(int)) : 0;
-  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = ctx_spin_stream(ctx);
   free_buffers(ctx, b, false);
   if (rc) return rc;
   if (e != cudaSuccess) return ctx_cuda(ctx, e, "match total download");

@@ -193,7 +193,7 @@ __device__ __forceinline__ void blur_level(const float* __restrict__ grey, float
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(BT_THREADS)
+__global__ void __launch_bounds__(BT_THREADS, 3)
 k_blur_dog_fast(const OctMeta* __restrict__ octs, const BlurTile* __restrict__ tiles,
                 float* __restrict__ arena, const __grid_constant__ GaussTable gt) {
   extern __shared__ float smem[];
@@ -700,8 +700,10 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
   DescWarpSmem& S = reinterpret_cast<DescWarpSmem*>(desc_smem_raw)[wid];
   const float pi2 = (float)(2 * PANO_PI);
   const float nbin_per_rad = 8 / pi2;
-  const int cell = lane >> 1, role = lane & 1, by = cell >> 2, bx = cell & 3;
-  const unsigned pair_mask = 3u << (lane & ~1);
+  // lane = (cell, parity): the lane owns the 4 orientation bins of its cell whose index
+  // has its parity.  A record adds to bins hbinf and hbinf+1 — one even, one odd — so
+  // each bin has exactly one owner lane and the accumulators can live in registers.
+  const int cell = lane >> 1, parity = lane & 1, by = cell >> 2, bx = cell & 3;
   const int warp_global = blockIdx.x * DESC_WARPS + wid, warp_stride = gridDim.x * DESC_WARPS;
 
   for (int img = 0; img < n_img; ++img) {
@@ -724,23 +726,25 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
       // bin in [-1,3]  <=>  rot in [-2.5, 1.5] * hist_w (the exact test is in phase B)
       const float lo = -2.5f * hist_w - 0.02f * hist_w - 1e-3f, hi = 1.5f * hist_w + 0.02f * hist_w + 1e-3f;
       const float fr2 = (float)radius * (float)radius;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) S.acc[lane + 32 * q] = 0.f;
-      __syncwarp();
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;   // bins (cell, parity + 2q), q = 0..3
+      uint32_t cm = 0;  // lanes 0..15: bit ci set <=> chunk ci has records touching cell `lane`
 
       int nstage = 0;   // survivors waiting in S.stage (warp-uniform)
       int nrec = 0;     // records in S.r_* (warp-uniform, multiple of 32 except after the tail)
 
       // phase D for the current record set, then reset it
       auto flush_records = [&]() {
-        const int nchunk = (nrec + 31) >> 5;
         __syncwarp();
-        volatile float* acc = S.acc;
+        uint32_t chunks = __shfl_sync(0xffffffffu, cm, cell);   // non-empty chunks of my cell
+        uint32_t word = 0u;
         int ci = 0;
-        uint32_t word = nchunk > 0 ? S.mask[cell][0] : 0u;
         while (true) {
-          while (word == 0u && ++ci < nchunk) word = S.mask[cell][ci];
-          if (ci >= nchunk) break;
+          if (word == 0u) {
+            if (chunks == 0u) break;
+            ci = __ffs(chunks) - 1;
+            chunks &= chunks - 1;
+            word = S.mask[cell][ci];
+          }
           const int b = __ffs(word) - 1;
           word &= word - 1;
           const int t = ci * 32 + b;
@@ -751,13 +755,15 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
           const float yd = S.r_yd[t], xd = S.r_xd[t], hd = S.r_hd[t];
           const float w_y = S.r_w[t] * (dy ? yd : 1 - yd);
           const float w_x = w_y * (dx ? xd : 1 - xd);
-          const float v = w_x * (role ? hd : 1 - hd);
-          const int bin = cell * 8 + ((hbinf + role) & 7);
-          __syncwarp(pair_mask);          // the pair's previous read-modify-write is complete
-          acc[bin] = acc[bin] + v;
+          // my parity's bin: hbinf itself (factor 1-hd) or hbinf+1 (factor hd)
+          const int up = (hbinf ^ parity) & 1;
+          const float v = w_x * (up ? hd : 1 - hd);
+          const int q = ((hbinf + up) & 7) >> 1;
+          if (q == 0) a0 += v; else if (q == 1) a1 += v; else if (q == 2) a2 += v; else a3 += v;
         }
         __syncwarp();
         nrec = 0;
+        cm = 0;
       };
 
       // phase B on the first 32 staged survivors (or the tail when final)
@@ -794,12 +800,17 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
         const int t = nrec + lane;
         S.r_pk[t] = pk; S.r_w[t] = wgt; S.r_yd[t] = ybind; S.r_xd[t] = xbind; S.r_hd[t] = hbind;
         const int ci = nrec >> 5;
+        uint32_t mine = 0;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const int cy = c >> 2, cxx = c & 3;
           const bool touch = (unsigned)(cy - ybinf) <= 1u && (unsigned)(cxx - xbinf) <= 1u;
           const unsigned m = __ballot_sync(0xffffffffu, touch);
-          if (lane == 0) S.mask[c][ci] = m;
+          if (lane == c) mine = m;
+        }
+        if (lane < 16) {
+          S.mask[lane][ci] = mine;
+          if (mine) cm |= 1u << ci;
         }
         nrec += 32;
         // shift the ring: survivors 32.. move to the front
@@ -844,6 +855,9 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
       if (nrec > 0) flush_records();
 
       // RootSIFT: L1 normalise (sequential sum), sqrt, * DESC_INT_FACTOR
+      S.acc[cell * 8 + parity] = a0; S.acc[cell * 8 + parity + 2] = a1;
+      S.acc[cell * 8 + parity + 4] = a2; S.acc[cell * 8 + parity + 6] = a3;
+      __syncwarp();
       float sum = 0.f;
       if (lane == 0) {
 #pragma unroll 16
@@ -1083,7 +1097,7 @@ int featureset_sync_counts(pano_featureset* fs) {
   if (fs->counts_on_host) return PANO_OK;
   pano_ctx* ctx = fs->ctx;
   if (fs->counts_ready) {
-    PANO_CUDA(ctx, cudaEventSynchronize(fs->counts_ready));
+    PANO_CUDA(ctx, ctx_spin_event(fs->counts_ready));
     fs->h_count.assign(fs->h_count_pinned, fs->h_count_pinned + fs->n_images);
     for (int i = 0; i < fs->n_images; ++i) {
       if (fs->h_count_pinned[fs->n_images + i] > SIFT_CAND_CAP)
