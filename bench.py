@@ -14,7 +14,11 @@ outside the hot path).  Metric: megapixels of INPUT per second.
 Prints ONE JSON line on rank 0 (contract in the task statement):
   value    : K steps with inputs resident in HBM (device-timed, max over ranks)
   e2e      : the same through the public API with pinned HOST inputs/outputs,
-             H2D of the images and D2H of the mosaic + matches inside the timing
+             H2D of the images and D2H of the mosaic + matches inside the timing.
+             Host formats are the reference's file formats (8-bit pixels as read_img
+             receives them, cropped 8-bit mosaic as write_rgb saves it; conversions
+             and crop on the device, timed); e2e.mat32f_boundary is the same with
+             f32 Mat32f buffers both ways (4x the PCIe bytes)
   roofline : dominant kernel, algorithmic bytes / event-timed duration
   cpu_baseline : oracle/_ref (the reference's own TUs, OpenMP) on this host
 """
@@ -47,12 +51,17 @@ def make_workload(rank: int, bands: int):
 
     cfg = dict(synth.CONFIGS[WORKLOAD])
     cfg["seed"] = cfg["seed"] + 1000 * rank          # each rank stitches its own stack (weak scaling)
-    imgs, origins = synth.make_stack(**cfg)
+    views, origins = synth.make_stack(**cfg)
+    # The stack as the reference meets it: 8-bit decoded pixels (CImg<unsigned char>, imgio.cc:72)
+    # turned into Mat32f by read_img's `(float)v / 255.0` (imgio.cc:79-81).  `pix` feeds the 8-bit
+    # e2e boundary, `imgs` (bit-identical to read_img(pix)) every Mat32f leg and the CPU arms.
+    pix = [(v * 255.0 + 0.5).astype(np.uint8) for v in views]
+    imgs = [(p.astype(np.float32).astype(np.float64) / 255.0).astype(np.float32) for p in pix]
     items, geom = synth.translation_blend_setup(origins, cfg["w"], cfg["h"])
     params = default_params(ordered_input=1, multiband=bands)
     pairs = ordered_pairs(len(imgs))
     mpx = sum(im.shape[0] * im.shape[1] for im in imgs) / 1e6
-    return imgs, pairs, items, geom, params, mpx
+    return imgs, pairs, items, geom, params, mpx, pix
 
 
 def octave_dims(w, h, params):
@@ -212,7 +221,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     use_all_host_threads()
-    imgs, pairs, items, geom, params, mpx = make_workload(0, args.bands)
+    imgs, pairs, items, geom, params, mpx, _ = make_workload(0, args.bands)
     chk, kind = load_cpu_checker()
     devnull = os.open(os.devnull, os.O_WRONLY)
     saved = os.dup(1)
@@ -235,7 +244,9 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "bands": args.bands, "matcher": "PairWiseMatcher (FLANN kd-forest)",
-                   "geometry": "generator-known homographies", "features": nfeat, "matches": nmatch},
+                   "geometry": "generator-known homographies", "features": nfeat, "matches": nmatch,
+                   "boundary": "Mat32f in / Mat32f out: read_img's, crop's and write_rgb's loops are NOT in the "
+                               "timed region (less work than the CUDA arm's rgb8 e2e, which includes them)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": chk.num_threads(), "kind": kind,
                          "sample": f"full {WORKLOAD} workload per step (host cores: {os.cpu_count()})",
                          "stage_ms": {"features": stage[0] / args.steps * 1e3, "match": stage[1] / args.steps * 1e3,
@@ -284,7 +295,7 @@ def main():
         if world > 1:
             dist.barrier()
 
-    imgs, pairs, items, geom, params, mpx = make_workload(rank, args.bands)
+    imgs, pairs, items, geom, params, mpx, pix = make_workload(rank, args.bands)
     shapes = [im.shape[:2] for im in imgs]
     out_w, out_h = max(it[2] for it in items), max(it[3] for it in items)
 
@@ -359,42 +370,60 @@ def main():
             nm_e2e = sum(len(x) for x in m)
         torch.cuda.synchronize()
         e2e_latency = (time.perf_counter() - t0) / n_lat
-        d2h_bytes += nm_e2e * 8 + len(imgs) * 8
         assert float(host_out[out_h // 2, out_w // 2, 0]) >= 0.0      # the mosaic really came back
         # (b) throughput: consecutive jobs pipelined (PipelinedStitcher): job i+1's H2D and
         # job i-1's D2H overlap job i's kernels; every step still uploads its own inputs
         # from pinned host memory and downloads its own mosaic + match lists.
-        from openpano_b200.stitcher import PipelinedStitcher
-        ps = PipelinedStitcher(local_rank, params, depth=3)
-        host_outs = [host_out, torch.empty_like(host_out).pin_memory(), torch.empty_like(host_out).pin_memory()]
+        from openpano_b200.stitcher import PipelinedStitcher, unpack_rgb8_mosaic
 
-        def pipelined(n_jobs):
-            slot = ps.stage(host_ptrs, shapes, (out_w, out_h))
-            pending, total = None, 0
-            for i in range(n_jobs):
-                nxt = ps.stage(host_ptrs, shapes, (out_w, out_h)) if i + 1 < n_jobs else None
-                job = ps.run(slot, pairs, items, geom, host_outs[i % 3].data_ptr(), args.bands)
-                if pending is not None:
-                    total += sum(len(x) for x in ps.wait(pending))
-                pending, slot = job, nxt
-            total += sum(len(x) for x in ps.wait(pending))
-            return total
+        def pipelined_leg(rgb8):
+            ps = PipelinedStitcher(local_rank, params, depth=3, rgb8=rgb8, crop=True)
+            if rgb8:
+                src = [torch.from_numpy(p).pin_memory() for p in pix]
+                outs = [torch.empty(ps.out_bytes((out_w, out_h)), dtype=torch.uint8).pin_memory() for _ in range(3)]
+            else:
+                src = host
+                outs = [host_out, torch.empty_like(host_out).pin_memory(), torch.empty_like(host_out).pin_memory()]
+            ptrs = [t.data_ptr() for t in src]
 
-        pipelined(3)
-        torch.cuda.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        nm_pipe = pipelined(args.steps)
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        assert nm_pipe == args.steps * nm_e2e, (nm_pipe, nm_e2e)      # every job returned the same matches
-        assert float(host_outs[(args.steps - 1) % 3][out_h // 2, out_w // 2, 0]) >= 0.0
-        ps.close()
-        t_e2e = torch.tensor([e2e_s], device="cuda")
-        if world > 1:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e_per_step = float(t_e2e.item()) / args.steps
+            def pipelined(n_jobs):
+                slot = ps.stage(ptrs, shapes, (out_w, out_h))
+                pending, total = None, 0
+                for i in range(n_jobs):
+                    nxt = ps.stage(ptrs, shapes, (out_w, out_h)) if i + 1 < n_jobs else None
+                    job = ps.run(slot, pairs, items, geom, outs[i % 3].data_ptr(), args.bands)
+                    if pending is not None:
+                        total += sum(len(x) for x in ps.wait(pending))
+                    pending, slot = job, nxt
+                total += sum(len(x) for x in ps.wait(pending))
+                return total
+
+            pipelined(3)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            nm_pipe = pipelined(args.steps)
+            torch.cuda.synchronize()
+            secs = time.perf_counter() - t0
+            assert nm_pipe == args.steps * nm_e2e, (nm_pipe, nm_e2e)      # every job returned the same matches
+            last = outs[(args.steps - 1) % 3]
+            if rgb8:
+                rect, px = unpack_rgb8_mosaic(last.numpy(), (out_w, out_h))
+                assert rect[2] > out_w // 2 and rect[3] > out_h // 2 and int(px[rect[3] // 2, rect[2] // 2].max()) > 0
+            else:
+                assert float(last[out_h // 2, out_w // 2, 0]) >= 0.0
+            h2d, d2h = ps.in_bytes(shapes), ps.out_bytes((out_w, out_h)) + nm_e2e * 8 + len(imgs) * 8
+            ps.close()
+            t = torch.tensor([secs], device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item()) / args.steps, h2d, d2h
+
+        # headline: the reference's file formats at the boundary (8-bit pixels in, cropped 8-bit
+        # mosaic out; conversions and crop on the device).  Beside it the Mat32f boundary.
+        e2e_per_step, h2d_bytes, d2h_bytes = pipelined_leg(True)
         e2e_value = world * mpx / e2e_per_step
+        f32_per_step, f32_h2d, f32_d2h = pipelined_leg(False)
 
         # ---- roofline of the dominant kernel (event-timed per launch, separate untimed pass)
         roof = None
@@ -432,8 +461,14 @@ def main():
                 kernels[name] = ent
             top = max(kernels, key=lambda k: kernels[k]["share"])
             t = kernels[top]
+            # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this
+            # same workload (profiles/*_traffic.json, written by tools/ncu_summary.py); null if absent
+            traffic = None
+            tr_files = sorted((ROOT / "profiles").glob("*_traffic.json"))
+            if tr_files and not args.bands:
+                traffic = json.loads(tr_files[-1].read_text()).get(top, {}).get("dram_bytes_per_launch")
             roof = {"kernel": top, "bound": t.get("bound"), "achieved": t.get("achieved"), "peak": t.get("peak"),
-                    "unit": t.get("unit"), "frac": t.get("frac"), "traffic": None, "peak_source": peak_src,
+                    "unit": t.get("unit"), "frac": t.get("frac"), "traffic": traffic, "peak_source": peak_src,
                     "share_of_step": t["share"], "avg_ms": t["avg_ms"]}
 
         # ---- CPU baseline (rank 0, N == 1): the reference's own TUs on this host
@@ -474,8 +509,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_per_step * 1e3,
                     "mode": "PipelinedStitcher: consecutive jobs overlap H2D / kernels / D2H (depth 3)",
-                    "single_job_latency_ms": e2e_latency * 1e3,
-                    "single_job_value": world * mpx / e2e_latency},
+                    "boundary": "rgb8: decoded 8-bit pixels in (read_img's input), crop()+write_rgb 8-bit mosaic out; "
+                                "u8<->f32 conversions and crop run on the device inside the timed region",
+                    "mat32f_boundary": {"value": world * mpx / f32_per_step, "ms_per_step": f32_per_step * 1e3,
+                                        "h2d_bytes_per_step": int(f32_h2d), "d2h_bytes_per_step": int(f32_d2h)},
+                    "single_job_latency_ms_mat32f": e2e_latency * 1e3,
+                    "single_job_value_mat32f": world * mpx / e2e_latency},
             "gpu_launches": int(launches * world),
             "roofline": roof,
             "cpu_baseline": cpu,

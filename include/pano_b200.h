@@ -220,6 +220,32 @@ int pano_blend(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_bl
 int pano_blend_dev(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g,
                    int bands, const pano_params* p, float* d_out_hwc, int out_w, int out_h);
 
+/* ------------------------------------------------ 8-bit image boundary
+ * The byte formats either side of the path: decoded 8-bit
+ * pixels in, 8-bit mosaic out, so 3 B/px cross PCIe instead of 12.  All
+ * pointers are device pointers; work is queued on the context's stream. */
+/* read_img's conversion loop (lib/imgio.cc:75-88): channels == 3 -> every
+ * sample is (float)((double)v / 255.0); channels == 1 -> the grey value is
+ * replicated to R,G,B WITHOUT the division (imgio.cc:84-87).  d_pix is
+ * h×w×channels interleaved u8; d_out_hwc is h×w×3 f32. */
+int pano_rgb8_to_mat32f_dev(pano_ctx* ctx, const unsigned char* d_pix, int w, int h, int channels,
+                            float* d_out_hwc);
+/* The same for n images in one launch (the calc_feature loop reads every image,
+ * stitcherbase.cc:14-17).  d_pix[i] must be 4-byte, d_out_hwc[i] 16-byte aligned;
+ * the pointer arrays themselves are host arrays of device pointers. */
+int pano_rgb8_to_mat32f_batch_dev(pano_ctx* ctx, int n, const unsigned char* const* d_pix, const int* w,
+                                  const int* h, const int* channels, float* const* d_out_hwc);
+/* crop()'s rectangle (lib/imgproc.cc:200-235): the largest axis-aligned
+ * rectangle of pixels whose max(r,g,b) >= 0, first maximum in (line, column)
+ * order.  d_rect receives {x0, y0, width, height} (device int[4]). */
+int pano_crop_rect_dev(pano_ctx* ctx, const float* d_mat_hwc, int w, int h, int* d_rect);
+/* write_rgb's conversion loop (lib/imgio.cc:98-113) applied to the sub-rectangle
+ * d_rect = {x0,y0,cw,ch} (device int[4]; NULL = whole image): every sample is
+ * (unsigned char)((v < 0 ? 1 : v) * 255), i.e. Color::NO turns white.  Output
+ * is packed ch×cw×3 u8 at d_out (capacity h*w*3). */
+int pano_mat32f_to_rgb8_dev(pano_ctx* ctx, const float* d_mat_hwc, int w, int h, const int* d_rect,
+                            unsigned char* d_out);
+
 /* ------------------------------------------------------- device utilities */
 int pano_dev_alloc(pano_ctx* ctx, size_t bytes, void** d_ptr);
 int pano_dev_free(pano_ctx* ctx, void* d_ptr);

@@ -71,6 +71,10 @@ def _load():
                                  C.c_int, P, _fp, C.c_int, C.c_int]),
         "pano_blend_dev": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PanoBlendImage),
                                      C.POINTER(PanoBlendGeom), C.c_int, P, C.c_void_p, C.c_int, C.c_int]),
+        "pano_rgb8_to_mat32f_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+        "pano_rgb8_to_mat32f_batch_dev": (C.c_int, [C.c_void_p, C.c_int, _vpp, _ip, _ip, _ip, _vpp]),
+        "pano_crop_rect_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+        "pano_mat32f_to_rgb8_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
         "pano_dev_alloc": (C.c_int, [C.c_void_p, C.c_size_t, _vpp]),
         "pano_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
         "pano_dev_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -457,3 +461,66 @@ class Engine:
         arr, g = self._blend_args(ptrs, shapes, items, geom)
         self._check(LIB.pano_blend_dev(self._h, len(ptrs), arr, C.byref(g), bands, C.byref(params),
                                        C.c_void_p(d_out), out_w, out_h))
+
+    # ---- 8-bit boundary: read_img / crop / write_rgb formats (device pointers)
+    def rgb8_to_mat32f_batch_dev(self, d_pix, ws, hs, channels, d_out):
+        """u8 -> f32 for n images in one launch (read_img's conversion, imgio.cc:75-88)."""
+        n = len(d_pix)
+        src = (C.c_void_p * n)(*d_pix)
+        dst = (C.c_void_p * n)(*d_out)
+        self._check(LIB.pano_rgb8_to_mat32f_batch_dev(self._h, n, src, (C.c_int * n)(*ws), (C.c_int * n)(*hs),
+                                                      (C.c_int * n)(*channels), dst))
+
+    def rgb8_to_mat32f_dev(self, d_pix, w, h, channels, d_out):
+        self._check(LIB.pano_rgb8_to_mat32f_dev(self._h, C.c_void_p(d_pix), w, h, channels, C.c_void_p(d_out)))
+
+    def crop_rect_dev(self, d_mat, w, h, d_rect):
+        """crop()'s rectangle (imgproc.cc:200-235) into device int[4] {x0,y0,w,h}."""
+        self._check(LIB.pano_crop_rect_dev(self._h, C.c_void_p(d_mat), w, h, C.c_void_p(d_rect)))
+
+    def mat32f_to_rgb8_dev(self, d_mat, w, h, d_rect, d_out):
+        """write_rgb's conversion (imgio.cc:98-113) of the rectangle d_rect (0/None = whole image)."""
+        self._check(LIB.pano_mat32f_to_rgb8_dev(self._h, C.c_void_p(d_mat), w, h, C.c_void_p(d_rect or 0),
+                                                C.c_void_p(d_out)))
+
+    # numpy conveniences for tests
+    def read_img_rgb8(self, pix):
+        pix = np.ascontiguousarray(pix, np.uint8)
+        h, w = pix.shape[:2]
+        ch = 1 if pix.ndim == 2 else pix.shape[2]
+        d_in = self.dev_alloc(max(pix.nbytes, 256))
+        d_out = self.dev_alloc(h * w * 12)
+        out = np.empty((h, w, 3), np.float32)
+        try:
+            self.dev_upload(d_in, pix)
+            self.rgb8_to_mat32f_dev(d_in, w, h, ch, d_out)
+            self.dev_download(out, d_out)
+        finally:
+            self.dev_free(d_in)
+            self.dev_free(d_out)
+        return out
+
+    def crop_write_rgb8(self, mat, crop=True):
+        """Returns (rect or None, 8-bit pixels of the (cropped) mosaic)."""
+        mat = np.ascontiguousarray(mat, np.float32)
+        h, w = mat.shape[:2]
+        d_mat = self.dev_alloc(mat.nbytes)
+        d_rect = self.dev_alloc(256)
+        d_out = self.dev_alloc(max(h * w * 3, 256))
+        rect = np.zeros(4, np.int32)
+        out = np.empty(h * w * 3, np.uint8)
+        try:
+            self.dev_upload(d_mat, mat)
+            if crop:
+                self.crop_rect_dev(d_mat, w, h, d_rect)
+            self.mat32f_to_rgb8_dev(d_mat, w, h, d_rect if crop else 0, d_out)
+            self.dev_download(out, d_out)
+            if crop:
+                self.dev_download(rect, d_rect)
+        finally:
+            for p_ in (d_mat, d_rect, d_out):
+                self.dev_free(p_)
+        if not crop:
+            return None, out.reshape(h, w, 3)
+        cw, ch = int(rect[2]), int(rect[3])
+        return rect, out[:cw * ch * 3].reshape(ch, cw, 3).copy()

@@ -273,11 +273,14 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
   double* d_tab = nullptr;
   float4 *d_cur = nullptr, *d_next = nullptr, *d_tmp = nullptr;
   unsigned char *d_mask = nullptr, *d_tmask = nullptr;
-  cudaError_t e;
   if ((rc = ctx_alloc(ctx, (void**)&d_imgs, n * sizeof(BlendImg)))) goto done;
   if ((rc = ctx_alloc(ctx, (void**)&d_tab, std::max<size_t>(tab.size(), 1) * sizeof(double)))) goto done;
-  if ((rc = ctx_put(ctx, d_imgs, job.imgs.data(), n * sizeof(BlendImg)))) goto done;
-  if (!tab.empty() && (rc = ctx_put(ctx, d_tab, tab.data(), tab.size() * sizeof(double)))) goto done;
+  {
+    void* dsts[2] = {d_imgs, d_tab};
+    const void* srcs[2] = {job.imgs.data(), tab.data()};
+    size_t sizes[2] = {n * sizeof(BlendImg), tab.size() * sizeof(double)};
+    if ((rc = ctx_put_many(ctx, 2, dsts, srcs, sizes))) goto done;
+  }
   job.g.projection = g->projection; job.g.res_x = g->res_x; job.g.res_y = g->res_y;
   job.g.min_x = g->proj_min_x; job.g.min_y = g->proj_min_y;
   job.g.col_sin = d_tab; job.g.col_cos = d_tab + ncol; job.g.row_tan = d_tab + 2 * ncol;

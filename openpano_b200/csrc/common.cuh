@@ -80,6 +80,10 @@ int  ctx_fetch(pano_ctx* ctx, void* d_dst, const void* h_pinned_src, size_t byte
 int  ctx_store(pano_ctx* ctx, void* h_pinned_dst, const void* d_src, size_t bytes);
 int  ctx_put(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 int  ctx_zero(pano_ctx* ctx, void* d_dst, size_t bytes);
+// up to CTX_MAX_SEGS moves in one launch; h_src[i] == nullptr zero-fills d_dst[i]
+#define CTX_MAX_SEGS 8
+int  ctx_put_many(pano_ctx* ctx, int n, void* const* d_dst, const void* const* h_src, const size_t* bytes);
+int  ctx_store_many(pano_ctx* ctx, int n, void* const* h_pinned_dst, const void* const* d_src, const size_t* bytes);
 void ctx_prof_begin(pano_ctx* ctx, const char* name);
 void ctx_prof_end(pano_ctx* ctx);
 

@@ -144,6 +144,70 @@ int ctx_zero(pano_ctx* ctx, void* d_dst, size_t bytes) {
   return PANO_OK;
 }
 
+// Several small moves in ONE launch (segment table passed by value): every launch that
+// touches host memory pays a PCIe round trip, which stretches to tens of microseconds
+// while image uploads / mosaic downloads keep the link busy.
+struct CopySegs {
+  uint32_t* dst[CTX_MAX_SEGS];
+  const uint32_t* src[CTX_MAX_SEGS];   // nullptr = fill with zeros
+  unsigned words[CTX_MAX_SEGS];
+};
+__global__ void k_copy_segs(CopySegs s) {
+  uint32_t* d = s.dst[blockIdx.y];
+  const uint32_t* q = s.src[blockIdx.y];
+  const unsigned n = s.words[blockIdx.y];
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) d[i] = q ? q[i] : 0u;
+}
+
+static int launch_segs(pano_ctx* ctx, const CopySegs& segs, int n, size_t max_words) {
+  if (!n) return PANO_OK;
+  dim3 grid((unsigned)small_grid(max_words), (unsigned)n);
+  PANO_LAUNCH(ctx, "k_copy_u32", k_copy_segs, grid, 256, 0, segs);
+  return PANO_OK;
+}
+
+int ctx_put_many(pano_ctx* ctx, int n, void* const* d_dst, const void* const* h_src, const size_t* bytes) {
+  if (n > CTX_MAX_SEGS) return ctx_fail(ctx, PANO_ERR_INVALID, "ctx_put_many: %d segments", n);
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) if (h_src[i]) total += align_up(bytes[i] + 4, 64);
+  char* st = total ? (char*)ctx_ring(ctx, total) : nullptr;
+  if (total && !st) return ctx_fail(ctx, PANO_ERR_CUDA, "pinned ring allocation failed");
+  CopySegs segs;
+  int m = 0;
+  size_t max_words = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!bytes[i]) continue;
+    segs.dst[m] = (uint32_t*)d_dst[i];
+    segs.words[m] = (unsigned)((bytes[i] + 3) / 4);
+    if (h_src[i]) {
+      memcpy(st, h_src[i], bytes[i]);
+      segs.src[m] = (const uint32_t*)st;
+      st += align_up(bytes[i] + 4, 64);
+    } else {
+      segs.src[m] = nullptr;
+    }
+    max_words = std::max(max_words, (size_t)segs.words[m]);
+    ++m;
+  }
+  return launch_segs(ctx, segs, m, max_words);
+}
+
+int ctx_store_many(pano_ctx* ctx, int n, void* const* h_pinned_dst, const void* const* d_src, const size_t* bytes) {
+  if (n > CTX_MAX_SEGS) return ctx_fail(ctx, PANO_ERR_INVALID, "ctx_store_many: %d segments", n);
+  CopySegs segs;
+  int m = 0;
+  size_t max_words = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!bytes[i]) continue;
+    segs.dst[m] = (uint32_t*)h_pinned_dst[i];
+    segs.src[m] = (const uint32_t*)d_src[i];
+    segs.words[m] = (unsigned)((bytes[i] + 3) / 4);
+    max_words = std::max(max_words, (size_t)segs.words[m]);
+    ++m;
+  }
+  return launch_segs(ctx, segs, m, max_words);
+}
+
 static cudaEvent_t get_event(pano_ctx* ctx) {
   if (!ctx->event_pool.empty()) { cudaEvent_t e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return e; }
   cudaEvent_t e;

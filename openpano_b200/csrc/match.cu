@@ -480,9 +480,15 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
   b.n_counters = 8 + 3 * n_sides;
   if ((rc = ctx_alloc(ctx, (void**)&b.counters, b.n_counters * sizeof(int)))) return rc;
   const void* tsrc = tensor ? (const void*)pl.tc_tasks.data() : (const void*)pl.exact_tasks.data();
-  if ((rc = ctx_put(ctx, b.tasks, tsrc, bt)) || (rc = ctx_put(ctx, b.pairs, pl.pairs.data(), bp)) ||
-      (rc = ctx_put(ctx, b.sides, pl.sides.data(), bs)) || (rc = ctx_zero(ctx, b.counters, b.n_counters * sizeof(int))))
-    return rc;
+  const size_t bg = tensor ? pl.gsides.size() * sizeof(TcGatherSide) : 0;
+  if (bg && (rc = ctx_alloc(ctx, (void**)&b.gsides, bg))) return rc;
+  {
+    // plan tables + counter reset in one launch
+    void* dsts[5] = {b.tasks, b.pairs, b.sides, b.counters, b.gsides};
+    const void* srcs[5] = {tsrc, pl.pairs.data(), pl.sides.data(), nullptr, pl.gsides.data()};
+    size_t sizes[5] = {bt, bp, bs, b.n_counters * sizeof(int), bg};
+    if ((rc = ctx_put_many(ctx, 5, dsts, srcs, sizes))) return rc;
+  }
   if (pl.pairs.empty()) return PANO_OK;
   const float rs = ratio * ratio;
   dim3 gd(std::max(1, ceil_div(pl.max_small, 256)), (unsigned)pl.pairs.size());
@@ -521,9 +527,7 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
     const int block_cap = (int)std::min<size_t>(std::max<size_t>(pl.tc_tasks.size(), 1), 4096);
     const size_t grow = (size_t)block_cap * 128;
     TcFilter f;
-    if ((rc = ctx_alloc(ctx, (void**)&b.gsides, pl.gsides.size() * sizeof(TcGatherSide))) ||
-        (rc = ctx_put(ctx, b.gsides, pl.gsides.data(), pl.gsides.size() * sizeof(TcGatherSide))) ||
-        (rc = ctx_alloc(ctx, (void**)&b.list_rows, nres * sizeof(int))) ||
+    if ((rc = ctx_alloc(ctx, (void**)&b.list_rows, nres * sizeof(int))) ||
         (rc = ctx_alloc(ctx, (void**)&b.gtasks, (size_t)block_cap * sizeof(TcTask))) ||
         (rc = ctx_alloc(ctx, (void**)&b.gq, (size_t)block_cap * tc_block_bytes())) ||
         (rc = ctx_alloc(ctx, (void**)&b.g_meta, grow * sizeof(int2))) ||

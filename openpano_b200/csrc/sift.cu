@@ -1003,21 +1003,14 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
   fs->base.resize(n);
   for (int i = 0; i < n; ++i) fs->base[i] = (long long)i * SIFT_DESC_CAP;
 
-  // metadata upload through the pinned staging buffer
+  // metadata upload + candidate-counter reset: one launch through the pinned ring
   {
-    size_t b_img = n * sizeof(ImgMeta), b_oct = wk->h_oct.size() * sizeof(OctMeta), b_t = tiles.size() * sizeof(BlurTile);
-    char* st = (char*)ctx_ring(ctx, b_img + b_oct + b_t + 192);
-    if (!st) { sift_work_free(ctx, wk); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned alloc failed"); }
-    char* st_oct = st + align_up(b_img, 64);
-    char* st_t = st_oct + align_up(b_oct, 64);
-    memcpy(st, wk->h_img.data(), b_img);
-    memcpy(st_oct, wk->h_oct.data(), b_oct);
-    memcpy(st_t, tiles.data(), b_t);
-    SIFT_TRY(ctx_fetch(ctx, wk->d_img, st, b_img));
-    SIFT_TRY(ctx_fetch(ctx, wk->d_oct, st_oct, b_oct));
-    SIFT_TRY(ctx_fetch(ctx, wk->d_tiles, st_t, b_t));
+    void* dsts[4] = {wk->d_img, wk->d_oct, wk->d_tiles, wk->cand_count};
+    const void* srcs[4] = {wk->h_img.data(), wk->h_oct.data(), tiles.data(), nullptr};
+    size_t sizes[4] = {n * sizeof(ImgMeta), wk->h_oct.size() * sizeof(OctMeta), tiles.size() * sizeof(BlurTile),
+                       n * sizeof(int)};
+    SIFT_TRY(ctx_put_many(ctx, 4, dsts, srcs, sizes));
   }
-  SIFT_TRY(ctx_zero(ctx, wk->cand_count, n * sizeof(int)));
 
 #define SIFT_LAUNCH(name, kernel, grid, block, smem, ...)                                   \
   do {                                                                                      \
@@ -1082,8 +1075,12 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     fs->h_count_pinned = (int*)ctx_small_pinned_get(ctx, (size_t)2 * n * sizeof(int) + 16, &fs->h_count_cap);
     if (!fs->h_count_pinned) { sift_work_free(ctx, wk); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned allocation failed"); }
   }
-  SIFT_TRY(ctx_store(ctx, fs->h_count_pinned, fs->d_count, n * sizeof(int)));
-  SIFT_TRY(ctx_store(ctx, fs->h_count_pinned + n, wk->cand_count, n * sizeof(int)));
+  {
+    void* dsts[2] = {fs->h_count_pinned, fs->h_count_pinned + n};
+    const void* srcs[2] = {fs->d_count, wk->cand_count};
+    size_t sizes[2] = {n * sizeof(int), n * sizeof(int)};
+    SIFT_TRY(ctx_store_many(ctx, 2, dsts, srcs, sizes));
+  }
   if (!fs->counts_ready) fs->counts_ready = ctx_sync_event_get(ctx);
   SIFT_CUDA(cudaEventRecord(fs->counts_ready, ctx->stream));
   fs->counts_on_host = false;

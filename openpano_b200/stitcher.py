@@ -130,13 +130,22 @@ class PipelinedStitcher:
     host while the match lists come back, and that is when the next upload flies.
     """
 
-    def __init__(self, device: int, params=None, depth: int = 2):
+    def __init__(self, device: int, params=None, depth: int = 2, rgb8: bool = False, crop: bool = True):
+        """rgb8: the host side speaks the reference's FILE formats instead of Mat32f —
+        decoded 8-bit pixels in (what read_img starts from, imgio.cc:72) and the 8-bit
+        mosaic out (what write_rgb saves, imgio.cc:98-113, after crop() when `crop`,
+        main.cc:226-229) — so 3 B/px cross PCIe each way instead of 12.  The conversions
+        run on the device with the reference's arithmetic.  The output buffer then
+        holds a 256-byte header (int32 x0, y0, width, height of the crop rectangle)
+        followed by height*width*3 packed bytes."""
         self.params = params or default_params()
         self.up = Engine(device)
         self.cmp = Engine(device)
         self.dn = Engine(device)
         self.depth = depth
-        self.slots = [dict(imgs=None, out=None, shapes=None, offs=None, out_wh=None,
+        self.rgb8 = rgb8
+        self.crop = crop
+        self.slots = [dict(imgs=None, out=None, shapes=None, offs=None, out_wh=None, pix=None, pix_offs=None, out8=None,
                            ev_up=self.up.event_create(), ev_cmp=self.cmp.event_create(),
                            ev_dn=self.dn.event_create(), busy=False) for _ in range(depth)]
         self._next = 0
@@ -151,12 +160,36 @@ class PipelinedStitcher:
                 total += (h * w * 3 * 4 + 255) // 256 * 256
             s["imgs"] = self.cmp.dev_alloc(max(total, 256))
             s["shapes"], s["offs"] = list(shapes), offs
+            if self.rgb8:
+                if s["pix"]:
+                    self.cmp.dev_free(s["pix"])
+                poffs, ptotal = [], 0
+                for (h, w) in shapes:
+                    poffs.append(ptotal)
+                    ptotal += (h * w * 3 + 255) // 256 * 256
+                s["pix"] = self.cmp.dev_alloc(max(ptotal, 256))
+                s["pix_offs"] = poffs
         if s["out_wh"] != out_wh:
             if s["out"]:
                 self.cmp.dev_free(s["out"])
             s["out"] = self.cmp.dev_alloc(max(out_wh[0] * out_wh[1] * 3 * 4, 256))
+            if self.rgb8:
+                if s["out8"]:
+                    self.cmp.dev_free(s["out8"])
+                s["out8"] = self.cmp.dev_alloc(self.out_bytes(out_wh))
             s["out_wh"] = tuple(out_wh)
             self.cmp.sync()
+
+    RGB8_HEADER = 256
+
+    def out_bytes(self, out_wh) -> int:
+        """Size of the host buffer run() fills for a canvas of out_wh."""
+        if self.rgb8:
+            return self.RGB8_HEADER + out_wh[0] * out_wh[1] * 3
+        return out_wh[0] * out_wh[1] * 3 * 4
+
+    def in_bytes(self, shapes) -> int:
+        return sum(h * w * 3 * (1 if self.rgb8 else 4) for (h, w) in shapes)
 
     def stage(self, host_ptrs, shapes, out_wh) -> int:
         k = self._next
@@ -167,8 +200,12 @@ class PipelinedStitcher:
             s["busy"] = False
         self._ensure(s, list(shapes), tuple(out_wh))
         self.up.event_wait(s["ev_cmp"])            # its previous compute no longer reads these images
-        for p, o, (h, w) in zip(host_ptrs, s["offs"], shapes):
-            self.up.dev_upload_async(s["imgs"] + o, p, h * w * 3 * 4)
+        if self.rgb8:
+            for p, o, (h, w) in zip(host_ptrs, s["pix_offs"], shapes):
+                self.up.dev_upload_async(s["pix"] + o, p, h * w * 3)
+        else:
+            for p, o, (h, w) in zip(host_ptrs, s["offs"], shapes):
+                self.up.dev_upload_async(s["imgs"] + o, p, h * w * 3 * 4)
         self.up.event_record(s["ev_up"])
         return k
 
@@ -177,15 +214,26 @@ class PipelinedStitcher:
         shapes = s["shapes"]
         ptrs = [s["imgs"] + o for o in s["offs"]]
         self.cmp.event_wait(s["ev_up"])
+        if self.rgb8:
+            self.cmp.rgb8_to_mat32f_batch_dev([s["pix"] + o for o in s["pix_offs"]], [q[1] for q in shapes],
+                                              [q[0] for q in shapes], [3] * len(shapes), ptrs)
         fs = self.cmp.sift_detect_batch_ptr(ptrs, [q[1] for q in shapes], [q[0] for q in shapes], self.params,
                                             device=True)
         matches = self.cmp.match_pairs(fs, pairs, self.params)       # host waits here; copies keep flowing
         self.cmp.event_wait(s["ev_dn"])                               # previous mosaic of this slot is out
-        self.cmp.blend_dev(ptrs, shapes, items, geom, s["out"], s["out_wh"][0], s["out_wh"][1], bands, self.params)
+        ow, oh = s["out_wh"]
+        self.cmp.blend_dev(ptrs, shapes, items, geom, s["out"], ow, oh, bands, self.params)
+        if self.rgb8:
+            if self.crop:
+                self.cmp.crop_rect_dev(s["out"], ow, oh, s["out8"])
+            self.cmp.mat32f_to_rgb8_dev(s["out"], ow, oh, s["out8"] if self.crop else 0, s["out8"] + self.RGB8_HEADER)
         self.cmp.event_record(s["ev_cmp"])
         fs.free()
         self.dn.event_wait(s["ev_cmp"])
-        self.dn.dev_download_async(out_host_ptr, s["out"], s["out_wh"][0] * s["out_wh"][1] * 3 * 4)
+        if self.rgb8:
+            self.dn.dev_download_async(out_host_ptr, s["out8"], self.out_bytes((ow, oh)))
+        else:
+            self.dn.dev_download_async(out_host_ptr, s["out"], ow * oh * 3 * 4)
         self.dn.event_record(s["ev_dn"])
         s["busy"] = True
         return (k, matches)
@@ -207,8 +255,22 @@ class PipelinedStitcher:
                 self.cmp.dev_free(s["imgs"])
             if s["out"]:
                 self.cmp.dev_free(s["out"])
+            for key in ("pix", "out8"):
+                if s[key]:
+                    self.cmp.dev_free(s[key])
             for key in ("ev_up", "ev_cmp", "ev_dn"):
                 Engine.event_destroy(s[key])
         self.slots = []
         for e in (self.up, self.cmp, self.dn):
             e.close()
+
+
+def unpack_rgb8_mosaic(buf: np.ndarray, out_wh, cropped: bool = True):
+    """View of the 8-bit mosaic PipelinedStitcher(rgb8=True).run() wrote into `buf`
+    (uint8, out_bytes long).  Returns (rect (x0, y0, w, h), H×W×3 uint8 view)."""
+    hdr = PipelinedStitcher.RGB8_HEADER
+    if cropped:
+        x0, y0, w, h = (int(v) for v in buf[:16].view(np.int32))
+    else:
+        x0, y0, w, h = 0, 0, out_wh[0], out_wh[1]
+    return (x0, y0, w, h), buf[hdr:hdr + w * h * 3].reshape(h, w, 3)

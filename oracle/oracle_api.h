@@ -53,6 +53,15 @@ extern "C" {
                    const pano_blend_image* bimgs, const pano_blend_geom* g, int bands, \
                    const pano_params* p, float* out_hwc, int out_w, int out_h,         \
                    int* n_feat, int* n_match, double* seconds);                        \
+  /* read_img's conversion of decoded 8-bit pixels (imgio.cc:67-90); channels 1|3 */   \
+  int  P##_read_img_rgb8(const unsigned char* pix, int w, int h, int channels,         \
+                         float* out_hwc);                                              \
+  /* crop (imgproc.cc:200-235): out receives the cropped pixels (capacity w*h*3),      \
+   * rect = {x0, y0, width, height}; the ref_ build cannot know x0,y0 (crop returns    \
+   * only the pixels) and sets them to -1 */                                           \
+  int  P##_crop(const float* mat_hwc, int w, int h, int* rect, float* out_hwc);        \
+  /* write_rgb's conversion to 8-bit (imgio.cc:98-113) */                              \
+  int  P##_write_rgb8(const float* mat_hwc, int w, int h, unsigned char* out);         \
   /* number of host threads the library will use (1 for the scalar port) */            \
   int  P##_num_threads(void);
 

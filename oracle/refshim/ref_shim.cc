@@ -4,9 +4,10 @@
 // This file contains no algorithm: every call lands in a translation unit that
 // is compiled, unmodified, from /root/reference/src by oracle/Makefile.  The
 // only stand-ins are lib/matrix.cc (needs Eigen, absent here: see
-// matrix_standin.cc), read_img (file I/O, stubbed below) and a syntactic
-// Eigen/Dense stub so lib/imgproc.cc compiles (its two Eigen functions are off
-// the hot path and are never called).
+// matrix_standin.cc) and a syntactic Eigen/Dense stub so lib/imgproc.cc compiles
+// (its two Eigen functions are off the hot path and are never called).
+// lib/imgio.cc is built with -DDISABLE_JPEG (CImg's native PNM reader/writer and
+// the vendored lodepng need no external library); ref_imgio.cc drives it.
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -35,14 +36,6 @@
 #include "../oracle_api.h"
 
 using namespace pano;
-
-namespace pano {
-// imgio.cc (CImg + lodepng + libjpeg) is not part of the hot path.
-Mat32f read_img(const char*) {
-  fprintf(stderr, "ref_shim: read_img is stubbed\n");
-  abort();
-}
-}  // namespace pano
 
 namespace {
 

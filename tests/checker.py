@@ -150,7 +150,41 @@ class Checker:
                                   C.POINTER(PanoBlendImage), C.POINTER(PanoBlendGeom), C.c_int,
                                   C.POINTER(PanoParams), _fp, C.c_int, C.c_int, _ip, _ip, _dp]
         fn("num_threads").restype = C.c_int
+        _up = C.POINTER(C.c_ubyte)
+        fn("read_img_rgb8").argtypes = [_up, C.c_int, C.c_int, C.c_int, _fp]
+        fn("crop").argtypes = [_fp, C.c_int, C.c_int, _ip, _fp]
+        fn("write_rgb8").argtypes = [_fp, C.c_int, C.c_int, _up]
         self._fn = fn
+
+    # ---- 8-bit boundary (read_img / crop / write_rgb)
+    def read_img_rgb8(self, pix):
+        """pix: H×W×3 or H×W uint8 -> H×W×3 float32 as read_img produces it."""
+        pix = np.ascontiguousarray(pix, np.uint8)
+        h, w = pix.shape[:2]
+        ch = 1 if pix.ndim == 2 else pix.shape[2]
+        out = np.empty((h, w, 3), np.float32)
+        rc = self._fn("read_img_rgb8")(pix.ctypes.data_as(C.POINTER(C.c_ubyte)), w, h, ch, _f(out))
+        assert rc == 0
+        return out
+
+    def crop(self, mat):
+        """Returns (rect [x0,y0,w,h] — x0,y0 are -1 from the ref_ build — and the cropped pixels)."""
+        mat = np.ascontiguousarray(mat, np.float32)
+        h, w = mat.shape[:2]
+        rect = np.zeros(4, np.int32)
+        out = np.empty((h, w, 3), np.float32)
+        rc = self._fn("crop")(_f(mat), w, h, _i(rect), _f(out))
+        assert rc == 0
+        cw, ch = int(rect[2]), int(rect[3])
+        return rect, out.reshape(-1)[:cw * ch * 3].reshape(ch, cw, 3).copy()
+
+    def write_rgb8(self, mat):
+        mat = np.ascontiguousarray(mat, np.float32)
+        h, w = mat.shape[:2]
+        out = np.empty((h, w, 3), np.uint8)
+        rc = self._fn("write_rgb8")(_f(mat), w, h, out.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        assert rc == 0
+        return out
 
     def num_threads(self):
         return self._fn("num_threads")()

@@ -37,9 +37,25 @@ def plane_crc(a):
     return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest()[:8], np.uint64).copy()
 
 
+def imgio(ref):
+    """read_img / crop / write_rgb through the reference's own lib/imgio.cc + lib/imgproc.cc."""
+    from tests.golden_util import imgio_inputs
+    pix, grey, mos = imgio_inputs()
+    rect, cropped = ref.crop(mos)
+    np.savez_compressed(OUT / "imgio.npz", input_sha=np.array(sha(pix, grey, mos)),
+                        read_rgb=ref.read_img_rgb8(pix), read_grey=ref.read_img_rgb8(grey),
+                        crop_wh=rect[2:], cropped=cropped, write_full=ref.write_rgb8(mos),
+                        write_cropped=ref.write_rgb8(cropped))
+    print("imgio: crop", rect, cropped.shape)
+
+
 def main():
     ref = get_checker("ref")
     assert ref.num_threads() == 1
+    if sys.argv[1:] == ["imgio"]:      # add this fixture without rewriting the others
+        imgio(ref)
+        return
+    imgio(ref)
 
     # ---- SIFT chain on one 240x180 view
     img = synth.make_canvas(180, 240, 101)

@@ -43,6 +43,20 @@ def blend_inputs():
     return imgs, items, geom
 
 
+def imgio_inputs():
+    """(8-bit colour image, 8-bit grey image, f32 mosaic with Color::NO outside a slanted quadrilateral
+    and a few holes) for the read_img / crop / write_rgb fixtures."""
+    pix = (synth.make_canvas(60, 90, 105) * 255.0 + 0.5).astype(np.uint8)
+    grey = pix[..., 1].copy()
+    mos = synth.make_canvas(70, 110, 106)
+    yy, xx = np.mgrid[0:70, 0:110]
+    inside = (yy > 4 + 0.08 * xx) & (yy < 64 - 0.05 * xx) & (xx > 3 + 0.1 * yy) & (xx < 105 - 0.07 * yy)
+    mos[~inside] = -1.0
+    mos[30:33, 50:54] = -1.0
+    mos[10:12, 80:81] = -1.0
+    return pix, grey, mos
+
+
 def same_bits(a, b):
     a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
     if a.shape != b.shape or a.dtype != b.dtype:

@@ -91,3 +91,41 @@ def test_blend_projections(orc, ref, projection, bands, capfd):
     b = ref.blend(imgs, items, geom, bands)
     assert (a >= 0).mean() > 0.3
     assert gu.same_bits(a, b)
+
+
+def _random_mosaic(rng, h, w):
+    m = rng.rand(h, w, 3).astype(np.float32)
+    for _ in range(rng.randint(0, 6)):
+        y0, x0 = rng.randint(0, h), rng.randint(0, w)
+        m[y0:y0 + rng.randint(1, 8), x0:x0 + rng.randint(1, 10)] = -1
+    if rng.rand() < 0.4:
+        m[:rng.randint(0, 4)] = -1
+        m[:, :rng.randint(0, 5)] = -1
+    return m
+
+
+def test_imgio_read_write(orc, ref):
+    """read_img / write_rgb through the reference's imgio.cc (lossless PNM files) vs the restatement."""
+    rng = np.random.RandomState(11)
+    allv = np.arange(256, dtype=np.uint8).reshape(16, 16)
+    for pix in (rng.randint(0, 256, (37, 53, 3)).astype(np.uint8), np.stack([allv] * 3, -1), allv,
+                rng.randint(0, 256, (9, 31)).astype(np.uint8)):
+        assert np.array_equal(orc.read_img_rgb8(pix), ref.read_img_rgb8(pix))
+    m = _random_mosaic(rng, 40, 60)
+    m[0, 0] = (1.0, 0.0, 0.999999)
+    m[0, 1] = np.float32(1.0) / np.float32(255.0) * np.arange(1, 4, dtype=np.float32)
+    assert np.array_equal(orc.write_rgb8(m), ref.write_rgb8(m))
+
+
+def test_imgio_crop(orc, ref):
+    rng = np.random.RandomState(12)
+    cases = [_random_mosaic(rng, rng.randint(5, 60), rng.randint(5, 90)) for _ in range(25)]
+    cases.append(-np.ones((6, 7, 3), np.float32))                  # nothing valid: 0 x 1 result
+    cases.append(rng.rand(8, 9, 3).astype(np.float32))              # everything valid
+    for m in cases:
+        ro, co = orc.crop(m)
+        rr, cr = ref.crop(m)
+        assert np.array_equal(ro[2:], rr[2:])
+        assert np.array_equal(co, cr)
+        x0, y0, cw, ch = ro
+        assert np.array_equal(co, m[y0:y0 + ch, x0:x0 + cw])
