@@ -140,6 +140,14 @@ int pano_sift_detect(pano_ctx* ctx, const float* rgb_hwc, int w, int h,
 int pano_featureset_upload(pano_ctx* ctx, int n_images, const int* n_kp,
                            const float* const* desc, const double* const* coor_xy,
                            pano_featureset** out);
+/* The same from DEVICE pointers, queued on the context's stream without a host
+ * sync (the sources must stay valid until the stream has passed this call): the
+ * receiving side of the multi-GPU descriptor exchange. */
+int pano_featureset_import_dev(pano_ctx* ctx, int n_images, const int* n_kp,
+                               const float* const* d_desc, const double* const* d_coor_xy,
+                               pano_featureset** out);
+/* Copies image i's rows device-to-device (the sending side); either may be NULL. */
+int pano_featureset_export_dev(pano_featureset* fs, int image, double* d_coor_xy, float* d_desc);
 int pano_featureset_num_images(const pano_featureset* fs);
 /* Number of descriptors of image i (synchronizes on first use). */
 int pano_featureset_count(pano_featureset* fs, int image);
@@ -219,6 +227,14 @@ int pano_blend(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_bl
 /* Device-resident variant: imgs[k].rgb_hwc and d_out_hwc are device pointers. */
 int pano_blend_dev(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g,
                    int bands, const pano_params* p, float* d_out_hwc, int out_w, int out_h);
+
+/* Rows [row0, row1) of the same mosaic into d_out_rows ((row1-row0)×out_w×3 f32): the
+ * strip partition of the canvas across GPUs (every output pixel of
+ * LinearBlender::run is independent, blender.cc:37-96, so concatenated strips are
+ * bit-identical to pano_blend_dev).  bands must be 0. */
+int pano_blend_rows_dev(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g,
+                        int bands, const pano_params* p, float* d_out_rows, int out_w, int out_h,
+                        int row0, int row1);
 
 /* ------------------------------------------------ 8-bit image boundary
  * The byte formats either side of the path: decoded 8-bit

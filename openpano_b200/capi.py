@@ -71,6 +71,10 @@ def _load():
                                  C.c_int, P, _fp, C.c_int, C.c_int]),
         "pano_blend_dev": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PanoBlendImage),
                                      C.POINTER(PanoBlendGeom), C.c_int, P, C.c_void_p, C.c_int, C.c_int]),
+        "pano_blend_rows_dev": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PanoBlendImage), C.POINTER(PanoBlendGeom),
+                                          C.c_int, P, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "pano_featureset_import_dev": (C.c_int, [C.c_void_p, C.c_int, _ip, _vpp, _vpp, _vpp]),
+        "pano_featureset_export_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
         "pano_rgb8_to_mat32f_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
         "pano_rgb8_to_mat32f_batch_dev": (C.c_int, [C.c_void_p, C.c_int, _vpp, _ip, _ip, _ip, _vpp]),
         "pano_crop_rect_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
@@ -140,6 +144,10 @@ class FeatureSet:
         desc = np.zeros((n, 128), np.float32)
         self.eng._check(LIB.pano_featureset_download(self._h, i, _d(coor), _f(desc)))
         return coor, desc
+
+    def export_dev(self, i, d_coor, d_desc):
+        """Device-to-device copy of image i's rows (coordinates n×2 f64, descriptors n×128 f32)."""
+        self.eng._check(LIB.pano_featureset_export_dev(self._h, i, C.c_void_p(d_coor or 0), C.c_void_p(d_desc or 0)))
 
     def free(self):
         if self._h:
@@ -377,19 +385,36 @@ class Engine:
         self._check(LIB.pano_featureset_upload(self._h, n, cnt, dp, cp, C.byref(out)))
         return FeatureSet(self, out)
 
+    def featureset_import_dev(self, counts, d_descs, d_coors=None) -> FeatureSet:
+        """Featureset from device pointers (stream-ordered, no host sync)."""
+        n = len(counts)
+        cnt = (C.c_int * n)(*counts)
+        dp = (C.c_void_p * n)(*d_descs)
+        cp = (C.c_void_p * n)(*d_coors) if d_coors is not None else None
+        out = C.c_void_p()
+        self._check(LIB.pano_featureset_import_dev(self._h, n, cnt, dp, cp, C.byref(out)))
+        return FeatureSet(self, out)
+
+    def blend_rows_dev(self, ptrs, shapes, items, geom, d_out_rows, out_w, out_h, row0, row1, bands=0, params=None):
+        """Rows [row0, row1) of the mosaic into a (row1-row0)×out_w×3 device buffer."""
+        params = params or default_params()
+        arr, g = self._blend_args(ptrs, shapes, items, geom)
+        self._check(LIB.pano_blend_rows_dev(self._h, len(ptrs), arr, C.byref(g), bands, C.byref(params),
+                                            C.c_void_p(d_out_rows), out_w, out_h, row0, row1))
+
     # -- matching
     def match_pairs(self, fs: FeatureSet, pairs, params=None):
         params = params or default_params()
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         m = PanoMatches()
         self._check(LIB.pano_match_pairs(self._h, fs._h, len(pairs), _i(pairs), C.byref(params), C.byref(m)))
-        out = []
-        for k in range(m.n_pairs):
-            o, c = m.offset[k], m.count[k]
-            out.append(np.ctypeslib.as_array(m.idx, shape=(2 * m.offset[m.n_pairs],))[2 * o:2 * (o + c)]
-                       .reshape(-1, 2).copy() if c else np.zeros((0, 2), np.int32))
+        n = m.n_pairs
+        offs = np.ctypeslib.as_array(m.offset, shape=(n + 1,)).copy() if n else np.zeros(1, np.int32)
+        total = int(offs[n]) if n else 0
+        idx = (np.ctypeslib.as_array(m.idx, shape=(2 * total,)).reshape(-1, 2).copy() if total
+               else np.zeros((0, 2), np.int32))
         LIB.pano_matches_free(C.byref(m))
-        return out
+        return [idx[offs[k]:offs[k + 1]] for k in range(n)]
 
     def match_pairs_dev(self, fs: FeatureSet, pairs, params=None) -> int:
         params = params or default_params()

@@ -52,10 +52,11 @@ __device__ __forceinline__ void coor_func(const BlendImg& im, const BlendGeom& g
 // blender.cc:24-96.  lazy != 0 selects the LAZY_READ branch (exclusive max
 // bounds, accumulate then divide); otherwise the per-pixel branch.
 __global__ void k_linear_blend(const BlendImg* __restrict__ imgs, int n, BlendGeom g, int lazy, int ordered,
-                               float* __restrict__ out, int tw, int th) {
+                               float* __restrict__ out, int tw, int row0, int row1) {
+  // rows [row0, row1) of the canvas; `out` starts at row0 (a strip of a row-sharded mosaic, or the whole)
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  int i = blockIdx.y * blockDim.y + threadIdx.y;
-  if (j >= tw || i >= th) return;
+  int i = row0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= tw || i >= row1) return;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, wsum = 0.f;
   for (int k = 0; k < n; ++k) {
     const BlendImg& im = imgs[k];
@@ -74,7 +75,7 @@ __global__ void k_linear_blend(const BlendImg* __restrict__ imgs, int n, BlendGe
     s0 += c0 * w; s1 += c1 * w; s2 += c2 * w;
     wsum += w;
   }
-  float* p = out + ((size_t)i * tw + j) * 3;
+  float* p = out + ((size_t)(i - row0) * tw + j) * 3;
   if (lazy) {
     if (wsum != 0.f) { p[0] = s0 / wsum; p[1] = s1 / wsum; p[2] = s2 / wsum; }
     else { p[0] = -1.f; p[1] = -1.f; p[2] = -1.f; }
@@ -233,8 +234,13 @@ struct BlendJob {
   } while (0)
 
 static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g, int bands,
-                        const pano_params* p, float* d_out, int ow, int oh) {
+                        const pano_params* p, float* d_out, int ow, int oh, int row0, int row1) {
   if (!ctx || n <= 0 || !imgs || !g || !p || !d_out || bands < 0) return PANO_ERR_INVALID;
+  if (row0 < 0 || row1 > oh || row0 > row1)
+    return ctx_fail(ctx, PANO_ERR_INVALID, "blend: rows [%d, %d) outside the %d-row canvas", row0, row1, oh);
+  if (bands > 0 && (row0 != 0 || row1 != oh))
+    return ctx_fail(ctx, PANO_ERR_INVALID, "blend: row strips are implemented for the linear blender only");
+  if (row0 == row1) return PANO_OK;
   BlendJob job;
   job.imgs.resize(n);
   for (int k = 0; k < n; ++k) {
@@ -287,7 +293,9 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
   {
     dim3 b(32, 8), gt(ceil_div(tw, 32), ceil_div(th, 8));
     if (bands == 0) {
-      BL_LAUNCH(ctx, "k_linear_blend", k_linear_blend, gt, b, d_imgs, n, job.g, p->lazy_read, p->ordered_input, d_out, tw, th);
+      dim3 gs(ceil_div(tw, 32), ceil_div(row1 - row0, 8));
+      BL_LAUNCH(ctx, "k_linear_blend", k_linear_blend, gs, b, d_imgs, n, job.g, p->lazy_read, p->ordered_input, d_out, tw,
+                row0, row1);
     } else {
       size_t roi = (size_t)job.roi_total;
       if ((rc = ctx_alloc(ctx, (void**)&d_cur, roi * sizeof(float4)))) goto done;
@@ -339,7 +347,12 @@ int pano_blend_target_size(int n, const pano_blend_image* imgs, int* ow, int* oh
 
 int pano_blend_dev(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g, int bands,
                    const pano_params* p, float* d_out, int ow, int oh) {
-  return blend_device(ctx, n, imgs, g, bands, p, d_out, ow, oh);
+  return blend_device(ctx, n, imgs, g, bands, p, d_out, ow, oh, 0, oh);
+}
+
+int pano_blend_rows_dev(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g, int bands,
+                        const pano_params* p, float* d_out_rows, int ow, int oh, int row0, int row1) {
+  return blend_device(ctx, n, imgs, g, bands, p, d_out_rows, ow, oh, row0, row1);
 }
 
 int pano_blend(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g, int bands,
@@ -361,7 +374,7 @@ int pano_blend(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_bl
   }
   size_t ob = (size_t)std::max(ow, 0) * std::max(oh, 0) * 3 * sizeof(float);
   if (!rc) rc = ctx_alloc(ctx, (void**)&d_out, ob);
-  if (!rc) rc = blend_device(ctx, n, dimgs.data(), g, bands, p, d_out, ow, oh);
+  if (!rc) rc = blend_device(ctx, n, dimgs.data(), g, bands, p, d_out, ow, oh, 0, oh);
   if (!rc) {
     e = cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -484,8 +484,8 @@ int pano_sift_detect(pano_ctx* ctx, const float* rgb, int w, int h, const pano_p
   return pano_sift_detect_batch(ctx, 1, &rgb, &w, &h, p, out);
 }
 
-int pano_featureset_upload(pano_ctx* ctx, int n_images, const int* n_kp, const float* const* desc,
-                           const double* const* coor, pano_featureset** out) {
+static int featureset_build(pano_ctx* ctx, int n_images, const int* n_kp, const float* const* desc,
+                            const double* const* coor, pano_featureset** out, bool from_device) {
   if (!ctx || !out || n_images <= 0 || !n_kp || !desc) return PANO_ERR_INVALID;
   *out = nullptr;
   pano_featureset* fs = new pano_featureset;
@@ -504,18 +504,49 @@ int pano_featureset_upload(pano_ctx* ctx, int n_images, const int* n_kp, const f
   cudaError_t e = cudaSuccess;
   for (int i = 0; i < n_images && e == cudaSuccess; ++i) {
     if (!n_kp[i]) continue;
-    e = cudaMemcpyAsync(fs->d_desc + fs->base[i] * 128, desc[i], (size_t)n_kp[i] * 128 * sizeof(float),
-                        cudaMemcpyHostToDevice, ctx->stream);
+    const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    e = cudaMemcpyAsync(fs->d_desc + fs->base[i] * 128, desc[i], (size_t)n_kp[i] * 128 * sizeof(float), kind, ctx->stream);
     if (e == cudaSuccess && coor && coor[i])
-      e = cudaMemcpyAsync(fs->d_coor + fs->base[i] * 2, coor[i], (size_t)n_kp[i] * 2 * sizeof(double),
-                          cudaMemcpyHostToDevice, ctx->stream);
+      e = cudaMemcpyAsync(fs->d_coor + fs->base[i] * 2, coor[i], (size_t)n_kp[i] * 2 * sizeof(double), kind, ctx->stream);
   }
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(fs->d_count, fs->h_count.data(), n_images * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // sources are pageable host memory
+  if (e == cudaSuccess) {
+    if (from_device) {
+      if (ctx_put(ctx, fs->d_count, fs->h_count.data(), n_images * sizeof(int))) e = cudaErrorUnknown;
+    } else {
+      e = cudaMemcpyAsync(fs->d_count, fs->h_count.data(), n_images * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // sources are pageable host memory
+    }
+  }
   if (e != cudaSuccess) { rc = ctx_cuda(ctx, e, "featureset upload"); featureset_release(fs); return rc; }
   fs->counts_on_host = true;
   *out = fs;
+  return PANO_OK;
+}
+
+int pano_featureset_upload(pano_ctx* ctx, int n_images, const int* n_kp, const float* const* desc,
+                           const double* const* coor, pano_featureset** out) {
+  return featureset_build(ctx, n_images, n_kp, desc, coor, out, false);
+}
+
+int pano_featureset_import_dev(pano_ctx* ctx, int n_images, const int* n_kp, const float* const* d_desc,
+                               const double* const* d_coor, pano_featureset** out) {
+  return featureset_build(ctx, n_images, n_kp, d_desc, d_coor, out, true);
+}
+
+int pano_featureset_export_dev(pano_featureset* fs, int image, double* d_coor_xy, float* d_desc) {
+  if (!fs || image < 0 || image >= fs->n_images) return PANO_ERR_INVALID;
+  int rc = featureset_sync_counts(fs);
+  if (rc) return rc;
+  pano_ctx* ctx = fs->ctx;
+  const int n = fs->h_count[image];
+  if (n == 0) return PANO_OK;
+  if (d_desc) PANO_CUDA(ctx, cudaMemcpyAsync(d_desc, fs->d_desc + fs->base[image] * 128, (size_t)n * 128 * sizeof(float),
+                                             cudaMemcpyDeviceToDevice, ctx->stream));
+  if (d_coor_xy) {
+    if (!fs->d_coor) return ctx_fail(ctx, PANO_ERR_INVALID, "featureset has no coordinates");
+    PANO_CUDA(ctx, cudaMemcpyAsync(d_coor_xy, fs->d_coor + fs->base[image] * 2, (size_t)n * 2 * sizeof(double),
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+  }
   return PANO_OK;
 }
 

@@ -153,3 +153,151 @@ class EngineBackend:
             return self.eng.match_pairs(fs, [(remap[i], remap[j]) for i, j in pairs], self.params)
         finally:
             fs.free()
+
+
+# ----------------------------------------------------------------------------- device-resident path (NCCL)
+class DistributedStitcher:
+    """The sharded hot path with every payload resident in HBM (one instance per
+    rank, `torch.distributed` initialised with the NCCL backend, the Engine created
+    on torch's CURRENT non-default stream so engine kernels and NCCL order on it).
+
+      SIFT      owned images (k mod G)                              no collective
+      C1        descriptors + coordinates: export_dev -> ncclAllGather -> import_dev
+      match     the dealt pair tasks against the gathered featureset  no collective
+      results   match lists -> rank 0 (host objects, a few KB)
+      images    every rank blends a strip of every image: ncclAllGather of the inputs
+      blend     rows [r·H/G, (r+1)·H/G) of the canvas (LinearBlender pixels are
+                independent, blender.cc:37-96)                      no collective
+      C2        strips -> ncclAllGather -> the mosaic (bit-identical to one GPU)
+    """
+
+    def __init__(self, engine, params=None):
+        from ._abi import default_params
+        self.eng = engine
+        self.params = params or default_params()
+        self.ms = {}
+
+    def _timed(self, name, fn):
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn()
+        e1.record()
+        self._events.append((name, e0, e1))
+        return out
+
+    def run(self, owned: dict, n_images: int, shapes, pairs, items, geom):
+        """owned: {image index: cuda float32 tensor H×W×3} following shard_images().
+        Returns (matches on rank 0 / None elsewhere, mosaic tensor th×tw×3 on every rank)."""
+        import torch
+        dist = _dist()
+        eng, params = self.eng, self.params
+        world, rank = dist.get_world_size(), dist.get_rank()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        owners = [shard_images(n_images, world, r) for r in range(world)]
+        mine = owners[rank]
+        assert sorted(owned) == mine, "images must follow shard_images()"
+        self._events = []
+
+        # ---- SIFT on the owned images
+        def sift():
+            return eng.sift_detect_batch_ptr([owned[k].data_ptr() for k in mine], [shapes[k][1] for k in mine],
+                                             [shapes[k][0] for k in mine], params, device=True) if mine else None
+        fs_local = self._timed("sift", sift)
+
+        # ---- C1: all-gather of the descriptor sets
+        def exchange():
+            counts_t = torch.zeros(n_images, dtype=torch.int64, device=dev)
+            if mine:
+                counts_t[torch.tensor(mine, device=dev)] = torch.tensor([fs_local.count(q) for q in range(len(mine))],
+                                                                         dtype=torch.int64, device=dev)
+            dist.all_reduce(counts_t)
+            counts = [int(c) for c in counts_t.tolist()]
+            rows = [sum(counts[k] for k in owners[r]) for r in range(world)]
+            pad = max(max(rows), 1)
+            my_d = torch.zeros((pad, 128), dtype=torch.float32, device=dev)
+            my_c = torch.zeros((pad, 2), dtype=torch.float64, device=dev)
+            off = 0
+            for q, k in enumerate(mine):
+                fs_local.export_dev(q, my_c.data_ptr() + off * 16, my_d.data_ptr() + off * 512)
+                off += counts[k]
+            all_d = torch.empty((world * pad, 128), dtype=torch.float32, device=dev)
+            all_c = torch.empty((world * pad, 2), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(all_d, my_d)
+            dist.all_gather_into_tensor(all_c, my_c)
+            pd, pc = [0] * n_images, [0] * n_images
+            for r in range(world):
+                off = 0
+                for k in owners[r]:
+                    pd[k] = all_d.data_ptr() + (r * pad + off) * 512
+                    pc[k] = all_c.data_ptr() + (r * pad + off) * 16
+                    off += counts[k]
+            fs_all = eng.featureset_import_dev(counts, pd, pc)
+            return fs_all, counts, (all_d, all_c, my_d, my_c)
+        fs_all, counts, keep = self._timed("exchange_descriptors", exchange)
+        if fs_local is not None:
+            fs_local.free()
+
+        # ---- dealt pair tasks
+        dealt = deal_pairs(pairs, counts, world)
+        tasks = dealt[rank]
+        results = self._timed("match", lambda: eng.match_pairs(fs_all, [pairs[t] for t in tasks], params) if tasks else [])
+
+        # ---- match lists to every rank: per-task counts (all-reduce) + one padded all-gather
+        def gather_lists():
+            cnt = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
+            if tasks:
+                cnt[torch.tensor(tasks, device=dev)] = torch.tensor([len(m) for m in results], dtype=torch.int64, device=dev)
+            dist.all_reduce(cnt)
+            cnt_h = cnt.tolist()
+            pad = max(max(sum(cnt_h[t] for t in dealt[r]) for r in range(world)), 1)
+            my = torch.zeros((pad, 2), dtype=torch.int32, device=dev)
+            if tasks and sum(len(m) for m in results):
+                flat = np.concatenate([m for m in results if len(m)]).astype(np.int32)
+                my[:len(flat)] = torch.from_numpy(flat).to(dev)
+            allm = torch.empty((world * pad, 2), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(allm, my)
+            if rank != 0:
+                return None
+            host = allm.cpu().numpy()
+            full = [None] * len(pairs)
+            for r in range(world):
+                off = r * pad
+                for t in dealt[r]:
+                    full[t] = host[off:off + cnt_h[t]]
+                    off += cnt_h[t]
+            return full
+        matches = self._timed("gather_matches", gather_lists)
+
+        # ---- inputs of the blend: every image on every rank
+        def exchange_images():
+            max_px = max(h * w * 3 for (h, w) in shapes)
+            per_rank = max(len(o) for o in owners)
+            my_i = torch.zeros((per_rank, max_px), dtype=torch.float32, device=dev)
+            for q, k in enumerate(mine):
+                my_i[q, :owned[k].numel()] = owned[k].reshape(-1)
+            all_i = torch.empty((world * per_rank, max_px), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(all_i, my_i)
+            ptrs = [0] * n_images
+            for r in range(world):
+                for q, k in enumerate(owners[r]):
+                    ptrs[k] = all_i.data_ptr() + (r * per_rank + q) * max_px * 4
+            return ptrs, all_i
+        img_ptrs, keep_i = self._timed("exchange_images", exchange_images)
+
+        # ---- strip of the canvas, then C2
+        tw, th = max(it[2] for it in items), max(it[3] for it in items)
+        rows_per = (th + world - 1) // world
+        row0, row1 = min(th, rank * rows_per), min(th, (rank + 1) * rows_per)
+        strip = torch.empty((rows_per, tw, 3), dtype=torch.float32, device=dev)
+        self._timed("blend_strip", lambda: eng.blend_rows_dev(img_ptrs, shapes, items, geom, strip.data_ptr(), tw, th,
+                                                              row0, row1, 0, params))
+        mosaic = torch.empty((world * rows_per, tw, 3), dtype=torch.float32, device=dev)
+        self._timed("gather_strips", lambda: dist.all_gather_into_tensor(mosaic, strip))
+        torch.cuda.current_stream().synchronize()
+        self.ms = {}
+        for name, e0, e1 in self._events:
+            self.ms[name] = self.ms.get(name, 0.0) + e0.elapsed_time(e1)
+        fs_all.free()
+        del keep, keep_i
+        return matches, mosaic[:th]
