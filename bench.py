@@ -265,6 +265,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bands", type=int, default=0, help="0 = LinearBlender (reference default), k = MultiBandBlender{k}")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=2, help="concurrent stitch jobs per GPU in the e2e leg (StitchLanes)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -376,44 +377,39 @@ def main():
         # from pinned host memory and downloads its own mosaic + match lists.
         from openpano_b200.stitcher import PipelinedStitcher, unpack_rgb8_mosaic
 
-        def pipelined_leg(rgb8):
-            ps = PipelinedStitcher(local_rank, params, depth=3, rgb8=rgb8, crop=True)
+        def pipelined_leg(rgb8, n_lanes):
+            from openpano_b200.stitcher import StitchLanes
+            lanes = StitchLanes(local_rank, params, lanes=n_lanes, depth=3 if n_lanes == 1 else 2, rgb8=rgb8, crop=True)
+            n_out = 3 * n_lanes
             if rgb8:
                 src = [torch.from_numpy(p).pin_memory() for p in pix]
-                outs = [torch.empty(ps.out_bytes((out_w, out_h)), dtype=torch.uint8).pin_memory() for _ in range(3)]
+                outs = [torch.empty(lanes.out_bytes((out_w, out_h)), dtype=torch.uint8).pin_memory() for _ in range(n_out)]
             else:
                 src = host
-                outs = [host_out, torch.empty_like(host_out).pin_memory(), torch.empty_like(host_out).pin_memory()]
+                outs = [torch.empty_like(host_out).pin_memory() for _ in range(n_out)]
             ptrs = [t.data_ptr() for t in src]
 
-            def pipelined(n_jobs):
-                slot = ps.stage(ptrs, shapes, (out_w, out_h))
-                pending, total = None, 0
-                for i in range(n_jobs):
-                    nxt = ps.stage(ptrs, shapes, (out_w, out_h)) if i + 1 < n_jobs else None
-                    job = ps.run(slot, pairs, items, geom, outs[i % 3].data_ptr(), args.bands)
-                    if pending is not None:
-                        total += sum(len(x) for x in ps.wait(pending))
-                    pending, slot = job, nxt
-                total += sum(len(x) for x in ps.wait(pending))
-                return total
+            def jobs(n):
+                return [(ptrs, shapes, (out_w, out_h), pairs, items, geom, outs[i % n_out].data_ptr(), args.bands)
+                        for i in range(n)]
 
-            pipelined(3)
+            lanes.map(jobs(2 * n_out))
             torch.cuda.synchronize()
             barrier()
             t0 = time.perf_counter()
-            nm_pipe = pipelined(args.steps)
+            res = lanes.map(jobs(args.steps))
             torch.cuda.synchronize()
             secs = time.perf_counter() - t0
+            nm_pipe = sum(sum(len(x) for x in m) for m in res)
             assert nm_pipe == args.steps * nm_e2e, (nm_pipe, nm_e2e)      # every job returned the same matches
-            last = outs[(args.steps - 1) % 3]
+            last = outs[(args.steps - 1) % n_out]
             if rgb8:
                 rect, px = unpack_rgb8_mosaic(last.numpy(), (out_w, out_h))
                 assert rect[2] > out_w // 2 and rect[3] > out_h // 2 and int(px[rect[3] // 2, rect[2] // 2].max()) > 0
             else:
                 assert float(last[out_h // 2, out_w // 2, 0]) >= 0.0
-            h2d, d2h = ps.in_bytes(shapes), ps.out_bytes((out_w, out_h)) + nm_e2e * 8 + len(imgs) * 8
-            ps.close()
+            h2d, d2h = lanes.in_bytes(shapes), lanes.out_bytes((out_w, out_h)) + nm_e2e * 8 + len(imgs) * 8
+            lanes.close()
             t = torch.tensor([secs], device="cuda")
             if world > 1:
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -421,9 +417,10 @@ def main():
 
         # headline: the reference's file formats at the boundary (8-bit pixels in, cropped 8-bit
         # mosaic out; conversions and crop on the device).  Beside it the Mat32f boundary.
-        e2e_per_step, h2d_bytes, d2h_bytes = pipelined_leg(True)
+        e2e_per_step, h2d_bytes, d2h_bytes = pipelined_leg(True, args.lanes)
         e2e_value = world * mpx / e2e_per_step
-        f32_per_step, f32_h2d, f32_d2h = pipelined_leg(False)
+        one_lane_per_step = pipelined_leg(True, 1)[0] if args.lanes != 1 else e2e_per_step
+        f32_per_step, f32_h2d, f32_d2h = pipelined_leg(False, 1)
 
         # ---- roofline of the dominant kernel (event-timed per launch, separate untimed pass)
         roof = None
@@ -508,7 +505,9 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_per_step * 1e3,
-                    "mode": "PipelinedStitcher: consecutive jobs overlap H2D / kernels / D2H (depth 3)",
+                    "mode": f"StitchLanes: {args.lanes} concurrent pipelined jobs per GPU (one host thread each); every job "
+                            "uploads its own images and downloads its own mosaic + match lists",
+                    "one_lane": {"value": world * mpx / one_lane_per_step, "ms_per_step": one_lane_per_step * 1e3},
                     "boundary": "rgb8: decoded 8-bit pixels in (read_img's input), crop()+write_rgb 8-bit mosaic out; "
                                 "u8<->f32 conversions and crop run on the device inside the timed region",
                     "mat32f_boundary": {"value": world * mpx / f32_per_step, "ms_per_step": f32_per_step * 1e3,

@@ -123,11 +123,29 @@ __global__ void __launch_bounds__(256) k_crop_line(const unsigned* __restrict__ 
   const int c = line / CROP_CHUNK, bit = line % CROP_CHUNK;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  for (int k = tid; k < w; k += blockDim.x) {
-    // last invalid line <= `line` in column k
-    unsigned m = masks[(size_t)c * w + k] & (0xFFFFFFFFu >> (31 - bit));
-    int last = m ? c * CROP_CHUNK + 31 - __clz(m) : carry[(size_t)c * w + k];
-    hgt[k] = line - last;
+  {
+    // last invalid line <= `line` per column; loads batched 8 deep (the loop is latency-bound otherwise)
+    const unsigned* mrow = masks + (size_t)c * w;
+    const int* crow = carry + (size_t)c * w;
+    const unsigned lowmask = 0xFFFFFFFFu >> (31 - bit);
+    for (int k0 = tid; k0 < w; k0 += 8 * 256) {
+      unsigned m[8];
+      int cr[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u * 256;
+        m[u] = k < w ? __ldg(mrow + k) : 0u;
+        cr[u] = k < w ? __ldg(crow + k) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + u * 256;
+        if (k < w) {
+          const unsigned mm = m[u] & lowmask;
+          hgt[k] = line - (mm ? c * CROP_CHUNK + 31 - __clz(mm) : cr[u]);
+        }
+      }
+    }
   }
   __syncthreads();
 

@@ -282,14 +282,18 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
         tmem_ld32(lane_addr + (uint32_t)(as * 256 + c0), v);
         tmem_ld_wait();
         if (FILTER) {
+          // branch-free hit mask first: a conditional body inside the 256-way unrolled compare
+          // blows the loop up past the instruction cache (measured 3x slower per tile)
+          unsigned hit = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if ((int)(v[j] & 0xffffff00u) <= thr) {
-              const int col = t * 256 + c0 + j;
-              if (col < tk.t_n) {
-                const int slot = atomicAdd(&cand_cnt[grow], 1);
-                if (slot < TC_CAND_CAP) cand[(size_t)grow * TC_CAND_CAP + slot] = col;
-              }
+          for (int j = 0; j < 32; ++j) hit |= ((int)(v[j] & 0xffffff00u) <= thr) ? (1u << j) : 0u;
+          while (hit) {
+            const int j = __ffs(hit) - 1;
+            hit &= hit - 1;
+            const int col = t * 256 + c0 + j;
+            if (col < tk.t_n) {
+              const int slot = atomicAdd(&cand_cnt[grow], 1);
+              if (slot < TC_CAND_CAP) cand[(size_t)grow * TC_CAND_CAP + slot] = col;
             }
           }
         } else {

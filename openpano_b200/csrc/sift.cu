@@ -248,37 +248,62 @@ __device__ __forceinline__ uint32_t make_key(int oct, int scale, int y, int x) {
   return ((uint32_t)oct << 29) | ((uint32_t)scale << 26) | ((uint32_t)y << 13) | (uint32_t)x;
 }
 
-__global__ void k_extrema_scan(const OctMeta* __restrict__ octs, const float* __restrict__ arena,
-                               int nscale, float pre_color_thres, float diff_thres,
-                               int* __restrict__ cand_count, uint32_t* __restrict__ cand_keys) {
+#define EX_ROWS 4     // rows per thread (block 32x8 covers a 32x32 tile)
+#define EX_LEV 4      // centre levels fetched per batch
+
+__global__ void __launch_bounds__(256)
+k_extrema_scan(const OctMeta* __restrict__ octs, const float* __restrict__ arena,
+               int nscale, float pre_color_thres, float diff_thres,
+               int* __restrict__ cand_count, uint32_t* __restrict__ cand_keys) {
   const OctMeta om = octs[blockIdx.z];
-  int c = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  int r = blockIdx.y * blockDim.y + threadIdx.y + 1;
-  if (c >= om.w - 1 || r >= om.h - 1) return;
+  const int c = blockIdx.x * 32 + threadIdx.x + 1;
+  const int r0 = blockIdx.y * (8 * EX_ROWS) + threadIdx.y + 1;
+  if (c >= om.w - 1 || r0 >= om.h - 1) return;
   const float* dog = arena + om.dog_off;
-  const size_t o = (size_t)r * om.w + c;
-  for (int j = 1; j < nscale - 2; ++j) {
-    const float* now = dog + (size_t)j * om.plane;
-    float center = __ldg(now + o);
-    if (center < pre_color_thres) continue;
-    float cmp1 = center - diff_thres, cmp2 = center + diff_thres;
-    bool mx = true, mn = true;
+  // The scan is one dependent load per level for almost every pixel (the centre fails
+  // the colour threshold): fetch the centres of EX_ROWS rows x EX_LEV levels together
+  // so that 16 loads are in flight per thread, then test.
+  for (int j0 = 1; j0 < nscale - 2; j0 += EX_LEV) {
+    float cen[EX_ROWS][EX_LEV];
 #pragma unroll
-    for (int ds = -1; ds <= 1; ++ds) {
-      const float* pl = now + (ptrdiff_t)ds * om.plane;
+    for (int i = 0; i < EX_ROWS; ++i) {
+      const int r = r0 + 8 * i;
 #pragma unroll
-      for (int di = -1; di <= 1; ++di)
-#pragma unroll
-        for (int dj = -1; dj <= 1; ++dj) {
-          if (ds == 0 && di == 0 && dj == 0) continue;
-          float v = __ldg(pl + o + (ptrdiff_t)di * om.w + dj);
-          if (v >= cmp1) mx = false;
-          if (v <= cmp2) mn = false;
-        }
+      for (int l = 0; l < EX_LEV; ++l) {
+        const int j = j0 + l;
+        cen[i][l] = (r < om.h - 1 && j < nscale - 2) ? __ldg(dog + (size_t)j * om.plane + (size_t)r * om.w + c) : -1.f;
+      }
     }
-    if (mx || mn) {
-      int slot = atomicAdd(&cand_count[om.img], 1);
-      if (slot < SIFT_CAND_CAP) cand_keys[(size_t)om.img * SIFT_CAND_CAP + slot] = make_key(om.oct, j, r, c);
+#pragma unroll
+    for (int i = 0; i < EX_ROWS; ++i) {
+      const int r = r0 + 8 * i;
+      const size_t o = (size_t)r * om.w + c;
+#pragma unroll
+      for (int l = 0; l < EX_LEV; ++l) {
+        const float center = cen[i][l];
+        const int j = j0 + l;
+        if (center < pre_color_thres || r >= om.h - 1 || j >= nscale - 2) continue;
+        const float* now = dog + (size_t)j * om.plane;
+        float cmp1 = center - diff_thres, cmp2 = center + diff_thres;
+        bool mx = true, mn = true;
+#pragma unroll
+        for (int ds = -1; ds <= 1; ++ds) {
+          const float* pl = now + (ptrdiff_t)ds * om.plane;
+#pragma unroll
+          for (int di = -1; di <= 1; ++di)
+#pragma unroll
+            for (int dj = -1; dj <= 1; ++dj) {
+              if (ds == 0 && di == 0 && dj == 0) continue;
+              float v = __ldg(pl + o + (ptrdiff_t)di * om.w + dj);
+              if (v >= cmp1) mx = false;
+              if (v <= cmp2) mn = false;
+            }
+        }
+        if (mx || mn) {
+          int slot = atomicAdd(&cand_count[om.img], 1);
+          if (slot < SIFT_CAND_CAP) cand_keys[(size_t)om.img * SIFT_CAND_CAP + slot] = make_key(om.oct, j, r, c);
+        }
+      }
     }
   }
 }
@@ -1044,7 +1069,7 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     }
   }
   {
-    dim3 b(32, 8), g(ceil_div(max_w0 - 2, 32), ceil_div(max_h0 - 2, 8), n * n_oct);
+    dim3 b(32, 8), g(ceil_div(max_w0 - 2, 32), ceil_div(max_h0 - 2, 8 * EX_ROWS), n * n_oct);
     SIFT_LAUNCH("k_extrema_scan", k_extrema_scan, g, b, 0, wk->d_oct, wk->arena, n_scale, p->pre_color_thres,
                 p->judge_extrema_diff_thres, wk->cand_count, wk->cand_keys);
   }

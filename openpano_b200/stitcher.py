@@ -274,3 +274,71 @@ def unpack_rgb8_mosaic(buf: np.ndarray, out_wh, cropped: bool = True):
     else:
         x0, y0, w, h = 0, 0, out_wh[0], out_wh[1]
     return (x0, y0, w, h), buf[hdr:hdr + w * h * 3].reshape(h, w, 3)
+
+
+class StitchLanes:
+    """Several PipelinedStitcher lanes on ONE GPU, one host thread per lane.
+
+    A single lane leaves the compute stream idle whenever its host thread is between
+    two dependent phases of a job (feature counts -> match plan -> match lists ->
+    blend launch) and whenever a tiny metadata move waits on a busy PCIe link.  With
+    two lanes the other job's kernels fill those gaps (ctypes releases the GIL inside
+    every engine call, so the lanes' host threads run concurrently).
+
+        lanes = StitchLanes(device, params, lanes=2, rgb8=True)
+        results = lanes.map(jobs)     # jobs[i] = (host_ptrs, shapes, out_wh, pairs, items, geom, out_host_ptr, bands)
+    """
+
+    def __init__(self, device: int, params=None, lanes: int = 2, depth: int = 2, rgb8: bool = False, crop: bool = True):
+        self.lanes = [PipelinedStitcher(device, params, depth=depth, rgb8=rgb8, crop=crop) for _ in range(lanes)]
+
+    def out_bytes(self, out_wh):
+        return self.lanes[0].out_bytes(out_wh)
+
+    def in_bytes(self, shapes):
+        return self.lanes[0].in_bytes(shapes)
+
+    @staticmethod
+    def _run_lane(ps, jobs, results, errors):
+        try:
+            if not jobs:
+                return
+            it = iter(jobs)
+            idx, job = next(it)
+            slot = ps.stage(job[0], job[1], job[2])
+            pending = None
+            while job is not None:
+                nxt = next(it, None)
+                nslot = ps.stage(nxt[1][0], nxt[1][1], nxt[1][2]) if nxt is not None else None
+                handle = ps.run(slot, job[3], job[4], job[5], job[6], job[7])
+                if pending is not None:
+                    results[pending[0]] = ps.wait(pending[1])
+                pending = (idx, handle)
+                if nxt is None:
+                    break
+                (idx, job), slot = nxt, nslot
+            results[pending[0]] = ps.wait(pending[1])
+        except Exception as ex:  # surfaced by map()
+            errors.append(ex)
+
+    def map(self, jobs):
+        """Runs the jobs (in order within a lane, job i on lane i mod L); returns their match lists."""
+        import threading
+        jobs = list(jobs)
+        results = [None] * len(jobs)
+        errors = []
+        L = len(self.lanes)
+        threads = [threading.Thread(target=self._run_lane, args=(self.lanes[q], [(i, j) for i, j in enumerate(jobs) if i % L == q],
+                                                                 results, errors)) for q in range(L)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return results
+
+    def close(self):
+        for ps in self.lanes:
+            ps.close()
+        self.lanes = []

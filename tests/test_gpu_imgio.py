@@ -115,3 +115,37 @@ def test_pipelined_stitcher_rgb8_boundary(orc, crop):
             assert gu.same_bits(px, orc.write_rgb8(want))
         else:
             assert gu.same_bits(px, orc.write_rgb8(mosaic))
+
+
+def test_stitch_lanes_two_concurrent_jobs(orc):
+    """Two pipelined lanes (two host threads) sharing the GPU return, for every job, exactly what
+    the oracle chain returns — jobs differ, so a cross-talk between lanes would be seen."""
+    from openpano_b200 import synth
+    from openpano_b200._abi import default_params
+    from openpano_b200.stitcher import StitchLanes, ordered_pairs, unpack_rgb8_mosaic
+    p = default_params(ordered_input=1)
+    jobs, keep, expect = [], [], []
+    lanes = StitchLanes(0, p, lanes=2, depth=2, rgb8=True, crop=True)
+    for seed in (41, 42, 43, 44, 45):
+        n = 2 + seed % 2
+        imgs, org = synth.make_stack(n, 280, 190, 95, seed)
+        pix = [(im * 255.0 + 0.5).astype(np.uint8) for im in imgs]
+        items, geom = synth.translation_blend_setup(org, 280, 190)
+        pairs = ordered_pairs(n) if n > 2 else [(0, 1)]
+        ow, oh = max(it[2] for it in items), max(it[3] for it in items)
+        out = np.zeros(lanes.out_bytes((ow, oh)), np.uint8)
+        keep.append((pix, out))
+        jobs.append(([a.ctypes.data for a in pix], [a.shape[:2] for a in pix], (ow, oh), pairs, items, geom,
+                     out.ctypes.data, 0))
+        expect.append((pix, pairs, items, geom, (ow, oh), out))
+    got = lanes.map(jobs)
+    lanes.close()
+    for matches, (pix, pairs, items, geom, wh, out) in zip(got, expect):
+        f32 = [orc.read_img_rgb8(a) for a in pix]
+        descs = [orc.sift_detect(im, p)[1] for im in f32]
+        for (i, j), m in zip(pairs, matches):
+            assert np.array_equal(m, orc.match(descs[i], descs[j], p))
+        want_rect, want = orc.crop(orc.blend(f32, items, geom, 0, p))
+        rect, px = unpack_rgb8_mosaic(out, wh)
+        assert np.array_equal(rect, want_rect)
+        assert gu.same_bits(px, orc.write_rgb8(want))
