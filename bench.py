@@ -108,7 +108,7 @@ def algorithmic_bytes(imgs, items, params, counts):
         "k_linear_blend": roi * 12 + tw * th * 12,
         "k_mb_first_level": roi * (12 + 16),
         "k_mb_weight_argmax": roi * 8,
-        "k_mb_blur_col": roi * 32, "k_mb_blur_row": roi * 32,
+        "k_mb_blur": roi * 32,                                # read + write one float4 level (both passes fused)
         "k_mb_accumulate": roi * (16 + 12) + tw * th * 12,
         "k_fill": tw * th * 12,
     }

@@ -37,7 +37,8 @@ def _load():
         raise ImportError(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). openpano_b200 has no CPU fallback.")
-    lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_LOCAL)
+    # PANO_B200_LIB: development override to A/B a differently tuned build of the same library
+    lib = C.CDLL(os.environ.get("PANO_B200_LIB", str(LIB_PATH)), mode=os.RTLD_LOCAL)
     P = C.POINTER(PanoParams)
     sig = {
         "pano_params_default": (None, [P]),

@@ -48,18 +48,57 @@ __device__ __forceinline__ void coor_func(const BlendImg& im, const BlendGeom& g
   *oy = ry * denom + im.h * 0.5;
 }
 
+// ------------------------------------------------------------ per-tile image list
+// Canvas kernels run one thread per output pixel over a 32x8 tile.  A pixel is covered
+// by a few images, a mosaic has dozens: the first warp tests every image's range
+// against the tile once and compacts the hits IN ORDER (the per-pixel loops must keep
+// the reference's image order), so that the per-pixel loop runs over ~3 entries
+// instead of n.  More than TILE_LIST_CAP hits: the pixel loop falls back to all n.
+#define TILE_LIST_CAP 64
+struct TileList { int n; unsigned short idx[TILE_LIST_CAP]; };
+
+__device__ __forceinline__ void build_tile_list(const BlendImg* __restrict__ imgs, int n, int j0, int i0, int j1, int i1,
+                                                TileList* tl) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid < 32) {
+    int cnt = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int k = base + tid;
+      bool hit = false;
+      if (k < n) {
+        const BlendImg& im = imgs[k];
+        hit = im.y0 <= i1 && im.y1 >= i0 && im.x0 <= j1 && im.x1 >= j0;   // inclusive: superset of both range rules
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int slot = cnt + __popc(bal & ((1u << tid) - 1));
+        if (slot < TILE_LIST_CAP) tl->idx[slot] = (unsigned short)k;
+      }
+      cnt += __popc(bal);
+    }
+    if (tid == 0) tl->n = (cnt <= TILE_LIST_CAP && n <= 65535) ? cnt : -1;
+  }
+  __syncthreads();
+}
+
 // ============================================================ linear blend
 // blender.cc:24-96.  lazy != 0 selects the LAZY_READ branch (exclusive max
 // bounds, accumulate then divide); otherwise the per-pixel branch.
 __global__ void k_linear_blend(const BlendImg* __restrict__ imgs, int n, BlendGeom g, int lazy, int ordered,
                                float* __restrict__ out, int tw, int row0, int row1) {
   // rows [row0, row1) of the canvas; `out` starts at row0 (a strip of a row-sharded mosaic, or the whole)
+  __shared__ TileList tl;
+  {
+    const int tj0 = blockIdx.x * blockDim.x, ti0 = row0 + blockIdx.y * blockDim.y;
+    build_tile_list(imgs, n, tj0, ti0, tj0 + blockDim.x - 1, ti0 + blockDim.y - 1, &tl);
+  }
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   int i = row0 + blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= tw || i >= row1) return;
+  const int nl = tl.n < 0 ? n : tl.n;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, wsum = 0.f;
-  for (int k = 0; k < n; ++k) {
-    const BlendImg& im = imgs[k];
+  for (int q = 0; q < nl; ++q) {
+    const BlendImg& im = imgs[tl.n < 0 ? q : (int)tl.idx[q]];
     bool in = lazy ? (i >= im.y0 && i < im.y1 && j >= im.x0 && j < im.x1)
                    : (i >= im.y0 && i <= im.y1 && j >= im.x0 && j <= im.x1);
     if (!in) continue;
@@ -115,13 +154,19 @@ __global__ void k_mb_first_level(const BlendImg* __restrict__ imgs, BlendGeom g,
 
 // multiband.cc:125-143 update_weight_map (first image with the largest weight wins)
 __global__ void k_mb_weight_argmax(const BlendImg* __restrict__ imgs, int n, float4* __restrict__ cur, int tw, int th) {
+  __shared__ TileList tl;
+  {
+    const int tj0 = blockIdx.x * blockDim.x, ti0 = blockIdx.y * blockDim.y;
+    build_tile_list(imgs, n, tj0, ti0, tj0 + blockDim.x - 1, ti0 + blockDim.y - 1, &tl);
+  }
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   int i = blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= tw || i >= th) return;
+  const int nl = tl.n < 0 ? n : tl.n;
   float mx = 0.f;
   long long best = -1;
-  for (int k = 0; k < n; ++k) {
-    const BlendImg& im = imgs[k];
+  for (int q = 0; q < nl; ++q) {
+    const BlendImg& im = imgs[tl.n < 0 ? q : (int)tl.idx[q]];
     if (i >= im.y0 && i <= im.y1 && j >= im.x0 && j <= im.x1) {
       size_t o = (size_t)im.roi_off + (size_t)(i - im.y0) * im.rw + (j - im.x0);
       float w = cur[o].w;
@@ -135,51 +180,77 @@ __global__ void k_mb_weight_argmax(const BlendImg* __restrict__ imgs, int n, flo
 // gaussian.hh:29-90 on WeightedPixel (4 floats): column pass ...
 struct BlurTaps { int center; float taps[64]; };
 
-__global__ void k_mb_blur_col(const BlendImg* __restrict__ imgs, const float4* __restrict__ src, float4* __restrict__ tmp,
-                              const __grid_constant__ BlurTaps bt) {
-  const BlendImg& im = imgs[blockIdx.z];
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  int i = blockIdx.y * blockDim.y + threadIdx.y;
-  if (j >= im.rw || i >= im.rh) return;
-  const float4* base = src + im.roi_off;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = -bt.center; k <= bt.center; ++k) {
-    int y = min(max(i + k, 0), im.rh - 1);
-    float4 v = __ldg(base + (size_t)y * im.rw + j);
-    float t = bt.taps[k + bt.center];
-    acc.x += v.x * t; acc.y += v.y * t; acc.z += v.z * t; acc.w += v.w * t;
-  }
-  tmp[(size_t)im.roi_off + (size_t)i * im.rw + j] = acc;
-}
+#define MB_TW 64
+#define MB_TH 32
 
-// ... then row pass over the column result
-__global__ void k_mb_blur_row(const BlendImg* __restrict__ imgs, const float4* __restrict__ tmp, float4* __restrict__ dst,
-                              const __grid_constant__ BlurTaps bt) {
+// Both passes of GaussianBlur::blur on one ROI tile (gaussian.hh:29-90 on WeightedPixel):
+// the tile plus a halo of `center` pixels (replicated at the ROI border, exactly the
+// clamp of the reference's column/row buffers) is staged in shared memory, the column
+// pass writes an intermediate strip to shared memory, the row pass reads it — one read
+// and one write of the level per ROI pixel instead of two of each through HBM.
+__global__ void __launch_bounds__(256)
+k_mb_blur(const BlendImg* __restrict__ imgs, const float4* __restrict__ src, float4* __restrict__ dst,
+          const __grid_constant__ BlurTaps bt) {
+  extern __shared__ float4 mb_smem[];
   const BlendImg& im = imgs[blockIdx.z];
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  int i = blockIdx.y * blockDim.y + threadIdx.y;
-  if (j >= im.rw || i >= im.rh) return;
-  const float4* row = tmp + im.roi_off + (size_t)i * im.rw;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = -bt.center; k <= bt.center; ++k) {
-    int x = min(max(j + k, 0), im.rw - 1);
-    float4 v = __ldg(row + x);
-    float t = bt.taps[k + bt.center];
-    acc.x += v.x * t; acc.y += v.y * t; acc.z += v.z * t; acc.w += v.w * t;
+  const int tx0 = blockIdx.x * MB_TW, ty0 = blockIdx.y * MB_TH;
+  if (tx0 >= im.rw || ty0 >= im.rh) return;
+  const int c = bt.center, kw = 2 * c + 1;
+  const int SW = MB_TW + 2 * c, SH = MB_TH + 2 * c;
+  float4* tile = mb_smem;                 // [SH][SW]
+  float4* colres = mb_smem + SH * SW;     // [MB_TH][SW]
+  const float4* base = src + im.roi_off;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < SH * SW; idx += 256) {
+    const int r = idx / SW, q = idx - r * SW;
+    const int y = min(max(ty0 - c + r, 0), im.rh - 1), x = min(max(tx0 - c + q, 0), im.rw - 1);
+    tile[idx] = __ldg(base + (size_t)y * im.rw + x);
   }
-  dst[(size_t)im.roi_off + (size_t)i * im.rw + j] = acc;
+  __syncthreads();
+  // column pass: output row i (tile-local), every staged column
+  for (int idx = tid; idx < MB_TH * SW; idx += 256) {
+    const int i = idx / SW, q = idx - i * SW;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* col = tile + i * SW + q;
+    for (int k = 0; k < kw; ++k) {
+      const float4 v = col[k * SW];
+      const float t = bt.taps[k];
+      acc.x += v.x * t; acc.y += v.y * t; acc.z += v.z * t; acc.w += v.w * t;
+    }
+    colres[idx] = acc;
+  }
+  __syncthreads();
+  // row pass
+  for (int idx = tid; idx < MB_TH * MB_TW; idx += 256) {
+    const int i = idx / MB_TW, j = idx - i * MB_TW;
+    if (ty0 + i >= im.rh || tx0 + j >= im.rw) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* row = colres + i * SW + j;
+    for (int k = 0; k < kw; ++k) {
+      const float4 v = row[k];
+      const float t = bt.taps[k];
+      acc.x += v.x * t; acc.y += v.y * t; acc.z += v.z * t; acc.w += v.w * t;
+    }
+    dst[(size_t)im.roi_off + (size_t)(ty0 + i) * im.rw + tx0 + j] = acc;
+  }
 }
 
 // multiband.cc:75-108 per-level accumulate (+ :113-121 clamp on the last level)
 __global__ void k_mb_accumulate(const BlendImg* __restrict__ imgs, int n, const float4* __restrict__ cur,
                                 const float4* __restrict__ next, const unsigned char* __restrict__ mask,
                                 int is_last, float* __restrict__ out, unsigned char* __restrict__ tmask, int tw, int th) {
+  __shared__ TileList tl;
+  {
+    const int tj0 = blockIdx.x * blockDim.x, ti0 = blockIdx.y * blockDim.y;
+    build_tile_list(imgs, n, tj0, ti0, tj0 + blockDim.x - 1, ti0 + blockDim.y - 1, &tl);
+  }
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   int i = blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= tw || i >= th) return;
+  const int nl = tl.n < 0 ? n : tl.n;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, wsum = 0.f;
-  for (int k = 0; k < n; ++k) {
-    const BlendImg& im = imgs[k];
+  for (int q = 0; q < nl; ++q) {
+    const BlendImg& im = imgs[tl.n < 0 ? q : (int)tl.idx[q]];
     if (!(i >= im.y0 && i <= im.y1 && j >= im.x0 && j <= im.x1)) continue;
     size_t o = (size_t)im.roi_off + (size_t)(i - im.y0) * im.rw + (j - im.x0);
     if (mask[o]) continue;
@@ -279,6 +350,7 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
   double* d_tab = nullptr;
   float4 *d_cur = nullptr, *d_next = nullptr, *d_tmp = nullptr;
   unsigned char *d_mask = nullptr, *d_tmask = nullptr;
+  cudaError_t e = cudaSuccess;
   if ((rc = ctx_alloc(ctx, (void**)&d_imgs, n * sizeof(BlendImg)))) goto done;
   if ((rc = ctx_alloc(ctx, (void**)&d_tab, std::max<size_t>(tab.size(), 1) * sizeof(double)))) goto done;
   {
@@ -300,7 +372,6 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
       size_t roi = (size_t)job.roi_total;
       if ((rc = ctx_alloc(ctx, (void**)&d_cur, roi * sizeof(float4)))) goto done;
       if ((rc = ctx_alloc(ctx, (void**)&d_next, roi * sizeof(float4)))) goto done;
-      if ((rc = ctx_alloc(ctx, (void**)&d_tmp, roi * sizeof(float4)))) goto done;
       if ((rc = ctx_alloc(ctx, (void**)&d_mask, roi))) goto done;
       if ((rc = ctx_alloc(ctx, (void**)&d_tmask, (size_t)tw * th))) goto done;
       if ((rc = ctx_zero(ctx, d_tmask, (size_t)tw * th))) goto done;
@@ -320,8 +391,20 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
           int kw = host_gauss_kernel(sigma, p->gauss_window_factor, bt.taps, 63);
           if (kw < 0) { rc = ctx_fail(ctx, PANO_ERR_INVALID, "blend: gaussian window %d too wide", -kw); goto done; }
           bt.center = kw / 2;
-          BL_LAUNCH(ctx, "k_mb_blur_col", k_mb_blur_col, gr, b, d_imgs, d_cur, d_tmp, bt);
-          BL_LAUNCH(ctx, "k_mb_blur_row", k_mb_blur_row, gr, b, d_imgs, d_tmp, d_next, bt);
+          {
+            const int c = bt.center;
+            const size_t smem = sizeof(float4) * ((size_t)(MB_TH + 2 * c) * (MB_TW + 2 * c) + (size_t)MB_TH * (MB_TW + 2 * c));
+            if (smem > 200 * 1024) { rc = ctx_fail(ctx, PANO_ERR_INVALID, "blend: gaussian window %d too wide", kw); goto done; }
+            e = cudaFuncSetAttribute(k_mb_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) { rc = ctx_cuda(ctx, e, "k_mb_blur attribute"); goto done; }
+            dim3 gb(ceil_div(job.max_rw, MB_TW), ceil_div(job.max_rh, MB_TH), n);
+            ctx->launches++;
+            if (ctx->profiling) ctx_prof_begin(ctx, "k_mb_blur");
+            k_mb_blur<<<gb, 256, smem, ctx->stream>>>(d_imgs, d_cur, d_next, bt);
+            if (ctx->profiling) ctx_prof_end(ctx);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) { rc = ctx_cuda(ctx, e, "k_mb_blur"); goto done; }
+          }
         }
         BL_LAUNCH(ctx, "k_mb_accumulate", k_mb_accumulate, gt, b, d_imgs, n, d_cur, d_next, d_mask, is_last, d_out,
                   d_tmask, tw, th);

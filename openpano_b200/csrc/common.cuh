@@ -249,15 +249,18 @@ __device__ __forceinline__ bool interpolate_rgb(const float* __restrict__ img, i
   c -= (float)fc;
   const float* p00 = img + ((size_t)fr * w + fc) * 3;
   const float* p10 = p00 + (size_t)w * 3;
-  if (p00[0] < 0) return false;
-  if (p10[0] < 0) return false;
-  if (p10[3] < 0) return false;
-  if (p00[3] < 0) return false;
+  // all twelve samples first (the four positions are in range), tests afterwards: the
+  // loads overlap instead of each Color::NO test waiting on its own load
+  const float q00 = __ldg(p00), q01 = __ldg(p00 + 1), q02 = __ldg(p00 + 2);
+  const float q03 = __ldg(p00 + 3), q04 = __ldg(p00 + 4), q05 = __ldg(p00 + 5);
+  const float q10 = __ldg(p10), q11 = __ldg(p10 + 1), q12 = __ldg(p10 + 2);
+  const float q13 = __ldg(p10 + 3), q14 = __ldg(p10 + 4), q15 = __ldg(p10 + 5);
+  if (q00 < 0 || q10 < 0 || q13 < 0 || q03 < 0) return false;
   float w00 = (1 - r) * (1 - c), w10 = r * (1 - c), w11 = r * c, w01 = (1 - r) * c;
-  float a0 = 0.f + p00[0] * w00, a1 = 0.f + p00[1] * w00, a2 = 0.f + p00[2] * w00;
-  a0 += p10[0] * w10; a1 += p10[1] * w10; a2 += p10[2] * w10;
-  a0 += p10[3] * w11; a1 += p10[4] * w11; a2 += p10[5] * w11;
-  a0 += p00[3] * w01; a1 += p00[4] * w01; a2 += p00[5] * w01;
+  float a0 = 0.f + q00 * w00, a1 = 0.f + q01 * w00, a2 = 0.f + q02 * w00;
+  a0 += q10 * w10; a1 += q11 * w10; a2 += q12 * w10;
+  a0 += q13 * w11; a1 += q14 * w11; a2 += q15 * w11;
+  a0 += q03 * w01; a1 += q04 * w01; a2 += q05 * w01;
   *o0 = a0; *o1 = a1; *o2 = a2;
   return true;
 }

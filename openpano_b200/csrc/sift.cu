@@ -697,9 +697,15 @@ k_expand_scan(const int* __restrict__ cand_count, const unsigned char* __restric
 //      lane pairs advance independently and nearly every lane does useful work.
 #define DESC_WARPS 4
 #define DESC_THREADS (DESC_WARPS * 32)
+#ifndef DESC_REC_CAP
 #define DESC_REC_CAP 384                 // records per flush (more records simply flush again)
+#endif
 #define DESC_CHUNKS (DESC_REC_CAP / 32)
 #define DESC_SKIP 0xffffffffu
+#define DESC_MAX_IMG 512               // images per SIFT batch (prefix table in shared memory)
+#ifndef DESC_CTAS_PER_SM
+#define DESC_CTAS_PER_SM 6
+#endif
 
 struct DescParams { int hist_scale_factor; int int_factor; };
 
@@ -716,10 +722,17 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
              const float* __restrict__ arena, int n_oct, int n_img,
              const pano_sspoint* __restrict__ pts, const int* __restrict__ n_desc,
              const int* __restrict__ desc_cand, const float* __restrict__ desc_dir,
-             DescParams dp, float* __restrict__ out_desc, double* __restrict__ out_coor) {
+             DescParams dp, float* __restrict__ out_desc, double* __restrict__ out_coor,
+             int* __restrict__ work_counter) {
   extern __shared__ __align__(16) unsigned char desc_smem_raw[];
   __shared__ uint64_t s_exptab[32];
+  __shared__ int s_pref[DESC_MAX_IMG + 1];      // first flat index of each image's descriptors
   load_exp2f_tab(s_exptab, threadIdx.x);
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < n_img; ++i) { s_pref[i] = acc; acc += min(n_desc[i], SIFT_DESC_CAP); }
+    s_pref[n_img] = acc;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   DescWarpSmem& S = reinterpret_cast<DescWarpSmem*>(desc_smem_raw)[wid];
@@ -729,12 +742,20 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
   // has its parity.  A record adds to bins hbinf and hbinf+1 — one even, one odd — so
   // each bin has exactly one owner lane and the accumulators can live in registers.
   const int cell = lane >> 1, parity = lane & 1, by = cell >> 2, bx = cell & 3;
-  const int warp_global = blockIdx.x * DESC_WARPS + wid, warp_stride = gridDim.x * DESC_WARPS;
-
-  for (int img = 0; img < n_img; ++img) {
-    const int nd = min(n_desc[img], SIFT_DESC_CAP);
-    const ImgMeta im = imgs[img];
-    for (int d = warp_global; d < nd; d += warp_stride) {
+  // Work is handed out one descriptor at a time from a global counter: window sizes vary
+  // by an order of magnitude with the keypoint scale, and a static assignment left most
+  // warps idle while the unlucky ones worked through their heavy keypoints.
+  const int total = s_pref[n_img];
+  int img = 0;
+  {
+    while (true) {
+      int flat = 0;
+      if (lane == 0) flat = atomicAdd(work_counter, 1);
+      flat = __shfl_sync(0xffffffffu, flat, 0);
+      if (flat >= total) break;
+      while (flat >= s_pref[img + 1]) ++img;          // indices only grow: resume from the last image
+      const int d = flat - s_pref[img];
+      const ImgMeta im = imgs[img];
       const size_t dslot = (size_t)img * SIFT_DESC_CAP + d;
       const pano_sspoint p = pts[(size_t)img * SIFT_CAND_CAP + desc_cand[dslot]];
       const float ort = desc_dir[dslot];
@@ -939,6 +960,7 @@ void sift_work_free(pano_ctx* ctx, SiftWork* wk) {
 int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w, const int* h,
                    const pano_params* p, pano_featureset* fs, SiftWork** keep) {
   if (n <= 0 || !d_src || !w || !h || !p || !fs) return ctx_fail(ctx, PANO_ERR_INVALID, "sift: bad argument");
+  if (n > DESC_MAX_IMG) return ctx_fail(ctx, PANO_ERR_INVALID, "sift: %d images in one batch (limit %d): split the batch", n, DESC_MAX_IMG);
   const int n_oct = p->num_octave, n_scale = p->num_scale;
   if (n_oct < 1 || n_oct > SIFT_MAX_OCT || n_scale < 4 || n_scale - 1 > SIFT_MAX_LEVELS || n_scale - 2 > 7)
     return ctx_fail(ctx, PANO_ERR_INVALID, "sift: NUM_OCTAVE/NUM_SCALE out of supported range");
@@ -1009,7 +1031,7 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_img, n * sizeof(ImgMeta)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_oct, wk->h_oct.size() * sizeof(OctMeta)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_tiles, tiles.size() * sizeof(BlurTile)));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->cand_count, n * sizeof(int)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->cand_count, (n + 1) * sizeof(int)));   // [n] = descriptor work counter
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->cand_keys, ncand * sizeof(uint32_t)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->sorted_keys, ncand * sizeof(uint32_t)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->refined, ncand * sizeof(pano_sspoint)));
@@ -1033,7 +1055,7 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     void* dsts[4] = {wk->d_img, wk->d_oct, wk->d_tiles, wk->cand_count};
     const void* srcs[4] = {wk->h_img.data(), wk->h_oct.data(), tiles.data(), nullptr};
     size_t sizes[4] = {n * sizeof(ImgMeta), wk->h_oct.size() * sizeof(OctMeta), tiles.size() * sizeof(BlurTile),
-                       n * sizeof(int)};
+                       (n + 1) * sizeof(int)};
     SIFT_TRY(ctx_put_many(ctx, 4, dsts, srcs, sizes));
   }
 
@@ -1089,9 +1111,9 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     DescParams dp{p->desc_hist_scale_factor, p->desc_int_factor};
     const size_t dsm = sizeof(DescWarpSmem) * DESC_WARPS;
     SIFT_CUDA(cudaFuncSetAttribute(k_descriptor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-    int grid = ctx->num_sms * 6;
+    int grid = ctx->num_sms * DESC_CTAS_PER_SM;
     SIFT_LAUNCH("k_descriptor", k_descriptor, grid, DESC_THREADS, dsm, wk->d_oct, wk->d_img, wk->arena, n_oct, n,
-                wk->refined, fs->d_count, wk->desc_cand, wk->desc_dir, dp, fs->d_desc, fs->d_coor);
+                wk->refined, fs->d_count, wk->desc_cand, wk->desc_dir, dp, fs->d_desc, fs->d_coor, wk->cand_count + n);
   }
   wk->n_desc = fs->d_count;
 
