@@ -153,15 +153,16 @@ __global__ void k_mb_first_level(const BlendImg* __restrict__ imgs, BlendGeom g,
 }
 
 // multiband.cc:125-143 update_weight_map (first image with the largest weight wins)
-__global__ void k_mb_weight_argmax(const BlendImg* __restrict__ imgs, int n, float4* __restrict__ cur, int tw, int th) {
+__global__ void k_mb_weight_argmax(const BlendImg* __restrict__ imgs, int n, float4* __restrict__ cur, int tw,
+                                   int row0, int row1) {
   __shared__ TileList tl;
   {
-    const int tj0 = blockIdx.x * blockDim.x, ti0 = blockIdx.y * blockDim.y;
+    const int tj0 = blockIdx.x * blockDim.x, ti0 = row0 + blockIdx.y * blockDim.y;
     build_tile_list(imgs, n, tj0, ti0, tj0 + blockDim.x - 1, ti0 + blockDim.y - 1, &tl);
   }
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  int i = blockIdx.y * blockDim.y + threadIdx.y;
-  if (j >= tw || i >= th) return;
+  int i = row0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= tw || i >= row1) return;
   const int nl = tl.n < 0 ? n : tl.n;
   float mx = 0.f;
   long long best = -1;
@@ -238,15 +239,17 @@ k_mb_blur(const BlendImg* __restrict__ imgs, const float4* __restrict__ src, flo
 // multiband.cc:75-108 per-level accumulate (+ :113-121 clamp on the last level)
 __global__ void k_mb_accumulate(const BlendImg* __restrict__ imgs, int n, const float4* __restrict__ cur,
                                 const float4* __restrict__ next, const unsigned char* __restrict__ mask,
-                                int is_last, float* __restrict__ out, unsigned char* __restrict__ tmask, int tw, int th) {
+                                int is_last, float* __restrict__ out, unsigned char* __restrict__ tmask, int tw,
+                                int row0, int row1) {
+  // rows [row0, row1) of the canvas; out / tmask start at row0
   __shared__ TileList tl;
   {
-    const int tj0 = blockIdx.x * blockDim.x, ti0 = blockIdx.y * blockDim.y;
+    const int tj0 = blockIdx.x * blockDim.x, ti0 = row0 + blockIdx.y * blockDim.y;
     build_tile_list(imgs, n, tj0, ti0, tj0 + blockDim.x - 1, ti0 + blockDim.y - 1, &tl);
   }
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  int i = blockIdx.y * blockDim.y + threadIdx.y;
-  if (j >= tw || i >= th) return;
+  int i = row0 + blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= tw || i >= row1) return;
   const int nl = tl.n < 0 ? n : tl.n;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, wsum = 0.f;
   for (int q = 0; q < nl; ++q) {
@@ -265,7 +268,7 @@ __global__ void k_mb_accumulate(const BlendImg* __restrict__ imgs, int n, const 
     }
     wsum += w;
   }
-  size_t t = (size_t)i * tw + j;
+  size_t t = (size_t)(i - row0) * tw + j;
   float* p = out + t * 3;
   bool touched = tmask[t] != 0;
   if (!((double)wsum < 1e-6)) {
@@ -309,28 +312,55 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
   if (!ctx || n <= 0 || !imgs || !g || !p || !d_out || bands < 0) return PANO_ERR_INVALID;
   if (row0 < 0 || row1 > oh || row0 > row1)
     return ctx_fail(ctx, PANO_ERR_INVALID, "blend: rows [%d, %d) outside the %d-row canvas", row0, row1, oh);
-  if (bands > 0 && (row0 != 0 || row1 != oh))
-    return ctx_fail(ctx, PANO_ERR_INVALID, "blend: row strips are implemented for the linear blender only");
   if (row0 == row1) return PANO_OK;
+  // Multiband on a row strip: a band at level l of pixel p depends on level 0 inside a
+  // radius of the summed half-widths of the blurs up to l, so the strip is computed from
+  // each image's ROI clipped to [row0 - H, row1 + H) with H = that sum over all blurred
+  // levels.  The replicate rule at a clipped edge differs from the true neighbourhood only
+  // within H rows of it, i.e. outside the strip; true ROI edges are kept as they are.
+  std::vector<BlurTaps> level_taps;
+  int halo = 0;
+  for (int level = 0; level + 1 < bands; ++level) {   // multiband.cc:145-151
+    float sigma = (float)(sqrt(level * 2 + 1.0) * 4);
+    BlurTaps bt;
+    memset(&bt, 0, sizeof(bt));
+    int kw = host_gauss_kernel(sigma, p->gauss_window_factor, bt.taps, 63);
+    if (kw < 0) return ctx_fail(ctx, PANO_ERR_INVALID, "blend: gaussian window %d too wide", -kw);
+    bt.center = kw / 2;
+    halo += bt.center;
+    level_taps.push_back(bt);
+  }
+  const bool strip = bands > 0 && (row0 != 0 || row1 != oh);
+  const int clip0 = (strip && row0 > 0) ? std::max(0, row0 - halo) : INT_MIN;          // first ROI row kept
+  const int clip1 = (strip && row1 < oh) ? row1 + halo - 1 : INT_MAX;                  // last ROI row kept
   BlendJob job;
-  job.imgs.resize(n);
+  job.imgs.reserve(n);
   for (int k = 0; k < n; ++k) {
     const pano_blend_image& s = imgs[k];
     if (!s.rgb_hwc || s.w < 2 || s.h < 2 || s.x1 < s.x0 || s.y1 < s.y0 || s.x0 < 0 || s.y0 < 0)
       return ctx_fail(ctx, PANO_ERR_INVALID, "blend: image %d has an invalid shape or range", k);
-    BlendImg& d = job.imgs[k];
+    job.tw = std::max(job.tw, s.x1); job.th = std::max(job.th, s.y1);
+    BlendImg d;
     d.rgb = s.rgb_hwc; d.w = s.w; d.h = s.h;
-    d.x0 = s.x0; d.y0 = s.y0; d.x1 = s.x1; d.y1 = s.y1;
+    d.x0 = s.x0; d.x1 = s.x1;
+    d.y0 = std::max(s.y0, clip0); d.y1 = std::min(s.y1, clip1);
+    if (d.y0 > d.y1) continue;                         // no row of this image reaches the strip
     memcpy(d.hi, s.homo_inv, sizeof(d.hi));
-    d.rw = s.x1 - s.x0 + 1; d.rh = s.y1 - s.y0 + 1;
+    d.rw = d.x1 - d.x0 + 1; d.rh = d.y1 - d.y0 + 1;
     d.roi_off = job.roi_total;
     job.roi_total += (long long)align_up((size_t)d.rw * d.rh, 32);
     job.max_rw = std::max(job.max_rw, d.rw); job.max_rh = std::max(job.max_rh, d.rh);
-    job.tw = std::max(job.tw, s.x1); job.th = std::max(job.th, s.y1);
+    job.imgs.push_back(d);
   }
   if (job.tw != ow || job.th != oh || ow <= 0 || oh <= 0)
     return ctx_fail(ctx, PANO_ERR_INVALID, "blend: output is %dx%d but target_size is %dx%d", ow, oh, job.tw, job.th);
   const int tw = job.tw, th = job.th;
+  n = (int)job.imgs.size();                            // images that reach the strip (all of them for a full canvas)
+  if (n == 0) {
+    size_t nfl = (size_t)tw * (row1 - row0) * 3;
+    PANO_LAUNCH(ctx, "k_fill", k_fill, (unsigned)((nfl + 255) / 256), 256, 0, d_out, nfl, -1.f);
+    return PANO_OK;
+  }
   // ROIs reach one pixel past the canvas (inclusive max): tables cover [0, tw] / [0, th]
   std::vector<double> tab;
   size_t ncol = (size_t)tw + 2, nrow = (size_t)th + 2;
@@ -373,24 +403,24 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
       if ((rc = ctx_alloc(ctx, (void**)&d_cur, roi * sizeof(float4)))) goto done;
       if ((rc = ctx_alloc(ctx, (void**)&d_next, roi * sizeof(float4)))) goto done;
       if ((rc = ctx_alloc(ctx, (void**)&d_mask, roi))) goto done;
-      if ((rc = ctx_alloc(ctx, (void**)&d_tmask, (size_t)tw * th))) goto done;
-      if ((rc = ctx_zero(ctx, d_tmask, (size_t)tw * th))) goto done;
+      const size_t strip_px = (size_t)tw * (row1 - row0);
+      // the weight map is needed wherever a clipped ROI has pixels on the canvas
+      const int wrow0 = std::max(0, std::max(row0 - halo, clip0)), wrow1 = std::min(th, strip ? row1 + halo : th);
+      if ((rc = ctx_alloc(ctx, (void**)&d_tmask, strip_px))) goto done;
+      if ((rc = ctx_zero(ctx, d_tmask, strip_px))) goto done;
       dim3 gr(ceil_div(job.max_rw, 32), ceil_div(job.max_rh, 8), n);
+      dim3 gw(ceil_div(tw, 32), ceil_div(wrow1 - wrow0, 8)), gs(ceil_div(tw, 32), ceil_div(row1 - row0, 8));
       BL_LAUNCH(ctx, "k_mb_first_level", k_mb_first_level, gr, b, d_imgs, job.g, d_cur, d_mask);
-      BL_LAUNCH(ctx, "k_mb_weight_argmax", k_mb_weight_argmax, gt, b, d_imgs, n, d_cur, tw, th);
+      BL_LAUNCH(ctx, "k_mb_weight_argmax", k_mb_weight_argmax, gw, b, d_imgs, n, d_cur, tw, wrow0, wrow1);
       {
-        size_t nfl = (size_t)tw * th * 3;
+        size_t nfl = strip_px * 3;
         BL_LAUNCH(ctx, "k_fill", k_fill, (unsigned)((nfl + 255) / 256), 256, d_out, nfl, -1.f);
       }
       for (int level = 0; level < bands; ++level) {
         int is_last = level == bands - 1;
-        if (!is_last) {  // multiband.cc:145-151
-          float sigma = (float)(sqrt(level * 2 + 1.0) * 4);
-          BlurTaps bt;
-          memset(&bt, 0, sizeof(bt));
-          int kw = host_gauss_kernel(sigma, p->gauss_window_factor, bt.taps, 63);
-          if (kw < 0) { rc = ctx_fail(ctx, PANO_ERR_INVALID, "blend: gaussian window %d too wide", -kw); goto done; }
-          bt.center = kw / 2;
+        if (!is_last) {
+          const BlurTaps& bt = level_taps[level];
+          const int kw = 2 * bt.center + 1;
           {
             const int c = bt.center;
             const size_t smem = sizeof(float4) * ((size_t)(MB_TH + 2 * c) * (MB_TW + 2 * c) + (size_t)MB_TH * (MB_TW + 2 * c));
@@ -406,8 +436,8 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
             if (e != cudaSuccess) { rc = ctx_cuda(ctx, e, "k_mb_blur"); goto done; }
           }
         }
-        BL_LAUNCH(ctx, "k_mb_accumulate", k_mb_accumulate, gt, b, d_imgs, n, d_cur, d_next, d_mask, is_last, d_out,
-                  d_tmask, tw, th);
+        BL_LAUNCH(ctx, "k_mb_accumulate", k_mb_accumulate, gs, b, d_imgs, n, d_cur, d_next, d_mask, is_last, d_out,
+                  d_tmask, tw, row0, row1);
         if (!is_last) std::swap(d_cur, d_next);
       }
     }

@@ -167,7 +167,8 @@ class DistributedStitcher:
       results   match lists -> rank 0 (host objects, a few KB)
       images    every rank blends a strip of every image: ncclAllGather of the inputs
       blend     rows [r·H/G, (r+1)·H/G) of the canvas (LinearBlender pixels are
-                independent, blender.cc:37-96)                      no collective
+                independent, blender.cc:37-96; MultiBandBlender strips are computed
+                from ROIs clipped to the strip + the summed blur half-widths)   no collective
       C2        strips -> ncclAllGather -> the mosaic (bit-identical to one GPU)
     """
 
@@ -186,7 +187,7 @@ class DistributedStitcher:
         self._events.append((name, e0, e1))
         return out
 
-    def run(self, owned: dict, n_images: int, shapes, pairs, items, geom):
+    def run(self, owned: dict, n_images: int, shapes, pairs, items, geom, bands: int = 0):
         """owned: {image index: cuda float32 tensor H×W×3} following shard_images().
         Returns (matches on rank 0 / None elsewhere, mosaic tensor th×tw×3 on every rank)."""
         import torch
@@ -291,7 +292,7 @@ class DistributedStitcher:
         row0, row1 = min(th, rank * rows_per), min(th, (rank + 1) * rows_per)
         strip = torch.empty((rows_per, tw, 3), dtype=torch.float32, device=dev)
         self._timed("blend_strip", lambda: eng.blend_rows_dev(img_ptrs, shapes, items, geom, strip.data_ptr(), tw, th,
-                                                              row0, row1, 0, params))
+                                                              row0, row1, bands, params))
         mosaic = torch.empty((world * rows_per, tw, 3), dtype=torch.float32, device=dev)
         self._timed("gather_strips", lambda: dist.all_gather_into_tensor(mosaic, strip))
         torch.cuda.current_stream().synchronize()

@@ -142,3 +142,33 @@ def test_match_tensor_path_equals_exact_path(engine, orc, monkeypatch):
     assert np.array_equal(got_ex, want)
     assert np.array_equal(got_tc, want)
     assert 50 < len(want) < 1300
+
+
+@pytest.mark.parametrize("bands", [0, 2, 5])
+def test_blend_row_strips_equal_full_canvas(engine, bands):
+    """pano_blend_rows_dev: uneven row strips (the multi-GPU partition of the canvas) concatenate to
+    exactly the mosaic pano_blend_dev produces — for the multiband blender through ROIs clipped to
+    the strip plus the summed blur half-widths."""
+    imgs, org = synth.make_stack(5, 260, 200, 90, 77, rows=2, step_y=70)
+    items, geom = synth.translation_blend_setup(org, 260, 200)
+    p = default_params(multiband=bands, lazy_read=0)
+    shapes = [im.shape[:2] for im in imgs]
+    tw, th = max(it[2] for it in items), max(it[3] for it in items)
+    d_imgs = [engine.dev_alloc(im.nbytes) for im in imgs]
+    for d, im in zip(d_imgs, imgs):
+        engine.dev_upload(d, im)
+    d_out = engine.dev_alloc(tw * th * 12)
+    full = np.empty((th, tw, 3), np.float32)
+    engine.blend_dev(d_imgs, shapes, items, geom, d_out, tw, th, bands, p)
+    engine.dev_download(full, d_out)
+    cuts = [0, 7, 64, 65, 130, th]                     # strips thinner and thicker than the halo
+    parts = []
+    for r0, r1 in zip(cuts[:-1], cuts[1:]):
+        part = np.empty((r1 - r0, tw, 3), np.float32)
+        engine.blend_rows_dev(d_imgs, shapes, items, geom, d_out, tw, th, r0, r1, bands, p)
+        engine.dev_download(part, d_out)
+        parts.append(part)
+    for d in d_imgs + [d_out]:
+        engine.dev_free(d)
+    got = np.concatenate(parts)
+    assert got.tobytes() == full.tobytes()

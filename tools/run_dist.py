@@ -2,7 +2,7 @@
 """Multi-GPU check of the sharded hot path — launch with torchrun:
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-      tools/run_dist.py [small|unordered38] [reps]
+      tools/run_dist.py [small|unordered38] [reps] [bands]
 
 Every rank SIFTs its images (k mod G), descriptors are all-gathered over NCCL, pair
 tasks are dealt, strips of the mosaic are blended per rank and gathered.  Rank 0 then
@@ -30,6 +30,7 @@ from openpano_b200.stitcher import all_pairs  # noqa: E402
 def main():
     which = sys.argv[1] if len(sys.argv) > 1 else "small"
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    bands = int(sys.argv[3]) if len(sys.argv) > 3 else 0
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -57,7 +58,7 @@ def main():
             dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            matches, mosaic = ds.run(owned, n, shapes, pairs, items, geom)
+            matches, mosaic = ds.run(owned, n, shapes, pairs, items, geom, bands)
             e1.record()
             torch.cuda.synchronize()
             t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -77,14 +78,14 @@ def main():
                 ref_m = eng.match_pairs(fs, pairs, params)
                 tw, th = max(it[2] for it in items), max(it[3] for it in items)
                 ref_out = torch.empty((th, tw, 3), dtype=torch.float32, device="cuda")
-                eng.blend_dev(ptrs, shapes, items, geom, ref_out.data_ptr(), tw, th, 0, params)
+                eng.blend_dev(ptrs, shapes, items, geom, ref_out.data_ptr(), tw, th, bands, params)
                 s1.record()
                 torch.cuda.synchronize()
                 fs.free()
             same_m = all(np.array_equal(a, b) for a, b in zip(matches, ref_m)) and len(matches) == len(ref_m)
             same_o = bool(torch.equal(mosaic, ref_out))
             mpx = sum(s[0] * s[1] for s in shapes) / 1e6
-            res = {"workload": name, "n_gpus": world, "images": n, "pairs": len(pairs), "ms_sharded": round(best[0], 3),
+            res = {"workload": name, "bands": bands, "n_gpus": world, "images": n, "pairs": len(pairs), "ms_sharded": round(best[0], 3),
                    "phase_ms_rank0": {k: round(v, 3) for k, v in best[1].items()},
                    "ms_one_gpu": round(s0.elapsed_time(s1), 3), "mpx_per_s_sharded": round(mpx / best[0] * 1e3, 1),
                    "matches": int(sum(len(m) for m in matches)), "matches_identical": bool(same_m),
