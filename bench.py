@@ -265,7 +265,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--bands", type=int, default=0, help="0 = LinearBlender (reference default), k = MultiBandBlender{k}")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lanes", type=int, default=2, help="concurrent stitch jobs per GPU in the e2e leg (StitchLanes)")
+    ap.add_argument("--lanes", type=int, default=3, help="concurrent stitch jobs per GPU in the e2e leg (StitchLanes)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -287,7 +287,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else 0
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = bind_to_gpu_numa_node(local_rank)      # host threads + pinned buffers next to the GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -377,50 +378,76 @@ def main():
         # from pinned host memory and downloads its own mosaic + match lists.
         from openpano_b200.stitcher import PipelinedStitcher, unpack_rgb8_mosaic
 
-        def pipelined_leg(rgb8, n_lanes):
-            from openpano_b200.stitcher import StitchLanes
-            lanes = StitchLanes(local_rank, params, lanes=n_lanes, depth=3 if n_lanes == 1 else 2, rgb8=rgb8, crop=True)
-            n_out = 3 * n_lanes
-            if rgb8:
-                src = [torch.from_numpy(p).pin_memory() for p in pix]
-                outs = [torch.empty(lanes.out_bytes((out_w, out_h)), dtype=torch.uint8).pin_memory() for _ in range(n_out)]
-            else:
-                src = host
-                outs = [torch.empty_like(host_out).pin_memory() for _ in range(n_out)]
-            ptrs = [t.data_ptr() for t in src]
+        class Leg:
+            """One e2e configuration, set up once and timed in several trials of `steps` jobs."""
 
-            def jobs(n):
-                return [(ptrs, shapes, (out_w, out_h), pairs, items, geom, outs[i % n_out].data_ptr(), args.bands)
-                        for i in range(n)]
+            def __init__(self, rgb8, n_lanes):
+                from openpano_b200.stitcher import StitchLanes
+                self.rgb8, self.n_out = rgb8, 3 * n_lanes
+                self.lanes = StitchLanes(local_rank, params, lanes=n_lanes, depth=3 if n_lanes == 1 else 2, rgb8=rgb8,
+                                         crop=True)
+                if rgb8:
+                    self.src = [torch.from_numpy(p).pin_memory() for p in pix]
+                    self.outs = [torch.empty(self.lanes.out_bytes((out_w, out_h)), dtype=torch.uint8).pin_memory()
+                                 for _ in range(self.n_out)]
+                else:
+                    self.src = host
+                    self.outs = [torch.empty_like(host_out).pin_memory() for _ in range(self.n_out)]
+                self.ptrs = [t.data_ptr() for t in self.src]
+                self.h2d = self.lanes.in_bytes(shapes)
+                self.d2h = self.lanes.out_bytes((out_w, out_h)) + nm_e2e * 8 + len(imgs) * 8
+                self.trials = []
+                self.lanes.map(self.jobs(2 * self.n_out))           # warm-up
 
-            lanes.map(jobs(2 * n_out))
-            torch.cuda.synchronize()
-            barrier()
-            t0 = time.perf_counter()
-            res = lanes.map(jobs(args.steps))
-            torch.cuda.synchronize()
-            secs = time.perf_counter() - t0
-            nm_pipe = sum(sum(len(x) for x in m) for m in res)
-            assert nm_pipe == args.steps * nm_e2e, (nm_pipe, nm_e2e)      # every job returned the same matches
-            last = outs[(args.steps - 1) % n_out]
-            if rgb8:
-                rect, px = unpack_rgb8_mosaic(last.numpy(), (out_w, out_h))
-                assert rect[2] > out_w // 2 and rect[3] > out_h // 2 and int(px[rect[3] // 2, rect[2] // 2].max()) > 0
-            else:
-                assert float(last[out_h // 2, out_w // 2, 0]) >= 0.0
-            h2d, d2h = lanes.in_bytes(shapes), lanes.out_bytes((out_w, out_h)) + nm_e2e * 8 + len(imgs) * 8
-            lanes.close()
-            t = torch.tensor([secs], device="cuda")
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            return float(t.item()) / args.steps, h2d, d2h
+            def jobs(self, n):
+                return [(self.ptrs, shapes, (out_w, out_h), pairs, items, geom, self.outs[i % self.n_out].data_ptr(),
+                         args.bands) for i in range(n)]
+
+            def trial(self):
+                torch.cuda.synchronize()
+                barrier()
+                t0 = time.perf_counter()
+                res = self.lanes.map(self.jobs(args.steps))
+                torch.cuda.synchronize()
+                secs = time.perf_counter() - t0
+                nm_pipe = sum(sum(len(x) for x in m) for m in res)
+                assert nm_pipe == args.steps * nm_e2e, (nm_pipe, nm_e2e)      # every job returned the same matches
+                last = self.outs[(args.steps - 1) % self.n_out]
+                if self.rgb8:
+                    rect, px = unpack_rgb8_mosaic(last.numpy(), (out_w, out_h))
+                    assert rect[2] > out_w // 2 and rect[3] > out_h // 2 and int(px[rect[3] // 2, rect[2] // 2].max()) > 0
+                else:
+                    assert float(last[out_h // 2, out_w // 2, 0]) >= 0.0
+                t = torch.tensor([secs], device="cuda")
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                self.trials.append(float(t.item()) / args.steps)
+
+            def median(self):
+                return float(np.median(self.trials))
 
         # headline: the reference's file formats at the boundary (8-bit pixels in, cropped 8-bit
-        # mosaic out; conversions and crop on the device).  Beside it the Mat32f boundary.
-        e2e_per_step, h2d_bytes, d2h_bytes = pipelined_leg(True, args.lanes)
+        # mosaic out; conversions and crop on the device).  Beside it one lane, and the Mat32f
+        # boundary.  The GPU box is shared: other tenants' PCIe traffic slows whole legs down for
+        # seconds at a time (seen: 2.3 -> 5+ ms/job with identical kernel times), so every leg is
+        # timed in E2E_TRIALS trials of `steps` jobs, interleaved with the other legs, and the MEDIAN
+        # trial is reported (all trials are in the JSON line).
+        E2E_TRIALS = 5
+        legs = {"lanes": Leg(True, args.lanes)}
+        legs["one"] = Leg(True, 1) if args.lanes != 1 else legs["lanes"]
+        legs["f32"] = Leg(False, 1)
+        for _ in range(E2E_TRIALS):
+            for key in ("lanes", "one", "f32"):
+                if key == "one" and args.lanes == 1:
+                    continue
+                legs[key].trial()
+        e2e_per_step, h2d_bytes, d2h_bytes = legs["lanes"].median(), legs["lanes"].h2d, legs["lanes"].d2h
         e2e_value = world * mpx / e2e_per_step
-        one_lane_per_step = pipelined_leg(True, 1)[0] if args.lanes != 1 else e2e_per_step
-        f32_per_step, f32_h2d, f32_d2h = pipelined_leg(False, 1)
+        one_lane_per_step = legs["one"].median()
+        f32_per_step, f32_h2d, f32_d2h = legs["f32"].median(), legs["f32"].h2d, legs["f32"].d2h
+        e2e_trials = {k: [round(x * 1e3, 3) for x in v.trials] for k, v in legs.items()}
+        for v in {id(v): v for v in legs.values()}.values():
+            v.lanes.close()
 
         # ---- roofline of the dominant kernel (event-timed per launch, separate untimed pass)
         roof = None
@@ -472,6 +499,7 @@ def main():
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             try:
+                os.sched_setaffinity(0, all_cpus)          # the CPU arm gets every core again
                 use_all_host_threads()
                 chk, kind = load_cpu_checker()
                 devnull = os.open(os.devnull, os.O_WRONLY)
@@ -508,6 +536,8 @@ def main():
                     "mode": f"StitchLanes: {args.lanes} concurrent pipelined jobs per GPU (one host thread each); every job "
                             "uploads its own images and downloads its own mosaic + match lists",
                     "one_lane": {"value": world * mpx / one_lane_per_step, "ms_per_step": one_lane_per_step * 1e3},
+                    "reported": f"median of {E2E_TRIALS} trials of {args.steps} jobs each (trials interleaved across legs)",
+                    "trials_ms_per_step": e2e_trials,
                     "boundary": "rgb8: decoded 8-bit pixels in (read_img's input), crop()+write_rgb 8-bit mosaic out; "
                                 "u8<->f32 conversions and crop run on the device inside the timed region",
                     "mat32f_boundary": {"value": world * mpx / f32_per_step, "ms_per_step": f32_per_step * 1e3,

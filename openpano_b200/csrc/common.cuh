@@ -29,6 +29,7 @@ struct pano_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
+  cudaMemPool_t pool = nullptr;   // this context's own stream-ordered pool (see ctx_alloc)
   std::string err;
   bool profiling = false;
   std::vector<ProfEvent> prof_pending;
@@ -50,11 +51,17 @@ struct pano_ctx {
   // are slow and cudaFreeHost synchronises the whole device)
   std::vector<std::pair<void*, size_t>> small_pinned;
   std::vector<cudaEvent_t> sync_events;
+  // completion markers: a word in pinned host memory the stream writes sequence numbers to
+  volatile unsigned* flag = nullptr;
+  unsigned flag_seq = 0;
 };
 
 int  ctx_fail(pano_ctx* ctx, int code, const char* fmt, ...);
 int  ctx_cuda(pano_ctx* ctx, cudaError_t e, const char* what);
-// stream-ordered device memory from the device's default mempool
+// Stream-ordered device memory from the CONTEXT'S OWN pool.  Contexts sharing the device's
+// default pool hand each other freed blocks, and the allocator then makes the taking
+// stream wait for the giving stream ("internal dependencies"): concurrent stitch lanes
+// drifted from 2.3 to 5+ ms per job as their arenas started to cross over.
 int  ctx_alloc(pano_ctx* ctx, void** p, size_t bytes);
 void ctx_free(pano_ctx* ctx, void* p);
 void* ctx_pinned(pano_ctx* ctx, size_t bytes);   // staging buffer A (inputs)
@@ -71,6 +78,14 @@ void* ctx_pinned2(pano_ctx* ctx, size_t bytes);  // staging buffer B (results)
 // descheduled host thread on a busy machine costs milliseconds.
 cudaError_t ctx_spin_event(cudaEvent_t ev);
 cudaError_t ctx_spin_stream(pano_ctx* ctx);
+// Short waits poll a marker word in pinned host memory instead of the driver: a host
+// thread spinning in cudaEventQuery holds the context lock most of the time and starves
+// another thread's kernel launches (two stitch lanes on one GPU went bimodal, 2.5 vs 5 ms).
+// ctx_signal queues "write the next sequence number" on the ctx stream and returns it;
+// ctx_wait_signal spins until the word has reached it (stream sync after a long timeout
+// so that a device fault still surfaces).
+cudaError_t ctx_signal(pano_ctx* ctx, unsigned* token);
+cudaError_t ctx_wait_signal(pano_ctx* ctx, unsigned token);
 void* ctx_ring(pano_ctx* ctx, size_t bytes);
 void* ctx_small_pinned_get(pano_ctx* ctx, size_t bytes, size_t* cap);
 void ctx_small_pinned_put(pano_ctx* ctx, void* p, size_t cap);

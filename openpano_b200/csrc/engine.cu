@@ -1,5 +1,6 @@
 // engine.cu — context, memory, profiling and the extern "C" entry points of
 // libpano_b200.so that are not pure kernel drivers (see include/pano_b200.h).
+#include <mutex>
 #include "sift.cuh"
 #include <stdarg.h>
 #include <stdio.h>
@@ -26,7 +27,7 @@ int ctx_alloc(pano_ctx* ctx, void** p, size_t bytes) {
   *p = nullptr;
   bytes = (bytes + 15) / 16 * 16;      // word-granular helper kernels may touch the padding
   if (bytes == 0) bytes = 16;
-  cudaError_t e = cudaMallocAsync(p, bytes, ctx->stream);
+  cudaError_t e = ctx->pool ? cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream) : cudaMallocAsync(p, bytes, ctx->stream);
   if (e != cudaSuccess) return ctx_cuda(ctx, e, "cudaMallocAsync");
   return PANO_OK;
 }
@@ -52,21 +53,57 @@ void* ctx_pinned2(pano_ctx* ctx, size_t bytes) {
   return grow_pinned(&ctx->pinned2, &ctx->pinned2_bytes, bytes);
 }
 
-cudaError_t ctx_spin_event(cudaEvent_t ev) {
-  for (;;) {
-    cudaError_t e = cudaEventQuery(ev);
-    if (e != cudaErrorNotReady) return e;
+static inline void cpu_relax(int n) {
+  for (int i = 0; i < n; ++i) {
 #if defined(__x86_64__)
     __builtin_ia32_pause();
 #endif
   }
 }
+
+// Long waits (another stream's upload / download): poll the driver, but sparsely.
+cudaError_t ctx_spin_event(cudaEvent_t ev) {
+  for (;;) {
+    cudaError_t e = cudaEventQuery(ev);
+    if (e != cudaErrorNotReady) return e;
+    cpu_relax(400);
+  }
+}
+
+__global__ void k_set_flag(volatile unsigned* flag, unsigned seq) {
+  *flag = seq;
+  __threadfence_system();
+}
+
+cudaError_t ctx_signal(pano_ctx* ctx, unsigned* token) {
+  if (!ctx->flag) {
+    void* p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, 64, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) return e;
+    memset(p, 0, 64);
+    ctx->flag = (volatile unsigned*)p;
+  }
+  const unsigned seq = ++ctx->flag_seq;
+  ctx->launches++;
+  k_set_flag<<<1, 1, 0, ctx->stream>>>(ctx->flag, seq);
+  *token = seq;
+  return cudaGetLastError();
+}
+
+cudaError_t ctx_wait_signal(pano_ctx* ctx, unsigned token) {
+  if (!ctx->flag) return cudaStreamSynchronize(ctx->stream);
+  for (long long spins = 0;; ++spins) {
+    if ((int)(*ctx->flag - token) >= 0) return cudaSuccess;
+    cpu_relax(4);
+    if (spins > (1LL << 28)) return cudaStreamSynchronize(ctx->stream);   // seconds: let a device fault surface
+  }
+}
+
 cudaError_t ctx_spin_stream(pano_ctx* ctx) {
-  cudaEvent_t ev = ctx_sync_event_get(ctx);
-  cudaError_t e = cudaEventRecord(ev, ctx->stream);
-  if (e == cudaSuccess) e = ctx_spin_event(ev);
-  ctx_sync_event_put(ctx, ev);
-  return e;
+  unsigned token = 0;
+  cudaError_t e = ctx_signal(ctx, &token);
+  if (e != cudaSuccess) return e;
+  return ctx_wait_signal(ctx, token);
 }
 
 // ---- copy-engine-free small moves
@@ -132,6 +169,7 @@ int ctx_store(pano_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
 }
 int ctx_put(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
   if (!bytes) return PANO_OK;
+  if (bytes <= 960 * 4) return ctx_put_many(ctx, 1, &d_dst, &h_src, &bytes);
   void* st = ctx_ring(ctx, bytes + 4);
   if (!st) return ctx_fail(ctx, PANO_ERR_CUDA, "pinned ring allocation failed");
   memcpy(st, h_src, bytes);
@@ -166,8 +204,61 @@ static int launch_segs(pano_ctx* ctx, const CopySegs& segs, int n, size_t max_wo
   return PANO_OK;
 }
 
+// Small tables (< 4 KB) travel INSIDE the launch as a by-value kernel parameter, which the
+// front end delivers with the launch command, so the kernel never stalls on a PCIe read of
+// host memory.  (Larger by-value parameters — CUDA 12.1+ takes up to 32 KB — were measured
+// to slow concurrent launches from two host threads down badly; they use the ring.)
+template <int WORDS>
+struct ParamBlob {
+  uint32_t* dst[CTX_MAX_SEGS];
+  unsigned off[CTX_MAX_SEGS];     // word offset into data, ~0u = fill with zeros
+  unsigned words[CTX_MAX_SEGS];
+  uint32_t data[WORDS];
+};
+template <int WORDS>
+__global__ void k_copy_params(const __grid_constant__ ParamBlob<WORDS> b) {
+  uint32_t* d = b.dst[blockIdx.y];
+  const unsigned off = b.off[blockIdx.y], n = b.words[blockIdx.y];
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    d[i] = off == ~0u ? 0u : b.data[off + i];
+}
+
+template <int WORDS>
+static int put_many_params(pano_ctx* ctx, int n, void* const* d_dst, const void* const* h_src, const size_t* bytes) {
+  static ParamBlob<WORDS> blob;            // staging only: copied into the launch by value (ctx calls are serialised,
+  static std::mutex mu;                    // different contexts may race -> lock)
+  std::lock_guard<std::mutex> lock(mu);
+  int m = 0;
+  unsigned used = 0, max_words = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!bytes[i]) continue;
+    const unsigned w = (unsigned)((bytes[i] + 3) / 4);
+    blob.dst[m] = (uint32_t*)d_dst[i];
+    blob.words[m] = w;
+    if (h_src[i]) {
+      blob.off[m] = used;
+      blob.data[used + w - 1] = 0;
+      memcpy(blob.data + used, h_src[i], bytes[i]);
+      used += w;
+    } else {
+      blob.off[m] = ~0u;
+    }
+    max_words = std::max(max_words, w);
+    ++m;
+  }
+  if (!m) return PANO_OK;
+  dim3 grid((unsigned)small_grid(max_words), (unsigned)m);
+  PANO_LAUNCH(ctx, "k_copy_params", k_copy_params<WORDS>, grid, 256, 0, blob);
+  return PANO_OK;
+}
+
 int ctx_put_many(pano_ctx* ctx, int n, void* const* d_dst, const void* const* h_src, const size_t* bytes) {
   if (n > CTX_MAX_SEGS) return ctx_fail(ctx, PANO_ERR_INVALID, "ctx_put_many: %d segments", n);
+  {
+    size_t words = 0;
+    for (int i = 0; i < n; ++i) if (h_src[i]) words += (bytes[i] + 3) / 4;
+    if (words <= 960) return put_many_params<960>(ctx, n, d_dst, h_src, bytes);        // 4 KB launch
+  }
   size_t total = 0;
   for (int i = 0; i < n; ++i) if (h_src[i]) total += align_up(bytes[i] + 4, 64);
   char* st = total ? (char*)ctx_ring(ctx, total) : nullptr;
@@ -277,11 +368,21 @@ int pano_create(pano_ctx** out, int device, void* cuda_stream) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { delete ctx; return ctx_cuda(nullptr, e, "cudaStreamCreate"); }
     ctx->owns_stream = true;
   }
-  // keep freed blocks cached in the default pool: the same sizes recur every batch
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+  // a private pool that keeps its freed blocks: the same sizes recur every batch
+  {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if ((e = cudaMemPoolCreate(&ctx->pool, &props)) != cudaSuccess) {
+      if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+      delete ctx;
+      return ctx_cuda(nullptr, e, "cudaMemPoolCreate");
+    }
     uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
   *out = ctx;
   return PANO_OK;
@@ -296,8 +397,10 @@ void pano_destroy(pano_ctx* ctx) {
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->pinned2) cudaFreeHost(ctx->pinned2);
   if (ctx->ring) cudaFreeHost(ctx->ring);
+  if (ctx->flag) cudaFreeHost((void*)ctx->flag);
   for (auto& sp : ctx->small_pinned) cudaFreeHost(sp.first);
   for (auto e : ctx->sync_events) cudaEventDestroy(e);
+  if (ctx->pool) cudaMemPoolDestroy(ctx->pool);   // released once the last block has been freed
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

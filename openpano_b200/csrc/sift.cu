@@ -71,6 +71,13 @@ __global__ void k_octave_grey(const ImgMeta* __restrict__ imgs, const OctMeta* _
   arena[om.gauss_off + (size_t)r * om.w + c] = (v0 + v1 + v2) / 3.f;
 }
 
+// Tile table of the blur launch, built on the device from the octave table (one entry per
+// CTA: octave entry, tile x, tile y) so that it never crosses PCIe.
+__global__ void k_make_tiles(const int2* __restrict__ span, int n_om, int n_tiles, BlurTile* __restrict__ tiles) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n_tiles) tiles[t] = find_blur_tile(span, n_om, t);
+}
+
 // ============================================================ K2 blur + |DoG|
 // feature/gaussian.hh:29-90 (column pass, then row pass over the column result,
 // replicate border, ascending-k mul-then-add), every level from level 0
@@ -949,7 +956,7 @@ int host_gauss_kernel(float sigma, int window_factor, float* taps, int cap) {
 
 void sift_work_free(pano_ctx* ctx, SiftWork* wk) {
   if (!wk) return;
-  ctx_free(ctx, wk->arena); ctx_free(ctx, wk->d_img); ctx_free(ctx, wk->d_oct); ctx_free(ctx, wk->d_tiles);
+  ctx_free(ctx, wk->arena); ctx_free(ctx, wk->d_img); ctx_free(ctx, wk->d_oct); ctx_free(ctx, wk->d_tiles); ctx_free(ctx, wk->d_tilespan);
   ctx_free(ctx, wk->cand_count); ctx_free(ctx, wk->cand_keys); ctx_free(ctx, wk->sorted_keys);
   ctx_free(ctx, wk->refined); ctx_free(ctx, wk->kp_valid); ctx_free(ctx, wk->npeaks);
   ctx_free(ctx, wk->dirs); ctx_free(ctx, wk->n_refined);
@@ -971,7 +978,8 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
   wk->h_oct.resize((size_t)n * n_oct);
   size_t off = 0;
   int max_w0 = 0, max_h0 = 0;
-  std::vector<BlurTile> tiles;
+  int n_tiles = 0;
+  std::vector<int2> tilespan((size_t)n * n_oct);
   for (int i = 0; i < n; ++i) {
     if (w[i] < 2 || h[i] < 2) { delete wk; return ctx_fail(ctx, PANO_ERR_INVALID, "sift: image too small"); }
     ImgMeta& im = wk->h_img[i];
@@ -1001,13 +1009,12 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
       om.plane = (long long)align_up((size_t)om.w * om.h, 32);
       om.gauss_off = (long long)off; off += (size_t)om.plane * n_scale;
       om.dog_off = (long long)off; off += (size_t)om.plane * (n_scale - 1);
-      for (int ty = 0; ty < ceil_div(om.h, BT_H); ++ty)
-        for (int tx = 0; tx < ceil_div(om.w, BT_W); ++tx)
-          tiles.push_back(BlurTile{i * n_oct + o, tx, ty});
+      tilespan[(size_t)i * n_oct + o] = make_int2(n_tiles, ceil_div(om.w, BT_W));
+      n_tiles += ceil_div(om.w, BT_W) * ceil_div(om.h, BT_H);
     }
   }
   wk->arena_floats = off;
-  wk->n_tiles = (int)tiles.size();
+  wk->n_tiles = n_tiles;
 
   GaussTable gt;
   memset(&gt, 0, sizeof(gt));
@@ -1030,7 +1037,8 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->arena, off * sizeof(float)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_img, n * sizeof(ImgMeta)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_oct, wk->h_oct.size() * sizeof(OctMeta)));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_tiles, tiles.size() * sizeof(BlurTile)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_tiles, (size_t)std::max(n_tiles, 1) * sizeof(BlurTile)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_tilespan, tilespan.size() * sizeof(int2)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->cand_count, (n + 1) * sizeof(int)));   // [n] = descriptor work counter
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->cand_keys, ncand * sizeof(uint32_t)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->sorted_keys, ncand * sizeof(uint32_t)));
@@ -1052,9 +1060,9 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
 
   // metadata upload + candidate-counter reset: one launch through the pinned ring
   {
-    void* dsts[4] = {wk->d_img, wk->d_oct, wk->d_tiles, wk->cand_count};
-    const void* srcs[4] = {wk->h_img.data(), wk->h_oct.data(), tiles.data(), nullptr};
-    size_t sizes[4] = {n * sizeof(ImgMeta), wk->h_oct.size() * sizeof(OctMeta), tiles.size() * sizeof(BlurTile),
+    void* dsts[4] = {wk->d_img, wk->d_oct, wk->d_tilespan, wk->cand_count};
+    const void* srcs[4] = {wk->h_img.data(), wk->h_oct.data(), tilespan.data(), nullptr};
+    size_t sizes[4] = {n * sizeof(ImgMeta), wk->h_oct.size() * sizeof(OctMeta), tilespan.size() * sizeof(int2),
                        (n + 1) * sizeof(int)};
     SIFT_TRY(ctx_put_many(ctx, 4, dsts, srcs, sizes));
   }
@@ -1074,6 +1082,7 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     dim3 g2(ceil_div(max_w0, 32), ceil_div(max_h0, 8), n * n_oct);
     SIFT_LAUNCH("k_octave_grey", k_octave_grey, g2, b, 0, wk->d_img, wk->d_oct, wk->arena);
   }
+  SIFT_LAUNCH("k_make_tiles", k_make_tiles, ceil_div(wk->n_tiles, 256), 256, 0, wk->d_tilespan, n * n_oct, wk->n_tiles, wk->d_tiles);
   {
     const int R = gt.rmax;
     size_t smem = ((size_t)(BT_H + 2 * R) * (BT_W + 2 * R) + (size_t)BT_H * (BT_W + 2 * R)) * sizeof(float);
@@ -1117,7 +1126,7 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
   }
   wk->n_desc = fs->d_count;
 
-  // counts to the host (pinned, async); consumers wait on counts_ready
+  // counts to the host (pinned, async); consumers wait on the completion marker queued behind them
   if (!fs->h_count_pinned) {
     fs->h_count_pinned = (int*)ctx_small_pinned_get(ctx, (size_t)2 * n * sizeof(int) + 16, &fs->h_count_cap);
     if (!fs->h_count_pinned) { sift_work_free(ctx, wk); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned allocation failed"); }
@@ -1128,8 +1137,8 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     size_t sizes[2] = {n * sizeof(int), n * sizeof(int)};
     SIFT_TRY(ctx_store_many(ctx, 2, dsts, srcs, sizes));
   }
-  if (!fs->counts_ready) fs->counts_ready = ctx_sync_event_get(ctx);
-  SIFT_CUDA(cudaEventRecord(fs->counts_ready, ctx->stream));
+  SIFT_CUDA(ctx_signal(ctx, &fs->counts_token));
+  fs->counts_pending = true;
   fs->counts_on_host = false;
 
   if (keep) *keep = wk;
@@ -1140,8 +1149,9 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
 int featureset_sync_counts(pano_featureset* fs) {
   if (fs->counts_on_host) return PANO_OK;
   pano_ctx* ctx = fs->ctx;
-  if (fs->counts_ready) {
-    PANO_CUDA(ctx, ctx_spin_event(fs->counts_ready));
+  if (fs->counts_pending) {
+    PANO_CUDA(ctx, ctx_wait_signal(ctx, fs->counts_token));
+    fs->counts_pending = false;
     fs->h_count.assign(fs->h_count_pinned, fs->h_count_pinned + fs->n_images);
     for (int i = 0; i < fs->n_images; ++i) {
       if (fs->h_count_pinned[fs->n_images + i] > SIFT_CAND_CAP)

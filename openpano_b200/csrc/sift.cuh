@@ -29,6 +29,24 @@ struct OctMeta {
 
 struct BlurTile { int om; int tx, ty; };
 
+#ifdef __CUDACC__
+// CTA index -> (octave entry, tile x, tile y): binary search over the ascending tile_base
+// of the n_om octave entries (the table is a few KB and L1-resident), so that no per-tile
+// table has to be uploaded.
+// span[k] = (first tile of octave entry k, tiles per tile row)
+__device__ __forceinline__ BlurTile find_blur_tile(const int2* __restrict__ span, int n_om, int cta) {
+  int lo = 0, hi = n_om - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (span[mid].x <= cta) lo = mid; else hi = mid - 1;
+  }
+  const int local = cta - span[lo].x, tx_n = span[lo].y;
+  BlurTile t;
+  t.om = lo; t.ty = local / tx_n; t.tx = local - t.ty * tx_n;
+  return t;
+}
+#endif
+
 struct GaussTable {
   int nlev;
   int rmax;
@@ -47,6 +65,7 @@ struct SiftWork {
   ImgMeta* d_img = nullptr;
   OctMeta* d_oct = nullptr;
   BlurTile* d_tiles = nullptr;
+  int2* d_tilespan = nullptr;
   int n_tiles = 0;
   // keypoint state, all [n_img * SIFT_CAND_CAP] unless noted
   int* cand_count = nullptr;      // [n_img]
@@ -71,7 +90,9 @@ struct pano_featureset {
   std::vector<long long> base;  // first row of image i
   std::vector<int> h_count;
   bool counts_on_host = false;
-  cudaEvent_t counts_ready = nullptr;
+  cudaEvent_t counts_ready = nullptr;   // unused by the SIFT path (kept for uploaded sets)
+  unsigned counts_token = 0;            // completion marker of the count read-back (ctx_signal)
+  bool counts_pending = false;
   int* h_count_pinned = nullptr;
   size_t h_count_cap = 0;
   TcOperands tc;              // fp16 tensor-core operands of the descriptors (lazy)
