@@ -430,9 +430,9 @@ def main():
         # mosaic out; conversions and crop on the device).  Beside it one lane, and the Mat32f
         # boundary.  The GPU box is shared: other tenants' PCIe traffic slows whole legs down for
         # seconds at a time (seen: 2.3 -> 5+ ms/job with identical kernel times), so every leg is
-        # timed in E2E_TRIALS trials of `steps` jobs, interleaved with the other legs, and the MEDIAN
+        # timed in E2E_TRIALS (9) trials of `steps` jobs, interleaved with the other legs, and the MEDIAN
         # trial is reported (all trials are in the JSON line).
-        E2E_TRIALS = 5
+        E2E_TRIALS = 9
         legs = {"lanes": Leg(True, args.lanes)}
         legs["one"] = Leg(True, 1) if args.lanes != 1 else legs["lanes"]
         legs["f32"] = Leg(False, 1)

@@ -460,16 +460,19 @@ int pano_blend_target_size(int n, const pano_blend_image* imgs, int* ow, int* oh
 
 int pano_blend_dev(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g, int bands,
                    const pano_params* p, float* d_out, int ow, int oh) {
+  ctx_enter(ctx);
   return blend_device(ctx, n, imgs, g, bands, p, d_out, ow, oh, 0, oh);
 }
 
 int pano_blend_rows_dev(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g, int bands,
                         const pano_params* p, float* d_out_rows, int ow, int oh, int row0, int row1) {
+  ctx_enter(ctx);
   return blend_device(ctx, n, imgs, g, bands, p, d_out_rows, ow, oh, row0, row1);
 }
 
 int pano_blend(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g, int bands,
                const pano_params* p, float* out, int ow, int oh) {
+  ctx_enter(ctx);
   if (!ctx || n <= 0 || !imgs || !out) return PANO_ERR_INVALID;
   std::vector<pano_blend_image> dimgs(imgs, imgs + n);
   std::vector<float*> bufs(n, nullptr);

@@ -56,6 +56,11 @@ struct pano_ctx {
   unsigned flag_seq = 0;
 };
 
+// Every entry point makes its context's device current first: host threads other than the
+// creating one start on device 0 (a stitch lane's thread on rank 1 would otherwise issue
+// its copies against the wrong device).
+static inline void ctx_enter(const pano_ctx* ctx) { if (ctx) cudaSetDevice(ctx->device); }
+
 int  ctx_fail(pano_ctx* ctx, int code, const char* fmt, ...);
 int  ctx_cuda(pano_ctx* ctx, cudaError_t e, const char* what);
 // Stream-ordered device memory from the CONTEXT'S OWN pool.  Contexts sharing the device's

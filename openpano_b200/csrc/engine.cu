@@ -408,25 +408,30 @@ void pano_destroy(pano_ctx* ctx) {
 const char* pano_last_error(const pano_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 int pano_sync(pano_ctx* ctx) {
+  ctx_enter(ctx);
   PANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PANO_OK;
 }
 
-void* pano_stream(pano_ctx* ctx) { return (void*)ctx->stream; }
+void* pano_stream(pano_ctx* ctx) {
+  ctx_enter(ctx); return (void*)ctx->stream; }
 
 int pano_profile_enable(pano_ctx* ctx, int on) {
+  ctx_enter(ctx);
   prof_drain(ctx);
   ctx->profiling = on != 0;
   return PANO_OK;
 }
 
 int pano_profile_reset(pano_ctx* ctx) {
+  ctx_enter(ctx);
   prof_drain(ctx);
   ctx->prof_acc.clear();
   return PANO_OK;
 }
 
 int pano_profile_read(pano_ctx* ctx, int cap, char* names, int* launches, double* total_ms) {
+  ctx_enter(ctx);
   prof_drain(ctx);
   int i = 0;
   for (auto& kv : ctx->prof_acc) {
@@ -441,28 +446,36 @@ int pano_profile_read(pano_ctx* ctx, int cap, char* names, int* launches, double
   return i;
 }
 
-long long pano_launch_count(const pano_ctx* ctx) { return ctx->launches; }
-int pano_match_last_exact_rows(const pano_ctx* ctx) { return ctx->last_match_exact_rows; }
+long long pano_launch_count(const pano_ctx* ctx) {
+  ctx_enter(ctx); return ctx->launches; }
+int pano_match_last_exact_rows(const pano_ctx* ctx) {
+  ctx_enter(ctx); return ctx->last_match_exact_rows; }
 
 // ---------------------------------------------------------------- device utilities
-int pano_dev_alloc(pano_ctx* ctx, size_t bytes, void** d_ptr) { return ctx_alloc(ctx, d_ptr, bytes); }
-int pano_dev_free(pano_ctx* ctx, void* d_ptr) { ctx_free(ctx, d_ptr); return PANO_OK; }
+int pano_dev_alloc(pano_ctx* ctx, size_t bytes, void** d_ptr) {
+  ctx_enter(ctx); return ctx_alloc(ctx, d_ptr, bytes); }
+int pano_dev_free(pano_ctx* ctx, void* d_ptr) {
+  ctx_enter(ctx); ctx_free(ctx, d_ptr); return PANO_OK; }
 int pano_dev_upload(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  ctx_enter(ctx);
   PANO_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   PANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PANO_OK;
 }
 int pano_dev_download(pano_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  ctx_enter(ctx);
   PANO_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   PANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PANO_OK;
 }
 
 int pano_dev_upload_async(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  ctx_enter(ctx);
   PANO_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return PANO_OK;
 }
 int pano_dev_download_async(pano_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  ctx_enter(ctx);
   PANO_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return PANO_OK;
 }
@@ -477,6 +490,7 @@ int pano_host_free(void* h_ptr) { return cudaFreeHost(h_ptr) == cudaSuccess ? PA
 struct pano_event { cudaEvent_t ev; int device; };
 
 int pano_event_create(pano_ctx* ctx, pano_event** out) {
+  ctx_enter(ctx);
   if (!ctx || !out) return PANO_ERR_INVALID;
   pano_event* e = new pano_event;
   e->device = ctx->device;
@@ -486,20 +500,24 @@ int pano_event_create(pano_ctx* ctx, pano_event** out) {
   return PANO_OK;
 }
 int pano_event_record(pano_ctx* ctx, pano_event* ev) {
+  ctx_enter(ctx);
   if (!ctx || !ev) return PANO_ERR_INVALID;
   PANO_CUDA(ctx, cudaEventRecord(ev->ev, ctx->stream));
   return PANO_OK;
 }
 int pano_event_wait(pano_ctx* ctx, pano_event* ev) {
+  ctx_enter(ctx);
   if (!ctx || !ev) return PANO_ERR_INVALID;
   PANO_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev->ev, 0));
   return PANO_OK;
 }
 int pano_event_sync(pano_event* ev) {
+  if (ev) cudaSetDevice(ev->device);
   if (!ev) return PANO_ERR_INVALID;
   return ctx_spin_event(ev->ev) == cudaSuccess ? PANO_OK : PANO_ERR_CUDA;
 }
 void pano_event_destroy(pano_event* ev) {
+  if (ev) cudaSetDevice(ev->device);
   if (!ev) return;
   cudaEventDestroy(ev->ev);
   delete ev;
@@ -521,6 +539,7 @@ static void featureset_release(pano_featureset* fs) {
 
 int pano_sift_detect_batch_dev(pano_ctx* ctx, int n, const float* const* d_rgb, const int* w, const int* h,
                                const pano_params* p, pano_featureset** out) {
+  ctx_enter(ctx);
   if (!ctx || !out) return PANO_ERR_INVALID;
   *out = nullptr;
   pano_featureset* fs = new pano_featureset;
@@ -572,6 +591,7 @@ static int upload_images(pano_ctx* ctx, int n, const float* const* rgb, const in
 
 int pano_sift_detect_batch(pano_ctx* ctx, int n, const float* const* rgb, const int* w, const int* h,
                            const pano_params* p, pano_featureset** out) {
+  ctx_enter(ctx);
   if (!ctx || !out || n <= 0 || !rgb || !w || !h || !p) return PANO_ERR_INVALID;
   *out = nullptr;
   std::vector<float*> d_imgs;
@@ -584,6 +604,7 @@ int pano_sift_detect_batch(pano_ctx* ctx, int n, const float* const* rgb, const 
 }
 
 int pano_sift_detect(pano_ctx* ctx, const float* rgb, int w, int h, const pano_params* p, pano_featureset** out) {
+  ctx_enter(ctx);
   return pano_sift_detect_batch(ctx, 1, &rgb, &w, &h, p, out);
 }
 
@@ -628,15 +649,18 @@ static int featureset_build(pano_ctx* ctx, int n_images, const int* n_kp, const 
 
 int pano_featureset_upload(pano_ctx* ctx, int n_images, const int* n_kp, const float* const* desc,
                            const double* const* coor, pano_featureset** out) {
+  ctx_enter(ctx);
   return featureset_build(ctx, n_images, n_kp, desc, coor, out, false);
 }
 
 int pano_featureset_import_dev(pano_ctx* ctx, int n_images, const int* n_kp, const float* const* d_desc,
                                const double* const* d_coor, pano_featureset** out) {
+  ctx_enter(ctx);
   return featureset_build(ctx, n_images, n_kp, d_desc, d_coor, out, true);
 }
 
 int pano_featureset_export_dev(pano_featureset* fs, int image, double* d_coor_xy, float* d_desc) {
+  if (fs) ctx_enter(fs->ctx);
   if (!fs || image < 0 || image >= fs->n_images) return PANO_ERR_INVALID;
   int rc = featureset_sync_counts(fs);
   if (rc) return rc;
@@ -653,9 +677,11 @@ int pano_featureset_export_dev(pano_featureset* fs, int image, double* d_coor_xy
   return PANO_OK;
 }
 
-int pano_featureset_num_images(const pano_featureset* fs) { return fs ? fs->n_images : PANO_ERR_INVALID; }
+int pano_featureset_num_images(const pano_featureset* fs) {
+  if (fs) ctx_enter(fs->ctx); return fs ? fs->n_images : PANO_ERR_INVALID; }
 
 int pano_featureset_count(pano_featureset* fs, int image) {
+  if (fs) ctx_enter(fs->ctx);
   if (!fs || image < 0 || image >= fs->n_images) return PANO_ERR_INVALID;
   int rc = featureset_sync_counts(fs);
   if (rc) return rc;
@@ -663,6 +689,7 @@ int pano_featureset_count(pano_featureset* fs, int image) {
 }
 
 int pano_featureset_download(pano_featureset* fs, int image, double* coor_xy, float* desc) {
+  if (fs) ctx_enter(fs->ctx);
   if (!fs || image < 0 || image >= fs->n_images) return PANO_ERR_INVALID;
   int rc = featureset_sync_counts(fs);
   if (rc) return rc;
@@ -680,7 +707,8 @@ int pano_featureset_download(pano_featureset* fs, int image, double* coor_xy, fl
   return PANO_OK;
 }
 
-void pano_featureset_free(pano_featureset* fs) { featureset_release(fs); }
+void pano_featureset_free(pano_featureset* fs) {
+  if (fs) ctx_enter(fs->ctx); featureset_release(fs); }
 
 // ---------------------------------------------------------------- stage inspection
 
@@ -692,6 +720,7 @@ struct pano_sift_trace {
 };
 
 int pano_sift_trace_run(pano_ctx* ctx, const float* rgb, int w, int h, const pano_params* p, pano_sift_trace** out) {
+  ctx_enter(ctx);
   if (!ctx || !rgb || !p || !out) return PANO_ERR_INVALID;
   *out = nullptr;
   std::vector<float*> d_imgs;
@@ -711,17 +740,20 @@ int pano_sift_trace_run(pano_ctx* ctx, const float* rgb, int w, int h, const pan
 }
 
 int pano_sift_trace_working_size(const pano_sift_trace* t, int* w0, int* h0) {
+  if (t) ctx_enter(t->ctx);
   *w0 = t->wk->h_img[0].w0; *h0 = t->wk->h_img[0].h0;
   return PANO_OK;
 }
 
 int pano_sift_trace_octave_size(const pano_sift_trace* t, int o, int* w, int* h) {
+  if (t) ctx_enter(t->ctx);
   if (o < 0 || o >= t->wk->n_oct) return PANO_ERR_INVALID;
   *w = t->wk->h_oct[o].w; *h = t->wk->h_oct[o].h;
   return PANO_OK;
 }
 
 int pano_sift_trace_plane(pano_sift_trace* t, int kind, int o, int level, float* out) {
+  if (t) ctx_enter(t->ctx);
   pano_ctx* ctx = t->ctx;
   SiftWork* wk = t->wk;
   if (kind == 0) {
@@ -741,6 +773,7 @@ int pano_sift_trace_plane(pano_sift_trace* t, int kind, int o, int level, float*
 }
 
 int pano_sift_trace_points(pano_sift_trace* t, int stage, int cap, pano_sspoint* out) {
+  if (t) ctx_enter(t->ctx);
   pano_ctx* ctx = t->ctx;
   SiftWork* wk = t->wk;
   int n_raw = 0, n_desc = t->fs->h_count[0];
@@ -782,6 +815,7 @@ int pano_sift_trace_points(pano_sift_trace* t, int stage, int cap, pano_sspoint*
 }
 
 int pano_sift_trace_descriptors(pano_sift_trace* t, int cap, double* coor_xy, float* desc) {
+  if (t) ctx_enter(t->ctx);
   int n = t->fs->h_count[0];
   if (n <= cap && n > 0) {
     int rc = pano_featureset_download(t->fs, 0, coor_xy, desc);
@@ -791,6 +825,7 @@ int pano_sift_trace_descriptors(pano_sift_trace* t, int cap, double* coor_xy, fl
 }
 
 void pano_sift_trace_free(pano_sift_trace* t) {
+  if (t) ctx_enter(t->ctx);
   if (!t) return;
   sift_work_free(t->ctx, t->wk);
   featureset_release(t->fs);

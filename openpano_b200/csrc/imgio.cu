@@ -318,6 +318,7 @@ extern "C" {
 
 int pano_rgb8_to_mat32f_batch_dev(pano_ctx* ctx, int n, const unsigned char* const* d_pix, const int* w, const int* h,
                                   const int* channels, float* const* d_out_hwc) {
+  ctx_enter(ctx);
   if (!ctx || n < 0 || (n && (!d_pix || !w || !h || !channels || !d_out_hwc)))
     return ctx_fail(ctx, PANO_ERR_INVALID, "pano_rgb8_to_mat32f_batch_dev: bad argument");
   if (n == 0) return PANO_OK;
@@ -344,10 +345,12 @@ int pano_rgb8_to_mat32f_batch_dev(pano_ctx* ctx, int n, const unsigned char* con
 }
 
 int pano_rgb8_to_mat32f_dev(pano_ctx* ctx, const unsigned char* d_pix, int w, int h, int channels, float* d_out_hwc) {
+  ctx_enter(ctx);
   return pano_rgb8_to_mat32f_batch_dev(ctx, 1, &d_pix, &w, &h, &channels, &d_out_hwc);
 }
 
 int pano_crop_rect_dev(pano_ctx* ctx, const float* d_mat_hwc, int w, int h, int* d_rect) {
+  ctx_enter(ctx);
   if (!ctx || !d_mat_hwc || !d_rect || w <= 0 || h <= 0)
     return ctx_fail(ctx, PANO_ERR_INVALID, "pano_crop_rect_dev: bad argument");
   const int chunks = ceil_div(h, CROP_CHUNK);
@@ -372,6 +375,7 @@ int pano_crop_rect_dev(pano_ctx* ctx, const float* d_mat_hwc, int w, int h, int*
 }
 
 int pano_mat32f_to_rgb8_dev(pano_ctx* ctx, const float* d_mat_hwc, int w, int h, const int* d_rect, unsigned char* d_out) {
+  ctx_enter(ctx);
   if (!ctx || !d_mat_hwc || !d_out || w <= 0 || h <= 0)
     return ctx_fail(ctx, PANO_ERR_INVALID, "pano_mat32f_to_rgb8_dev: bad argument");
   long long blocks = ((long long)w * h + 255) / 256;

@@ -590,6 +590,7 @@ extern "C" {
 
 int pano_match_pairs(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int* ij, const pano_params* p,
                      pano_matches* out) {
+  ctx_enter(ctx);
   if (!ctx || !fs || !out || n_pairs < 0 || (n_pairs && !ij) || !p) return PANO_ERR_INVALID;
   memset(out, 0, sizeof(*out));
   MatchPlan pl;
@@ -641,6 +642,7 @@ void pano_matches_free(pano_matches* m) {
 
 int pano_match_pairs_dev(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int* ij, const pano_params* p,
                          int* total_matches) {
+  ctx_enter(ctx);
   if (!ctx || !fs || n_pairs < 0 || (n_pairs && !ij) || !p || !total_matches) return PANO_ERR_INVALID;
   MatchPlan pl;
   MatchBuffers b;
@@ -666,6 +668,7 @@ int pano_match_pairs_dev(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const 
 
 int pano_match_bruteforce(pano_ctx* ctx, const float* a, int n, const float* b, int m, const pano_params* p,
                           int* pairs_out, int* n_pairs_out) {
+  ctx_enter(ctx);
   if (!ctx || n < 0 || m < 0 || !p || !pairs_out || !n_pairs_out) return PANO_ERR_INVALID;
   *n_pairs_out = 0;
   if (n == 0 || m == 0) return PANO_OK;

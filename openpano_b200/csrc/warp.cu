@@ -111,6 +111,7 @@ int pano_cyl_warp_shape(int w, int h, double h_factor, const pano_params* p, int
 
 int pano_cyl_warp(pano_ctx* ctx, const float* rgb, int w, int h, double h_factor, const pano_params* p, float* out,
                   int ow, int oh, double* kpts, int nk) {
+  ctx_enter(ctx);
   if (!ctx || !rgb || !out || !p || w <= 1 || h <= 1 || nk < 0 || (nk && !kpts)) return PANO_ERR_INVALID;
   CylProj c = get_projector(w, h, h_factor, p);
   if (c.r <= 0) return ctx_fail(ctx, PANO_ERR_INVALID, "cylinder radius <= 0");
