@@ -184,7 +184,14 @@ def cpu_pass(checker, imgs, pairs, items, geom, bands, params):
 def load_cpu_checker():
     from tests.checker import get_checker, have
     if have("ref_fast"):
-        return get_checker("ref_fast"), "reference"
+        chk = get_checker("ref_fast")
+        try:
+            # every core this process may run on, whatever OMP_NUM_THREADS said when libgomp
+            # was first initialised (another library may have done that long ago)
+            chk.lib.omp_set_num_threads(len(os.sched_getaffinity(0)))
+        except (AttributeError, OSError):
+            pass
+        return chk, "reference"
     if have("ref"):
         return get_checker("ref"), "reference"
     return get_checker("orc"), "port"
