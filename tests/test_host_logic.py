@@ -67,3 +67,74 @@ def test_algorithmic_bytes_follow_survey_formula():
     assert ab["k_blur_dog"] == sp * 4 * 13                      # grey in, 6 levels + 6 |DoG| out
     assert ab["k_extrema_scan"] == sp * 24
     assert ab["k_descriptor"] == 1800 * 528
+
+
+class _FakeLane:
+    """Stands in for PipelinedStitcher: records the call order, returns the job's tag as its matches."""
+
+    def __init__(self, depth=2):
+        self.depth, self.log, self._next, self._inflight = depth, [], 0, {}
+
+    def stage(self, host_ptrs, shapes, out_wh):
+        k = self._next
+        self._next = (self._next + 1) % self.depth
+        if k in self._inflight and self._inflight[k] != "done":
+            # the real stage() blocks here until the slot's previous job has left the device
+            assert ("run", self._inflight[k]) in self.log, "slot reused before its job even ran"
+            self.log.append(("sync", self._inflight[k]))
+        self._inflight[k] = host_ptrs            # the tag travels in place of the pointers
+        self.log.append(("stage", host_ptrs))
+        return k
+
+    def run(self, k, pairs, items, geom, out_ptr, bands=0):
+        tag = self._inflight[k]
+        self.log.append(("run", tag))
+        return (k, tag)
+
+    def wait(self, job):
+        k, tag = job
+        if self._inflight.get(k) == tag:
+            self._inflight[k] = "done"
+        self.log.append(("wait", tag))
+        return [tag]
+
+    def close(self):
+        pass
+
+
+def test_stitch_lanes_schedule_every_job_once_and_in_order():
+    """StitchLanes.map: job i runs on lane i mod L, jobs of a lane run in order, the NEXT job of a
+    lane is staged before the current one runs (so its upload overlaps), every job is waited for
+    exactly once and results come back in job order."""
+    from openpano_b200.stitcher import StitchLanes
+    for n_lanes, n_jobs in ((1, 1), (2, 7), (3, 10), (3, 2)):
+        lanes = StitchLanes.__new__(StitchLanes)
+        lanes.lanes = [_FakeLane() for _ in range(n_lanes)]
+        jobs = [(f"job{i}", None, None, None, None, None, None, 0) for i in range(n_jobs)]
+        res = lanes.map(jobs)
+        assert res == [[f"job{i}"] for i in range(n_jobs)]
+        for q, lane in enumerate(lanes.lanes):
+            mine = [f"job{i}" for i in range(n_jobs) if i % n_lanes == q]
+            assert [t for op, t in lane.log if op == "run"] == mine
+            assert [t for op, t in lane.log if op == "wait"] == mine
+            assert [t for op, t in lane.log if op == "stage"] == mine
+            for a, b in zip(mine[:-1], mine[1:]):          # stage(next) precedes run(current)
+                assert lane.log.index(("stage", b)) < lane.log.index(("run", a))
+
+
+def test_stitch_lanes_surface_worker_errors():
+    from openpano_b200.stitcher import StitchLanes
+
+    class Boom(_FakeLane):
+        def run(self, *a, **k):
+            raise RuntimeError("lane failed")
+
+    lanes = StitchLanes.__new__(StitchLanes)
+    lanes.lanes = [_FakeLane(), Boom()]
+    jobs = [(f"job{i}", None, None, None, None, None, None, 0) for i in range(4)]
+    try:
+        lanes.map(jobs)
+    except RuntimeError as ex:
+        assert "lane failed" in str(ex)
+    else:
+        raise AssertionError("the worker's exception was swallowed")
