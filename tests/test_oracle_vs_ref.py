@@ -129,3 +129,60 @@ def test_imgio_crop(orc, ref):
         assert np.array_equal(co, cr)
         x0, y0, cw, ch = ro
         assert np.array_equal(co, m[y0:y0 + ch, x0:x0 + cw])
+
+
+_RATIO_SCRIPT = """
+import sys
+sys.path.insert(0, {root!r})
+import numpy as np
+from openpano_b200 import synth
+from openpano_b200._abi import default_params
+from tests.checker import get_checker
+orc, ref = get_checker('orc'), get_checker('ref')
+rng = np.random.RandomState(21)
+a = synth.rootsift_like(220, 22)
+b = (a[rng.permutation(220)][:190] + rng.randn(190, 128).astype(np.float32) * 30).astype(np.float32)
+p = default_params(match_reject_next_ratio={ratio})
+ab, ba = orc.match(a, b, p), orc.match(b, a, p)
+assert np.array_equal(ab, ref.match(a, b, p)) and np.array_equal(ba, ref.match(b, a, p))
+print(len(ab))
+"""
+
+
+@pytest.mark.parametrize("ratio,lo,hi", [(0.6, 1, 60), (0.95, 150, 190)])
+def test_match_other_ratios(ref, ratio, lo, hi):
+    """MATCH_REJECT_NEXT_RATIO is a config value (config.cfg:33).  The reference squares it into a
+    function-local `static const` on the FIRST call (matcher.cc:16, :91), i.e. it is frozen per
+    process exactly like the config file is — so every ratio is pinned in a fresh process."""
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = str(Path(__file__).resolve().parent.parent)
+    out = subprocess.run([sys.executable, "-c", _RATIO_SCRIPT.format(root=root, ratio=ratio)], capture_output=True,
+                         text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-1500:]
+    assert lo <= int(out.stdout.strip().splitlines()[-1]) <= hi
+
+
+@pytest.mark.parametrize("lazy,ordered", [(0, 0), (1, 1)])
+def test_blend_scaled_resolution(orc, ref, lazy, ordered):
+    """MAX_OUTPUT_SIZE shrinks the canvas through `resolution` (stitcher_image.cc:108-119): the
+    blend map then samples the sources at a stride > 1."""
+    imgs, org = synth.make_stack(3, 200, 150, 80, 73)
+    items, geom = synth.translation_blend_setup(org, 200, 150, max_output_size=170)
+    assert geom["res_x"] > 2.0
+    p = default_params(lazy_read=lazy, ordered_input=ordered)
+    a, b = orc.blend(imgs, items, geom, 0, p), ref.blend(imgs, items, geom, 0, p)
+    assert gu.same_bits(a, b) and (a >= 0).mean() > 0.5
+    a, b = orc.blend(imgs, items, geom, 3, p), ref.blend(imgs, items, geom, 3, p)
+    assert gu.same_bits(a, b)
+
+
+def test_cyl_warp_other_focal(orc, ref):
+    img = synth.make_canvas(120, 180, 62)
+    p = default_params(focal_length=24.0)
+    k = np.array([[10.0, 5.0], [-80.0, -50.0]])
+    assert orc.cyl_warp_shape(180, 120, 1.0, p) == ref.cyl_warp_shape(180, 120, 1.0, p)
+    oa, ka = orc.cyl_warp(img, k, 1.0, p)
+    ob, kb = ref.cyl_warp(img, k, 1.0, p)
+    assert gu.same_bits(oa, ob) and gu.same_bits(ka, kb)
