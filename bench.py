@@ -38,6 +38,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+RESULT_OUT = sys.stdout
 WORKLOAD = "ordered_13x1500x1112"
 METRIC = "Mpixels/sec SIFT+match+blend"
 UNIT = "Mpx/s"
@@ -260,7 +261,7 @@ def run_reference(args, rank, world):
                                       "blend": stage[2] / args.steps * 1e3}},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -274,6 +275,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=3, help="concurrent stitch jobs per GPU in the e2e leg (StitchLanes)")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries chat on fd 1 (NCCL's version banner, the
+    # reference's timers): keep a private handle to the real stdout for the line and point fd 1 at
+    # stderr for everything else.
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -557,7 +565,7 @@ def main():
             "cpu_baseline": cpu,
             "kernels": kernels,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
