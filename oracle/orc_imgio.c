@@ -35,42 +35,45 @@ int orc_read_img_rgb8(const unsigned char* pix, int w, int h, int channels, floa
   return 0;
 }
 
-/* imgproc.cc:200-235.  Line by line: height[k] = run of pixels with
- * max(r,g,b) >= 0 ending at this line; left[k] / right[k] = furthest columns
- * reachable through heights >= height[k] (path-compressed walks, :213-222);
- * the first strictly larger (right-left+1)*height wins (:223-225). */
+/* imgproc.cc:200-235.  Line by line: run[k] = number of consecutive pixels with
+ * max(r,g,b) >= 0 ending at this line in column k; lo[k] / hi[k] = furthest columns
+ * reachable from k through runs >= run[k] (:213-222); the first strictly larger
+ * (hi-lo+1)*run over (line, column) order wins (:223-225). */
 int orc_crop(const float* mat, int w, int h, int* rect, float* out_hwc) {
   if (!mat || w <= 0 || h <= 0) return -1;
-  int* height = (int*)calloc((size_t)w, sizeof(int));
-  int* left = (int*)malloc(sizeof(int) * (size_t)w);
-  int* right = (int*)malloc(sizeof(int) * (size_t)w);
-  int maxarea = 0, ll = 0, rr = 0, hh = 0, nl = 0;
+  int* run = (int*)calloc((size_t)w, sizeof(int));      /* valid pixels ending at this line, per column */
+  int* lo = (int*)malloc(sizeof(int) * (size_t)w);      /* leftmost column reachable over runs >= run[k] */
+  int* hi = (int*)malloc(sizeof(int) * (size_t)w);      /* rightmost such column */
+  int best = 0, best_lo = 0, best_hi = 0, best_run = 0, best_line = 0;
   for (int line = 0; line < h; ++line) {
-    for (int k = 0; k < w; ++k) {
-      const float* p = mat + ((size_t)line * w + k) * 3;
-      float m01 = (p[0] < p[1]) ? p[1] : p[0];                    /* std::max */
-      float m = (m01 < p[2]) ? p[2] : m01;
-      height[k] = m < 0 ? 0 : height[k] + 1;
+    const float* px = mat + (size_t)line * w * 3;
+    for (int k = 0; k < w; ++k, px += 3) {
+      float m01 = (px[0] < px[1]) ? px[1] : px[0];                /* std::max keeps its first argument on ties/NaN */
+      float m = (m01 < px[2]) ? px[2] : m01;
+      run[k] = m < 0 ? 0 : run[k] + 1;                            /* Color::NO ends the run */
     }
+    /* spans by pointer jumping over already-resolved neighbours, left then right (:213-222) */
     for (int k = 0; k < w; ++k) {
-      left[k] = k;
-      while (left[k] > 0 && height[k] <= height[left[k] - 1]) left[k] = left[left[k] - 1];
+      int l = k;
+      while (l > 0 && run[k] <= run[l - 1]) l = lo[l - 1];
+      lo[k] = l;
     }
     for (int k = w - 1; k >= 0; --k) {
-      right[k] = k;
-      while (right[k] < w - 1 && height[k] <= height[right[k] + 1]) right[k] = right[right[k] + 1];
+      int r = k;
+      while (r < w - 1 && run[k] <= run[r + 1]) r = hi[r + 1];
+      hi[k] = r;
     }
     for (int k = 0; k < w; ++k) {
-      int area = (right[k] - left[k] + 1) * height[k];
-      if (area > maxarea) {                                       /* update_max, utils.hh */
-        maxarea = area;
-        ll = left[k]; rr = right[k]; hh = height[k]; nl = line;
+      int area = (hi[k] - lo[k] + 1) * run[k];
+      if (area > best) {                                          /* update_max: strictly larger only */
+        best = area;
+        best_lo = lo[k]; best_hi = hi[k]; best_run = run[k]; best_line = line;
       }
     }
   }
-  free(height); free(left); free(right);
-  int cw = rr - ll + 1, ch = hh;
-  int offx = ll, offy = nl - hh + 1;
+  free(run); free(lo); free(hi);
+  const int cw = best_hi - best_lo + 1, ch = best_run;
+  const int offx = best_lo, offy = best_line - best_run + 1;
   if (rect) { rect[0] = offx; rect[1] = offy; rect[2] = cw; rect[3] = ch; }
   if (out_hwc)
     for (int i = 0; i < ch; ++i)
