@@ -509,6 +509,15 @@ def main():
             roof = {"kernel": top, "bound": t.get("bound"), "achieved": t.get("achieved"), "peak": t.get("peak"),
                     "unit": t.get("unit"), "frac": t.get("frac"), "traffic": traffic, "peak_source": peak_src,
                     "share_of_step": t["share"], "avg_ms": t["avg_ms"]}
+            # the dominant kernel (k_descriptor) is issue-bound: its §8d bytes are only its outputs, so its
+            # HBM fraction says little.  Beside it, the largest kernel that IS bandwidth-limited.
+            bw = [k for k, v in kernels.items() if v.get("bound") == "hbm" and (v.get("frac") or 0) >= 0.05]
+            if bw:
+                k2 = max(bw, key=lambda k: kernels[k]["share"])
+                v2 = kernels[k2]
+                roof["largest_bandwidth_bound_kernel"] = {
+                    "kernel": k2, "achieved": v2["achieved"], "peak": v2["peak"], "unit": v2["unit"], "frac": v2["frac"],
+                    "share_of_step": v2["share"], "avg_ms": v2["avg_ms"]}
 
         # ---- CPU baseline (rank 0, N == 1): the reference's own TUs on this host
         cpu = None
