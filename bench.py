@@ -490,7 +490,7 @@ def main():
             for name, (cnt, tms) in sorted(prof.items(), key=lambda kv: -kv[1][1]):
                 avg = tms / max(cnt, 1)
                 ent = {"launches_per_step": cnt / PROF_STEPS, "avg_ms": avg, "share": tms / tot if tot else 0}
-                if name == "k_match_top2":
+                if name in ("k_match_top2", "k_tc_top2"):
                     flops = sum(2.0 * counts[i] * counts[j] * 128 for i, j in pairs)   # §8d: 2·N·M·128 per pair
                     ent.update(bound="tensor", achieved=flops / (avg * 1e-3) / 1e12, peak=tf_peak, unit="TFLOP/s")
                 elif ab.get(name):
