@@ -8,10 +8,14 @@
  * torch / C++ types.  All functions return 0 on success or a negative
  * pano_status; they never call exit().
  *
- * Threading: a pano_ctx owns one CUDA stream and scratch pools; calls on one
- * ctx must be serialized by the caller (create one ctx per host thread, or use
- * the *_batch entry points, which is how the reference's
- * `#pragma omp parallel for` over images maps to this engine).
+ * Threading: a pano_ctx owns one CUDA stream, a private stream-ordered memory
+ * pool and pinned scratch; calls on one ctx must be serialized by the caller
+ * (create one ctx per host thread, or use the *_batch entry points, which is
+ * how the reference's `#pragma omp parallel for` over images maps to this
+ * engine).  Different contexts may be driven from different host threads at
+ * the same time; every entry point makes its context's device current for the
+ * calling thread, so a ctx can be used from any thread on a multi-GPU host.
+ * Work of different contexts overlaps on the device; order it with pano_event_*.
  */
 #ifndef PANO_B200_H
 #define PANO_B200_H
