@@ -48,7 +48,7 @@ UNIT = "Mpx/s"
 def make_workload(rank: int, bands: int):
     from openpano_b200 import synth
     from openpano_b200._abi import default_params
-    from openpano_b200.stitcher import ordered_pairs
+    from openpano_b200.synth import ordered_pairs
 
     cfg = dict(synth.CONFIGS[WORKLOAD])
     cfg["seed"] = cfg["seed"] + 1000 * rank          # each rank stitches its own stack (weak scaling)
@@ -66,53 +66,23 @@ def make_workload(rank: int, bands: int):
 
 
 def octave_dims(w, h, params):
-    """Working/octave sizes with the reference's float arithmetic (feature.cc:33-34, dog.cc:105-107)."""
-    f32 = np.float32
-    ratio = f32(params.sift_working_size) * f32(2.0) / f32(w + h)
-    h0, w0 = int(f32(h) * ratio), int(f32(w) * ratio)
-    dims = [(w0, h0)]
-    for o in range(1, params.num_octave):
-        factor = f32(float(params.scale_factor) ** (-o))
-        dims.append((int(np.ceil(f32(w0) * factor)), int(np.ceil(f32(h0) * factor))))
-    return dims
+    from tools.bench_configs import octave_dims as od
+    return od(w, h, params)
 
 
 def algorithmic_bytes(imgs, items, params, counts):
-    """Per-launch algorithmic traffic of each kernel (compulsory-traffic model of
-    SURVEY.md §8d: every array one stage produces and another consumes is written
-    once and read once; fused temporaries are free).  Returns name -> (bytes, unit)."""
-    n = len(imgs)
-    ns = params.num_scale
-    p_in = sum(im.shape[0] * im.shape[1] for im in imgs)
-    p0 = 0
-    sp = 0
-    for im in imgs:
-        d = octave_dims(im.shape[1], im.shape[0], params)
-        p0 += d[0][0] * d[0][1]
-        sp += sum(a * b for a, b in d)
-    n_desc = sum(counts)
-    roi = sum((it[2] - it[0] + 1) * (it[3] - it[1] + 1) for it in items)
-    tw, th = max(it[2] for it in items), max(it[3] for it in items)
-    L = max(params.multiband, 0)
-    return {
-        "k_working_resize": min(p_in, 4 * p0) * 12 + p0 * 12,
-        "k_octave_grey": p0 * 12 + sp * 4,
-        "k_blur_dog": sp * 4 * (1 + 2 * (ns - 1)),            # read grey, write 6 levels + 6 |DoG|
-        "k_extrema_scan": sp * 4 * (ns - 1),                  # reads the |DoG| levels once
-        "k_rank_sort": n_desc * 8,
-        "k_refine": n_desc * (27 * 4 + 40),
-        "k_orientation": n_desc * (196 * 4 + 8),
-        "k_expand_scan": n_desc * 16,
-        "k_descriptor": n_desc * (16 + 512),                  # §8d: outputs n_kp*(16+512)
-        "k_match_top2": None,                                 # tensor-bound, see flops below
-        "k_match_decide": n_desc * 32,
-        "k_linear_blend": roi * 12 + tw * th * 12,
-        "k_mb_first_level": roi * (12 + 16),
-        "k_mb_weight_argmax": roi * 8,
-        "k_mb_blur": roi * 32,                                # read + write one float4 level (both passes fused)
-        "k_mb_accumulate": roi * (16 + 12) + tw * th * 12,
-        "k_fill": tw * th * 12,
-    }
+    """Per-launch algorithmic traffic of each kernel (SURVEY.md §8d model; tools/bench_configs.py)."""
+    from tools.bench_configs import algorithmic_bytes as ab
+    return ab([im.shape[:2] for im in imgs], items, params, counts, params.multiband)
+
+
+def config_dict(imgs, pairs, bands, world, extra=None):
+    """The same keys on both arms (ours / reference), so the driver can compare them."""
+    d = {"workload": WORKLOAD, "images": len(imgs), "image_wh": [imgs[0].shape[1], imgs[0].shape[0]],
+         "pairs": len(pairs), "bands": bands, "blend": "linear" if bands == 0 else "multiband",
+         "geometry": "generator-known homographies (flat projection)", "parallelism": f"dp{world}"}
+    d.update(extra or {})
+    return d
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -251,10 +221,11 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "bands": args.bands, "matcher": "PairWiseMatcher (FLANN kd-forest)",
-                   "geometry": "generator-known homographies", "features": nfeat, "matches": nmatch,
-                   "boundary": "Mat32f in / Mat32f out: read_img's, crop's and write_rgb's loops are NOT in the "
-                               "timed region (less work than the CUDA arm's rgb8 e2e, which includes them)"},
+        "config": config_dict(imgs, pairs, args.bands, args.gpus),
+        "notes": {"matcher": "PairWiseMatcher (FLANN kd-forest)", "features": nfeat, "matches": nmatch,
+                  "boundary": "Mat32f in / Mat32f out: read_img's, crop's and write_rgb's loops are NOT in the "
+                              "timed region (less work than the CUDA arm's rgb8 e2e, which includes them; compare "
+                              "with e2e.mat32f_value of the CUDA arm for the same boundary)"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": chk.num_threads(), "kind": kind,
                          "sample": f"full {WORKLOAD} workload per step (host cores: {os.cpu_count()})",
                          "stage_ms": {"features": stage[0] / args.steps * 1e3, "match": stage[1] / args.steps * 1e3,
@@ -274,6 +245,10 @@ def main():
     ap.add_argument("--bands", type=int, default=0, help="0 = LinearBlender (reference default), k = MultiBandBlender{k}")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=3, help="concurrent stitch jobs per GPU in the e2e leg (StitchLanes)")
+    ap.add_argument("--configs", default="all",
+                    help="extra BASELINE.json configs measured in the same run at N=1 (comma list of 2mb,3,4,5; "
+                         "'all'; 'none').  N>1 adds the sharded config-3 leg instead.")
+    ap.add_argument("--sweep-sizes", default="10000,50000,100000,500000")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries chat on fd 1 (NCCL's version banner, the
     # reference's timers): keep a private handle to the real stdout for the line and point fd 1 at
@@ -540,6 +515,46 @@ def main():
             except Exception as ex:  # the checker is optional equipment on the box
                 cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(ex)}
 
+        # ---- the other BASELINE.json configs (N == 1) / the sharded path (N > 1), same run, same engine
+        configs, sharded = None, None
+        st.release_images()
+        want = [] if args.configs == "none" else (["2mb", "3", "4", "5"] if args.configs == "all" else args.configs.split(","))
+        if world == 1 and want:
+            from openpano_b200 import synth as _synth
+            from openpano_b200._abi import default_params as _dp
+            from tools import bench_configs as bc
+            loader = None if args.no_cpu_baseline else load_cpu_checker
+            use_all_host_threads()
+            configs = {}
+
+            def leg(key, fn):
+                try:
+                    configs[key] = fn()
+                except Exception as ex:      # one failing leg must not take the headline line down
+                    configs[key] = {"error": repr(ex)}
+            if "2mb" in want:
+                leg("config2_multiband5", lambda: bc.run_stack(
+                    eng, "ordered_13x1500x1112, MULTIBAND 5", "ordered_13x1500x1112", _synth.ordered_pairs, 5,
+                    _dp(ordered_input=1, multiband=5), cpu_loader=loader, all_cpus=all_cpus))
+            if "3" in want:
+                leg("config3_unordered38", lambda: bc.run_stack(
+                    eng, "unordered_38x1300x867, all 703 pairs, linear blend", "unordered_38x1300x867", _synth.all_pairs, 0,
+                    _dp(), cpu_loader=loader, all_cpus=all_cpus))
+            if "4" in want:
+                leg("config4_match_sweep", lambda: bc.run_sweep(eng, [int(x) for x in args.sweep_sizes.split(",")], _dp()))
+            if "5" in want:
+                leg("config5_uav64_multiband5", lambda: bc.run_stack(
+                    eng, "uav_64x4000x3000, MULTIBAND 5, LAZY_READ 0, MAX_OUTPUT_SIZE 8000", "uav_64x4000x3000",
+                    lambda n: [(i, i + 1) for i in range(n - 1)], 5, _dp(multiband=5, lazy_read=0), steps=3,
+                    max_output=8000, cpu_views=16, cpu_loader=loader, all_cpus=all_cpus))
+        if world > 1:
+            from openpano_b200._abi import default_params as _dp
+            from tools import bench_configs as bc
+            try:
+                sharded = bc.run_sharded(eng, rank, world, _dp())
+            except Exception as ex:
+                sharded = {"error": repr(ex)}
+
         st.close()
         eng.close()
 
@@ -548,12 +563,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "images": len(imgs), "image_wh": [imgs[0].shape[1], imgs[0].shape[0]],
-                       "pairs": len(pairs), "bands": args.bands, "blend": "linear" if args.bands == 0 else "multiband",
-                       "geometry": "generator-known homographies (flat projection)", "parallelism": f"dp{world}", "cpu_affinity_cpus": numa_cpus,
-                       "l2_policy": "inputs_exceed_l2 (260 MB of images + 0.9 GB pyramid arena per step)",
-                       "features": int(sum(counts)), "matches": int(n_matches),
-                       "match_rows_rescanned_exactly": int(exact_rows)},
+            "config": config_dict(imgs, pairs, args.bands, world),
+            "notes": {"cpu_affinity_cpus": numa_cpus,
+                      "l2_policy": "inputs_exceed_l2 (260 MB of images + 0.9 GB pyramid arena per step)",
+                      "features": int(sum(counts)), "matches": int(n_matches),
+                      "match_rows_rescanned_exactly": int(exact_rows)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                     "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_per_step * 1e3,
@@ -568,11 +582,19 @@ def main():
                     "mat32f_boundary": {"value": world * mpx / f32_per_step, "ms_per_step": f32_per_step * 1e3,
                                         "h2d_bytes_per_step": int(f32_h2d), "d2h_bytes_per_step": int(f32_d2h)},
                     "single_job_latency_ms_mat32f": e2e_latency * 1e3,
-                    "single_job_value_mat32f": world * mpx / e2e_latency},
+                    "single_job_value_mat32f": world * mpx / e2e_latency,
+                    # the same figures as flat scalars (nested objects get dropped by some JSON consumers)
+                    "one_lane_ms_per_step": one_lane_per_step * 1e3, "one_lane_value": world * mpx / one_lane_per_step,
+                    "mat32f_ms_per_step": f32_per_step * 1e3, "mat32f_value": world * mpx / f32_per_step,
+                    "mat32f_h2d_bytes_per_step": int(f32_h2d), "mat32f_d2h_bytes_per_step": int(f32_d2h),
+                    "single_job_ms": e2e_latency * 1e3, "single_job_value": world * mpx / e2e_latency,
+                    "lanes_trials_ms": e2e_trials["lanes"], "lanes_worst_trial_ms": max(e2e_trials["lanes"])},
             "gpu_launches": int(launches * world),
             "roofline": roof,
             "cpu_baseline": cpu,
             "kernels": kernels,
+            "configs": configs,
+            "sharded": sharded,
         }
         print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:

@@ -126,11 +126,20 @@ int pano_match_last_exact_rows(const pano_ctx* ctx);
 typedef struct pano_featureset pano_featureset;
 
 /* Host images: n pointers to H×W×3 f32 RGB in [0,1] (Mat32f layout,
- * lib/mat.h:7-60).  Includes H2D of the images (pinned staging + async). */
+ * lib/mat.h:7-60).  Includes H2D of the images.  Pageable buffers are staged and may
+ * be reused as soon as the call returns; PINNED buffers (pano_host_alloc /
+ * cudaHostAlloc) are read by an asynchronous copy and must stay untouched until the
+ * first pano_featureset_count / _download / pano_match_* on the result, or pano_sync.
+ *
+ * Capacity: per-image keypoint lists start at 8192 entries and are NOT a limit — when
+ * an image overflows them (the reference's vectors are unbounded, extrema.cc:56-57) the
+ * batch is run again with doubled lists at the first count query, transparently. */
 int pano_sift_detect_batch(pano_ctx* ctx, int n, const float* const* rgb_hwc,
                            const int* w, const int* h, const pano_params* p,
                            pano_featureset** out);
-/* Same, images already resident in device memory (device pointers). */
+/* Same, images already resident in device memory (device pointers).  The images must
+ * stay valid until the first count query / download / match on the featureset (they are
+ * read again if a keypoint list has to grow). */
 int pano_sift_detect_batch_dev(pano_ctx* ctx, int n, const float* const* d_rgb_hwc,
                                const int* w, const int* h, const pano_params* p,
                                pano_featureset** out);
@@ -235,7 +244,10 @@ int pano_blend_dev(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pan
 /* Rows [row0, row1) of the same mosaic into d_out_rows ((row1-row0)×out_w×3 f32): the
  * strip partition of the canvas across GPUs (every output pixel of
  * LinearBlender::run is independent, blender.cc:37-96, so concatenated strips are
- * bit-identical to pano_blend_dev).  bands must be 0. */
+ * bit-identical to pano_blend_dev).  bands > 0 (MultiBandBlender): the strip is computed
+ * from every image's ROI clipped to [row0 - H, row1 + H), H = the summed half-widths of
+ * the level blurs (6+6+6+9 = 27 rows for 5 bands): a band at level l depends on level 0
+ * only within that radius, so concatenated strips are bit-identical as well. */
 int pano_blend_rows_dev(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g,
                         int bands, const pano_params* p, float* d_out_rows, int out_w, int out_h,
                         int row0, int row1);

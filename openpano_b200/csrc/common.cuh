@@ -39,6 +39,10 @@ struct pano_ctx {
   int last_match_exact_rows = 0;   // rows the last match call had to decide exactly (gathered pass)
   int last_match_full_rescans = 0; // of those, rows that needed a scan of every target
   int num_sms = 148;
+  // cudaFuncSetAttribute is per device: remembered per context, never per process
+  bool attr_tc = false, attr_match = false;
+  int sift_cap = 0;                // per-image list capacity SIFT batches start with (grows on overflow, sticky)
+  void* tma_encode = nullptr;      // cuTensorMapEncodeTiled, resolved through the runtime (no -lcuda)
   // pinned host staging (grown on demand)
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -123,6 +127,14 @@ void ctx_prof_end(pano_ctx* ctx);
     cudaError_t _e = cudaGetLastError();                                            \
     if (_e != cudaSuccess) return ctx_cuda((ctx), _e, name);                        \
   } while (0)
+
+// A TMA descriptor (CUtensorMap: 128 bytes, 64-byte aligned) for cp.async.bulk.tensor tile
+// loads: an f32 tensor of `rank` dimensions (innermost first), strides_bytes[rank-1] for
+// dimensions 1.., box = tile extent per dimension.  Encoded on the host, copied to device
+// memory and handed to the kernels by pointer.
+struct __align__(64) TmaDesc { unsigned long long opaque[16]; };
+int ctx_tma_encode(pano_ctx* ctx, TmaDesc* out, void* base, int rank, const unsigned long long* dims,
+                   const unsigned long long* strides_bytes, const unsigned* box);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t a, size_t b) { return (a + b - 1) / b * b; }

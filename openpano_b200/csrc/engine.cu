@@ -4,6 +4,7 @@
 #include "sift.cuh"
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 
@@ -530,6 +531,7 @@ static void featureset_release(pano_featureset* fs) {
   pano_ctx* ctx = fs->ctx;
   if (ctx) {
     ctx_free(ctx, fs->d_desc); ctx_free(ctx, fs->d_coor); ctx_free(ctx, fs->d_count);
+    ctx_free(ctx, fs->owned_block);
     tc_release(ctx, &fs->tc);
   }
   if (fs->counts_ready) { if (ctx) ctx_sync_event_put(ctx, fs->counts_ready); else cudaEventDestroy(fs->counts_ready); }
@@ -542,9 +544,16 @@ int pano_sift_detect_batch_dev(pano_ctx* ctx, int n, const float* const* d_rgb, 
   ctx_enter(ctx);
   if (!ctx || !out) return PANO_ERR_INVALID;
   *out = nullptr;
+  if (n <= 0 || !d_rgb || !w || !h || !p) return ctx_fail(ctx, PANO_ERR_INVALID, "sift: bad argument");
   pano_featureset* fs = new pano_featureset;
   fs->ctx = ctx;
-  int rc = sift_run_batch(ctx, n, d_rgb, w, h, p, fs, nullptr);
+  // kept for the capacity retry of featureset_sync_counts
+  fs->src.assign(d_rgb, d_rgb + n); fs->src_w.assign(w, w + n); fs->src_h.assign(h, h + n); fs->src_params = *p;
+  if (ctx->sift_cap <= 0) {
+    const char* e = getenv("PANO_SIFT_CAP");            // test hook: start small to exercise the growth path
+    ctx->sift_cap = e ? std::max(256, atoi(e)) : SIFT_CAP_DEFAULT;
+  }
+  int rc = sift_run_batch(ctx, n, d_rgb, w, h, p, fs, nullptr, ctx->sift_cap);
   if (rc != 0) { featureset_release(fs); return rc; }
   *out = fs;
   return PANO_OK;
@@ -599,7 +608,8 @@ int pano_sift_detect_batch(pano_ctx* ctx, int n, const float* const* rgb, const 
   int rc = upload_images(ctx, n, rgb, w, h, d_imgs, &d_block);
   if (rc) { ctx_free(ctx, d_block); return rc; }
   rc = pano_sift_detect_batch_dev(ctx, n, d_imgs.data(), w, h, p, out);
-  ctx_free(ctx, d_block);
+  if (rc) { ctx_free(ctx, d_block); return rc; }
+  (*out)->owned_block = d_block;       // released once the counts are known (a capacity retry reads it again)
   return rc;
 }
 
@@ -730,9 +740,19 @@ int pano_sift_trace_run(pano_ctx* ctx, const float* rgb, int w, int h, const pan
   pano_featureset* fs = new pano_featureset;
   fs->ctx = ctx;
   SiftWork* wk = nullptr;
-  rc = sift_run_batch(ctx, 1, d_imgs.data(), &w, &h, p, fs, &wk);
-  if (rc) { featureset_release(fs); ctx_free(ctx, d_block); return rc; }
-  rc = featureset_sync_counts(fs);
+  // the trace keeps the work buffers of ONE run, so it grows the lists itself
+  for (int cap = SIFT_CAP_DEFAULT;; cap *= 2) {
+    rc = sift_run_batch(ctx, 1, d_imgs.data(), &w, &h, p, fs, &wk, cap);
+    if (rc) { featureset_release(fs); ctx_free(ctx, d_block); return rc; }
+    rc = featureset_sync_counts(fs);
+    if (rc == PANO_ERR_CAPACITY && cap < SIFT_CAP_MAX) {
+      sift_work_free(ctx, wk); wk = nullptr;
+      ctx_free(ctx, fs->d_desc); ctx_free(ctx, fs->d_coor); ctx_free(ctx, fs->d_count);
+      fs->d_desc = nullptr; fs->d_coor = nullptr; fs->d_count = nullptr; fs->error = 0;
+      continue;
+    }
+    break;
+  }
   if (rc) { sift_work_free(ctx, wk); featureset_release(fs); ctx_free(ctx, d_block); return rc; }
   pano_sift_trace* t = new pano_sift_trace{ctx, wk, fs, d_block};
   *out = t;
@@ -762,11 +782,15 @@ int pano_sift_trace_plane(pano_sift_trace* t, int kind, int o, int level, float*
   }
   if (o < 0 || o >= wk->n_oct) return PANO_ERR_INVALID;
   const OctMeta& om = wk->h_oct[o];
-  size_t bytes = (size_t)om.w * om.h * sizeof(float);
-  if (kind == 1 && level >= 0 && level < wk->n_scale)
-    return pano_dev_download(ctx, out, wk->arena + om.gauss_off + (size_t)level * om.plane, bytes);
-  if (kind == 2 && level >= 0 && level < wk->n_scale - 1)
-    return pano_dev_download(ctx, out, wk->arena + om.dog_off + (size_t)level * om.plane, bytes);
+  const float* src = nullptr;
+  if (kind == 1 && level >= 0 && level < wk->n_scale) src = wk->arena + om.gauss_off + (size_t)level * om.plane;
+  if (kind == 2 && level >= 0 && level < wk->n_scale - 1) src = wk->arena + om.dog_off + (size_t)level * om.plane;
+  if (src) {   // planes are pitched on the device, dense for the caller
+    PANO_CUDA(ctx, cudaMemcpy2DAsync(out, (size_t)om.w * sizeof(float), src, (size_t)om.pitch * sizeof(float),
+                                     (size_t)om.w * sizeof(float), (size_t)om.h, cudaMemcpyDeviceToHost, ctx->stream));
+    PANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PANO_OK;
+  }
   // mag/ort are never materialised by the engine (recomputed inside the
   // orientation/descriptor kernels); not available as planes.
   return PANO_ERR_INVALID;
@@ -778,7 +802,7 @@ int pano_sift_trace_points(pano_sift_trace* t, int stage, int cap, pano_sspoint*
   SiftWork* wk = t->wk;
   int n_raw = 0, n_desc = t->fs->h_count[0];
   if (pano_dev_download(ctx, &n_raw, wk->cand_count, sizeof(int))) return PANO_ERR_CUDA;
-  n_raw = std::min(n_raw, SIFT_CAND_CAP);
+  n_raw = std::min(n_raw, wk->cap);
   if (stage == 0) {
     std::vector<uint32_t> keys(std::max(n_raw, 1));
     if (n_raw && pano_dev_download(ctx, keys.data(), wk->sorted_keys, n_raw * sizeof(uint32_t))) return PANO_ERR_CUDA;

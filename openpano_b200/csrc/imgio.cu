@@ -339,8 +339,13 @@ int pano_rgb8_to_mat32f_batch_dev(pano_ctx* ctx, int n, const unsigned char* con
   if (int rc = ctx_put(ctx, d_jobs, jobs.data(), sizeof(Rgb8Job) * n)) { ctx_free(ctx, d_jobs); return rc; }
   long long per_img = (max_px * 3 / 4 + 255) / 256;
   int gx = (int)std::min<long long>(std::max<long long>(per_img, 1), std::max(1, ctx->num_sms * 8 / n));
-  PANO_LAUNCH(ctx, "k_rgb8_to_f32", k_rgb8_to_f32, dim3(gx, n), 256, 0, d_jobs);
+  ctx->launches++;
+  if (ctx->profiling) ctx_prof_begin(ctx, "k_rgb8_to_f32");
+  k_rgb8_to_f32<<<dim3(gx, n), 256, 0, ctx->stream>>>(d_jobs);
+  if (ctx->profiling) ctx_prof_end(ctx);
+  const cudaError_t le = cudaGetLastError();
   ctx_free(ctx, d_jobs);
+  if (le != cudaSuccess) return ctx_cuda(ctx, le, "k_rgb8_to_f32");
   return PANO_OK;
 }
 

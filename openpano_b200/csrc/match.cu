@@ -494,10 +494,9 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
   dim3 gd(std::max(1, ceil_div(pl.max_small, 256)), (unsigned)pl.pairs.size());
   if (!tensor) {
     const size_t smem = (size_t)2 * MT * MT_STRIDE * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!ctx->attr_match) {   // per device, hence per context (see match_tc.cu)
       PANO_CUDA(ctx, cudaFuncSetAttribute(k_match_top2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
+      ctx->attr_match = true;
     }
     if (!pl.exact_tasks.empty())
       PANO_LAUNCH(ctx, "k_match_top2", k_match_top2, (unsigned)pl.exact_tasks.size(), MT_THREADS, smem, fs->d_desc,
@@ -524,7 +523,8 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
     // (k_tc_filter), k_exact_cands takes exact fp32 distances to just those columns,
     // and only rows that overflow their candidate slots are re-scanned against every
     // target (k_exact_rows).
-    const int block_cap = (int)std::min<size_t>(std::max<size_t>(pl.tc_tasks.size(), 1), 4096);
+    int block_cap = (int)std::min<size_t>(std::max<size_t>(pl.tc_tasks.size(), 1), 4096);
+    if (const char* e = getenv("PANO_MATCH_BLOCK_CAP")) block_cap = std::max(1, std::min(block_cap, atoi(e)));   // test hook: force the full re-scan fallback
     const size_t grow = (size_t)block_cap * 128;
     TcFilter f;
     if ((rc = ctx_alloc(ctx, (void**)&b.list_rows, nres * sizeof(int))) ||
@@ -614,7 +614,10 @@ int pano_match_pairs(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int*
     const PairMeta& pm = pl.pairs[k];
     int c = 0;
     for (int r = 0; r < pm.n_small; ++r) {
-      if (h_out[pm.out_off + r] == OUT_PENDING) return ctx_fail(ctx, PANO_ERR_CUDA, "match: undecided row (internal error)");
+      if (h_out[pm.out_off + r] == OUT_PENDING) {
+        pano_matches_free(out);
+        return ctx_fail(ctx, PANO_ERR_CUDA, "match: undecided row (internal error)");
+      }
       c += h_out[pm.out_off + r] >= 0;
     }
     out->count[k] = c; out->offset[k] = total; total += c;

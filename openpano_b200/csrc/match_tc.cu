@@ -386,11 +386,11 @@ void tc_release(pano_ctx* ctx, TcOperands* ops) {
 int tc_run_top2(pano_ctx* ctx, const TcOperands* ops, const TcTask* d_tasks, int n_tasks, TcTop2* d_res) {
   if (n_tasks == 0) return PANO_OK;
   const size_t smem = tc_smem_bytes();
-  static bool attr_set = false;
-  if (!attr_set) {
+  // function attributes are per DEVICE: one process may hold contexts on several GPUs
+  if (!ctx->attr_tc) {
     PANO_CUDA(ctx, cudaFuncSetAttribute(k_tc_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PANO_CUDA(ctx, cudaFuncSetAttribute(k_tc_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    ctx->attr_tc = true;
   }
   PANO_LAUNCH(ctx, "k_tc_top2", k_tc_pass<false>, n_tasks, TC_THREADS, smem, ops->qbuf, ops->tbuf, d_tasks,
               (const int*)nullptr, ops->d_maxnorm, d_res, (const int*)nullptr, (int*)nullptr, (int*)nullptr);

@@ -10,6 +10,7 @@
 #include <math.h>
 #include <string.h>
 #include <algorithm>
+#include <cuda.h>   // CUtensorMap types only: the encoder is looked up at run time
 
 // ============================================================ K1a working resize
 // lib/imgproc.cc:22-80 resize_bilinear; the reference's per-row/col tables are
@@ -68,14 +69,7 @@ __global__ void k_octave_grey(const ImgMeta* __restrict__ imgs, const OctMeta* _
     v1 = rx * (p1[4] * ry + p1[1] * iry) + irx * (p0[4] * ry + p0[1] * iry);
     v2 = rx * (p1[5] * ry + p1[2] * iry) + irx * (p0[5] * ry + p0[2] * iry);
   }
-  arena[om.gauss_off + (size_t)r * om.w + c] = (v0 + v1 + v2) / 3.f;
-}
-
-// Tile table of the blur launch, built on the device from the octave table (one entry per
-// CTA: octave entry, tile x, tile y) so that it never crosses PCIe.
-__global__ void k_make_tiles(const int2* __restrict__ span, int n_om, int n_tiles, BlurTile* __restrict__ tiles) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < n_tiles) tiles[t] = find_blur_tile(span, n_om, t);
+  arena[om.gauss_off + (size_t)r * om.pitch + c] = (v0 + v1 + v2) / 3.f;
 }
 
 // ============================================================ K2 blur + |DoG|
@@ -88,10 +82,10 @@ __global__ void k_make_tiles(const int2* __restrict__ span, int n_om, int n_tile
 #define BT_THREADS 256
 
 __global__ void __launch_bounds__(BT_THREADS)
-k_blur_dog(const OctMeta* __restrict__ octs, const BlurTile* __restrict__ tiles,
+k_blur_dog(const OctMeta* __restrict__ octs, const int2* __restrict__ span, int n_om,
            float* __restrict__ arena, const __grid_constant__ GaussTable gt) {
   extern __shared__ float smem[];
-  const BlurTile tl = tiles[blockIdx.x];
+  const BlurTile tl = find_blur_tile(span, n_om, blockIdx.x);
   const OctMeta om = octs[tl.om];
   const int R = gt.rmax;
   const int GW = BT_W + 2 * R;           // grey tile width
@@ -106,7 +100,7 @@ k_blur_dog(const OctMeta* __restrict__ octs, const BlurTile* __restrict__ tiles,
     int yy = i / GW, xx = i - yy * GW;
     int gy = min(max(y0 + yy - R, 0), om.h - 1);
     int gx = min(max(x0 + xx - R, 0), om.w - 1);
-    grey[i] = __ldg(g0 + (size_t)gy * om.w + gx);
+    grey[i] = __ldg(g0 + (size_t)gy * om.pitch + gx);
   }
   __syncthreads();
 
@@ -139,7 +133,7 @@ k_blur_dog(const OctMeta* __restrict__ octs, const BlurTile* __restrict__ tiles,
       for (int k = 0; k <= 2 * c; ++k) tmp += row[k] * taps[k];
       int gx = x0 + tx, gy = y0 + y;
       if (gx < om.w && gy < om.h) {
-        size_t o = (size_t)gy * om.w + gx;
+        size_t o = (size_t)gy * om.pitch + gx;
         lvl[o] = tmp;
         dog[o] = fabsf(prev[i] - tmp);
       }
@@ -200,51 +194,117 @@ __device__ __forceinline__ void blur_level(const float* __restrict__ grey, float
   __syncthreads();
 }
 
+// ---- TMA / mbarrier helpers (tile loads of the blur kernel)
+__device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void sbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sbar_wait(uint32_t bar, uint32_t parity) {   // bounded: a protocol bug traps
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+// 2-D tiled TMA load (cp.async.bulk.tensor): box origin (cx, cy) may lie outside the tensor,
+// out-of-range elements arrive as zeros.  The descriptor lives in global memory (written by
+// an earlier kernel of this stream), hence the tensormap-proxy acquire fence.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const TmaDesc* map, int cx, int cy, uint32_t bar) {
+  asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(map) : "memory");
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(cx), "r"(cy), "r"(bar) : "memory");
+}
+
+// The reference's defaults (kw = 7 and 13).  PERSISTENT CTAs walk the tile list; the grey
+// tile + halo of the NEXT tile is fetched by TMA into the other half of a double buffer
+// while this tile's six levels are computed.  TMA zero-fills outside the plane where the
+// reference replicates the edge (gaussian.hh:52-58,74-81), so tiles that touch the plane
+// border patch their out-of-range cells from the staged in-range ones (the replicated source
+// cell is always inside the same staged tile).
 __global__ void __launch_bounds__(BT_THREADS, 3)
-k_blur_dog_fast(const OctMeta* __restrict__ octs, const BlurTile* __restrict__ tiles,
-                float* __restrict__ arena, const __grid_constant__ GaussTable gt) {
-  extern __shared__ float smem[];
-  const BlurTile tl = tiles[blockIdx.x];
-  const OctMeta om = octs[tl.om];
+k_blur_dog_fast(const OctMeta* __restrict__ octs, const int2* __restrict__ span, int n_om, int n_tiles,
+                const TmaDesc* __restrict__ maps, float* __restrict__ arena, const __grid_constant__ GaussTable gt) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t s_bar[2];
   const int R = gt.rmax;
   const int GW = BT_W + 2 * R, GH = BT_H + 2 * R;
+  const int GSZ = (GH * GW + 31) & ~31;  // floats per grey buffer, 128-byte multiple
   const int CS = GW | 1;                 // odd stride: row-pass lanes (rows) hit distinct banks
-  float* grey = smem;                    // [GH][GW]
-  float* colbuf = grey + GH * GW;        // [BT_H][CS]
+  float* grey0 = smem;                   // [2][GH][GW]
+  float* colbuf = smem + 2 * GSZ;        // [BT_H][CS]
   float* outT = colbuf + BT_H * CS;      // [BT_H][BT_W+1]
-  const int x0 = tl.tx * BT_W, y0 = tl.ty * BT_H;
-  const float* g0 = arena + om.gauss_off;
   const int tid = threadIdx.x;
-  for (int i = tid; i < GH * GW; i += BT_THREADS) {
-    int yy = i / GW, xx = i - yy * GW;
-    int gy = min(max(y0 + yy - R, 0), om.h - 1);
-    int gx = min(max(x0 + xx - R, 0), om.w - 1);
-    grey[i] = __ldg(g0 + (size_t)gy * om.w + gx);
+  const uint32_t tile_bytes = (uint32_t)(GH * GW * sizeof(float));
+  if (tid == 0) {
+    sbar_init(sm_u32(&s_bar[0]), 1);
+    sbar_init(sm_u32(&s_bar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const int tx = tid & (BT_W - 1), ty = tid / BT_W;   // 64 x 4
-  const int gx = x0 + tx;
-  float prev[BT_H / 4];
-#pragma unroll
-  for (int i = 0; i < BT_H / 4; ++i) prev[i] = grey[(ty + 4 * i + R) * GW + tx + R];
-  for (int s = 0; s < gt.nlev; ++s) {
-    if (gt.center[s] == 3) blur_level<3>(grey, colbuf, outT, gt.taps[s], R, GW, CS, tid);
-    else blur_level<6>(grey, colbuf, outT, gt.taps[s], R, GW, CS, tid);
-    float* lvl = arena + om.gauss_off + (size_t)(s + 1) * om.plane;
-    float* dog = arena + om.dog_off + (size_t)s * om.plane;
-#pragma unroll
-    for (int i = 0; i < BT_H / 4; ++i) {
-      const int y = ty + 4 * i, gy = y0 + y;
-      const float v = outT[y * (BT_W + 1) + tx];
-      if (gx < om.w && gy < om.h) {
-        size_t o = (size_t)gy * om.w + gx;
-        lvl[o] = v;
-        dog[o] = fabsf(prev[i] - v);
-      }
-      prev[i] = v;
+  int t = blockIdx.x;
+  if (tid == 0 && t < n_tiles) {
+    const BlurTile tl = find_blur_tile(span, n_om, t);
+    sbar_expect_tx(sm_u32(&s_bar[0]), tile_bytes);
+    tma_load_2d(sm_u32(grey0), maps + tl.om, tl.tx * BT_W - R, tl.ty * BT_H - R, sm_u32(&s_bar[0]));
+  }
+  for (int it = 0; t < n_tiles; t += gridDim.x, ++it) {
+    const int b = it & 1;
+    float* grey = grey0 + b * GSZ;
+    const BlurTile tl = find_blur_tile(span, n_om, t);
+    const OctMeta om = octs[tl.om];
+    const int x0 = tl.tx * BT_W, y0 = tl.ty * BT_H;
+    if (tid == 0 && t + (int)gridDim.x < n_tiles) {
+      // the other buffer was last read (and patched) in the previous iteration, which every
+      // thread has left through the barrier at the end of the loop body
+      const BlurTile nx = find_blur_tile(span, n_om, t + gridDim.x);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      sbar_expect_tx(sm_u32(&s_bar[b ^ 1]), tile_bytes);
+      tma_load_2d(sm_u32(grey0 + (b ^ 1) * GSZ), maps + nx.om, nx.tx * BT_W - R, nx.ty * BT_H - R, sm_u32(&s_bar[b ^ 1]));
     }
-    // no barrier needed here: the next level's column pass touches only grey/colbuf
-    // and its row pass (which rewrites outT) sits behind that pass's barrier
+    sbar_wait(sm_u32(&s_bar[b]), (uint32_t)(it >> 1) & 1u);
+    if (x0 - R < 0 || y0 - R < 0 || x0 + BT_W + R > om.w || y0 + BT_H + R > om.h) {   // uniform per CTA
+      for (int i = tid; i < GH * GW; i += BT_THREADS) {
+        const int yy = i / GW, xx = i - yy * GW;
+        const int gy = y0 + yy - R, gx = x0 + xx - R;
+        const int cy = min(max(gy, 0), om.h - 1), cx = min(max(gx, 0), om.w - 1);
+        if (cy != gy || cx != gx) grey[i] = grey[(cy - y0 + R) * GW + (cx - x0 + R)];
+      }
+      __syncthreads();
+    }
+    const int tx = tid & (BT_W - 1), ty = tid / BT_W;   // 64 x 4
+    const int gx = x0 + tx;
+    float prev[BT_H / 4];
+#pragma unroll
+    for (int i = 0; i < BT_H / 4; ++i) prev[i] = grey[(ty + 4 * i + R) * GW + tx + R];
+    for (int s = 0; s < gt.nlev; ++s) {
+      if (gt.center[s] == 3) blur_level<3>(grey, colbuf, outT, gt.taps[s], R, GW, CS, tid);
+      else blur_level<6>(grey, colbuf, outT, gt.taps[s], R, GW, CS, tid);
+      float* lvl = arena + om.gauss_off + (size_t)(s + 1) * om.plane;
+      float* dog = arena + om.dog_off + (size_t)s * om.plane;
+#pragma unroll
+      for (int i = 0; i < BT_H / 4; ++i) {
+        const int y = ty + 4 * i, gy = y0 + y;
+        const float v = outT[y * (BT_W + 1) + tx];
+        if (gx < om.w && gy < om.h) {
+          size_t o = (size_t)gy * om.pitch + gx;
+          lvl[o] = v;
+          dog[o] = fabsf(prev[i] - v);
+        }
+        prev[i] = v;
+      }
+      // no barrier needed here: the next level's column pass touches only grey/colbuf
+      // and its row pass (which rewrites outT) sits behind that pass's barrier
+    }
+    __syncthreads();   // colbuf / outT / this grey buffer are free for the next tiles
   }
 }
 
@@ -260,13 +320,15 @@ __device__ __forceinline__ uint32_t make_key(int oct, int scale, int y, int x) {
 
 __global__ void __launch_bounds__(256)
 k_extrema_scan(const OctMeta* __restrict__ octs, const float* __restrict__ arena,
-               int nscale, float pre_color_thres, float diff_thres,
+               int nscale, float pre_color_thres, float diff_thres, int cap,
                int* __restrict__ cand_count, uint32_t* __restrict__ cand_keys) {
   const OctMeta om = octs[blockIdx.z];
-  const int c = blockIdx.x * 32 + threadIdx.x + 1;
+  // column c = lane of a 128-byte aligned row segment (rows are pitched to 32 floats)
+  const int c = blockIdx.x * 32 + threadIdx.x;
   const int r0 = blockIdx.y * (8 * EX_ROWS) + threadIdx.y + 1;
-  if (c >= om.w - 1 || r0 >= om.h - 1) return;
+  if (c < 1 || c >= om.w - 1 || r0 >= om.h - 1) return;
   const float* dog = arena + om.dog_off;
+  const int pitch = om.pitch;
   // The scan is one dependent load per level for almost every pixel (the centre fails
   // the colour threshold): fetch the centres of EX_ROWS rows x EX_LEV levels together
   // so that 16 loads are in flight per thread, then test.
@@ -278,13 +340,13 @@ k_extrema_scan(const OctMeta* __restrict__ octs, const float* __restrict__ arena
 #pragma unroll
       for (int l = 0; l < EX_LEV; ++l) {
         const int j = j0 + l;
-        cen[i][l] = (r < om.h - 1 && j < nscale - 2) ? __ldg(dog + (size_t)j * om.plane + (size_t)r * om.w + c) : -1.f;
+        cen[i][l] = (r < om.h - 1 && j < nscale - 2) ? __ldg(dog + (size_t)j * om.plane + (size_t)r * pitch + c) : -1.f;
       }
     }
 #pragma unroll
     for (int i = 0; i < EX_ROWS; ++i) {
       const int r = r0 + 8 * i;
-      const size_t o = (size_t)r * om.w + c;
+      const size_t o = (size_t)r * pitch + c;
 #pragma unroll
       for (int l = 0; l < EX_LEV; ++l) {
         const float center = cen[i][l];
@@ -301,14 +363,14 @@ k_extrema_scan(const OctMeta* __restrict__ octs, const float* __restrict__ arena
 #pragma unroll
             for (int dj = -1; dj <= 1; ++dj) {
               if (ds == 0 && di == 0 && dj == 0) continue;
-              float v = __ldg(pl + o + (ptrdiff_t)di * om.w + dj);
+              float v = __ldg(pl + o + (ptrdiff_t)di * pitch + dj);
               if (v >= cmp1) mx = false;
               if (v <= cmp2) mn = false;
             }
         }
         if (mx || mn) {
           int slot = atomicAdd(&cand_count[om.img], 1);
-          if (slot < SIFT_CAND_CAP) cand_keys[(size_t)om.img * SIFT_CAND_CAP + slot] = make_key(om.oct, j, r, c);
+          if (slot < cap) cand_keys[(size_t)om.img * cap + slot] = make_key(om.oct, j, r, c);
         }
       }
     }
@@ -317,24 +379,27 @@ k_extrema_scan(const OctMeta* __restrict__ octs, const float* __restrict__ arena
 
 // ============================================================ K3b ordered compaction
 // Rank sort per image: keys are unique, rank = #keys smaller.
-__global__ void k_rank_sort(const int* __restrict__ cand_count, const uint32_t* __restrict__ keys,
-                            uint32_t* __restrict__ sorted) {
+__global__ void __launch_bounds__(256)
+k_rank_sort(const int* __restrict__ cand_count, const uint32_t* __restrict__ keys,
+            uint32_t* __restrict__ sorted, int cap) {
   __shared__ uint32_t sk[1024];
   const int img = blockIdx.y;
-  const int n = min(cand_count[img], SIFT_CAND_CAP);
-  const uint32_t* k = keys + (size_t)img * SIFT_CAND_CAP;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blockIdx.x * blockDim.x >= n) return;
-  uint32_t mine = i < n ? k[i] : 0xffffffffu;
-  int rank = 0;
-  for (int base = 0; base < n; base += 1024) {
-    int m = min(1024, n - base);
-    for (int t = threadIdx.x; t < m; t += blockDim.x) sk[t] = k[base + t];
-    __syncthreads();
-    for (int t = 0; t < m; ++t) rank += sk[t] < mine;
-    __syncthreads();
+  const int n = min(cand_count[img], cap);
+  const uint32_t* k = keys + (size_t)img * cap;
+  // the grid is sized for a typical count; CTAs stride over the 256-key chunks of the real one
+  for (int c0 = blockIdx.x * 256; c0 < n; c0 += gridDim.x * 256) {
+    const int i = c0 + threadIdx.x;
+    uint32_t mine = i < n ? k[i] : 0xffffffffu;
+    int rank = 0;
+    for (int base = 0; base < n; base += 1024) {
+      int m = min(1024, n - base);
+      __syncthreads();
+      for (int t = threadIdx.x; t < m; t += blockDim.x) sk[t] = k[base + t];
+      __syncthreads();
+      for (int t = 0; t < m; ++t) rank += sk[t] < mine;
+    }
+    if (i < n) sorted[(size_t)img * cap + rank] = mine;
   }
-  if (i < n) sorted[(size_t)img * SIFT_CAND_CAP + rank] = mine;
 }
 
 // ============================================================ K4 refinement
@@ -437,18 +502,17 @@ struct RefineParams {
 // feature/extrema.cc:63-168: calc_kp_offset(+_iter) and is_edge_response.
 __global__ void k_refine(const OctMeta* __restrict__ octs, const float* __restrict__ arena, int n_oct,
                          const int* __restrict__ cand_count, const uint32_t* __restrict__ sorted,
-                         RefineParams rp, pano_sspoint* __restrict__ out, unsigned char* __restrict__ valid) {
+                         RefineParams rp, int cap, pano_sspoint* __restrict__ out, unsigned char* __restrict__ valid) {
   const int img = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = min(cand_count[img], SIFT_CAND_CAP);
-  if (i >= n) return;
-  const size_t slot = (size_t)img * SIFT_CAND_CAP + i;
+  const int n = min(cand_count[img], cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const size_t slot = (size_t)img * cap + i;
   uint32_t key = sorted[slot];
   int oct = key >> 29, s0 = (key >> 26) & 7, y0 = (key >> 13) & 8191, x0 = key & 8191;
   const OctMeta om = octs[img * n_oct + oct];
   const float* dog = arena + om.dog_off;
   const int w = om.w, h = om.h;
-#define DG(xx, yy, ss) __ldg(dog + (size_t)(ss) * om.plane + (size_t)(yy) * w + (xx))
+#define DG(xx, yy, ss) __ldg(dog + (size_t)(ss) * om.plane + (size_t)(yy) * om.pitch + (xx))
   pano_sspoint sp;
   sp.x = x0; sp.y = y0; sp.pyr_id = oct; sp.scale_id = s0;
   sp.real_x = 0; sp.real_y = 0; sp.dir = 0; sp.scale_factor = 0;
@@ -513,6 +577,7 @@ __global__ void k_refine(const OctMeta* __restrict__ octs, const float* __restri
 #undef DG
   out[slot] = sp;
   valid[slot] = ok ? 1 : 0;
+  }
 }
 
 // ============================================================ K5 orientation
@@ -524,24 +589,40 @@ __global__ void k_refine(const OctMeta* __restrict__ octs, const float* __restri
 #define ORI_CHUNK 256
 #define ORI_WARPS 4
 
+#define SIFT_MAX_IMG 512                // images per SIFT batch (prefix tables in shared memory)
+
 __global__ void __launch_bounds__(ORI_WARPS * 32)
-k_orientation(const OctMeta* __restrict__ octs, const float* __restrict__ arena, int n_oct,
+k_orientation(const OctMeta* __restrict__ octs, const float* __restrict__ arena, int n_oct, int n_img, int cap,
               const int* __restrict__ cand_count, const pano_sspoint* __restrict__ pts,
               const unsigned char* __restrict__ valid, float ori_radius, int smooth_count,
-              int* __restrict__ npeaks, float* __restrict__ dirs) {
+              int* __restrict__ npeaks, float* __restrict__ dirs, int* __restrict__ work_counter) {
   __shared__ signed char s_bin[ORI_WARPS][ORI_CHUNK];
   __shared__ float s_val[ORI_WARPS][ORI_CHUNK];
   __shared__ float s_hist[ORI_WARPS][ORI_BINS + 4];
   __shared__ uint64_t s_exptab[32];
+  __shared__ int s_pref[SIFT_MAX_IMG + 1];      // first flat index of each image's candidates
   load_exp2f_tab(s_exptab, threadIdx.x);
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < n_img; ++i) { s_pref[i] = acc; acc += min(cand_count[i], cap); }
+    s_pref[n_img] = acc;
+  }
   __syncthreads();
-  const int img = blockIdx.y;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * ORI_WARPS + wid;
-  const int n = min(cand_count[img], SIFT_CAND_CAP);
-  if (i >= n) return;
-  const size_t slot = (size_t)img * SIFT_CAND_CAP + i;
-  if (!valid[slot]) { if (lane == 0) npeaks[slot] = 0; return; }
+  const int total_work = s_pref[n_img];
+  int img = 0;
+  // Candidates are handed out one at a time from a global counter (most of them were
+  // rejected by the refinement and cost nothing; the grid is a few CTAs per SM, not one
+  // warp per capacity slot).
+  while (true) {
+  int flat = 0;
+  if (lane == 0) flat = atomicAdd(work_counter, 1);
+  flat = __shfl_sync(0xffffffffu, flat, 0);
+  if (flat >= total_work) break;
+  while (flat >= s_pref[img + 1]) ++img;
+  const int i = flat - s_pref[img];
+  const size_t slot = (size_t)img * cap + i;
+  if (!valid[slot]) { if (lane == 0) npeaks[slot] = 0; continue; }
   const pano_sspoint p = pts[slot];
   const OctMeta om = octs[img * n_oct + p.pyr_id];
   const float* lvl = arena + om.gauss_off + (size_t)p.scale_id * om.plane;
@@ -564,7 +645,7 @@ k_orientation(const OctMeta* __restrict__ octs, const float* __restrict__ arena,
         float d2 = fx * fx + fy * fy;
         if (!(d2 > fr * fr)) {
           float mag, ort;
-          mag_ort_at(lvl, om.w, newx, newy, &mag, &ort);
+          mag_ort_at(lvl, om.pitch, newx, newy, &mag, &ort);
           int b = (int)roundf((float)ORI_BINS * halfipi * ort);
           if (b == ORI_BINS) b = 0;
           float weight = glibc_expf(-d2 / exp_denom, s_exptab);
@@ -626,6 +707,8 @@ k_orientation(const OctMeta* __restrict__ octs, const float* __restrict__ arena,
     count += __popc(mask);
   }
   if (lane == 0) npeaks[slot] = min(count, SIFT_MAX_PEAKS);
+  __syncwarp();
+  }
 }
 
 // ============================================================ K5b expansion scan
@@ -634,16 +717,16 @@ k_orientation(const OctMeta* __restrict__ octs, const float* __restrict__ arena,
 #define SCAN_THREADS 1024
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_expand_scan(const int* __restrict__ cand_count, const unsigned char* __restrict__ valid,
-              const int* __restrict__ npeaks, const float* __restrict__ dirs,
+              const int* __restrict__ npeaks, const float* __restrict__ dirs, int cap,
               int* __restrict__ n_desc, int* __restrict__ n_refined,
               int* __restrict__ desc_cand, float* __restrict__ desc_dir) {
   __shared__ int s_warp[32];
   __shared__ int s_warp2[32];
   const int img = blockIdx.x;
-  const int n = min(cand_count[img], SIFT_CAND_CAP);
-  const int per = (SIFT_CAND_CAP + SCAN_THREADS - 1) / SCAN_THREADS;
+  const int n = min(cand_count[img], cap);
+  const int per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const size_t base = (size_t)img * SIFT_CAND_CAP;
+  const size_t base = (size_t)img * cap;
   int local = 0, nval = 0;
   for (int k = 0; k < per; ++k) {
     int i = tid * per + k;
@@ -676,9 +759,9 @@ k_expand_scan(const int* __restrict__ cand_count, const unsigned char* __restric
       int np = npeaks[base + i];
       for (int q = 0; q < np; ++q) {
         int d = off + q;
-        if (d < SIFT_DESC_CAP) {
-          desc_cand[(size_t)img * SIFT_DESC_CAP + d] = i;
-          desc_dir[(size_t)img * SIFT_DESC_CAP + d] = dirs[(base + i) * SIFT_MAX_PEAKS + q];
+        if (d < cap) {
+          desc_cand[(size_t)img * cap + d] = i;
+          desc_dir[(size_t)img * cap + d] = dirs[(base + i) * SIFT_MAX_PEAKS + q];
         }
       }
       off += np;
@@ -709,7 +792,7 @@ k_expand_scan(const int* __restrict__ cand_count, const unsigned char* __restric
 #endif
 #define DESC_CHUNKS (DESC_REC_CAP / 32)
 #define DESC_SKIP 0xffffffffu
-#define DESC_MAX_IMG 512               // images per SIFT batch (prefix table in shared memory)
+#define DESC_MAX_IMG SIFT_MAX_IMG
 #ifndef DESC_CTAS_PER_SM
 #define DESC_CTAS_PER_SM 6
 #endif
@@ -726,7 +809,7 @@ struct __align__(16) DescWarpSmem {
 
 __global__ void __launch_bounds__(DESC_THREADS)
 k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
-             const float* __restrict__ arena, int n_oct, int n_img,
+             const float* __restrict__ arena, int n_oct, int n_img, int cap,
              const pano_sspoint* __restrict__ pts, const int* __restrict__ n_desc,
              const int* __restrict__ desc_cand, const float* __restrict__ desc_dir,
              DescParams dp, float* __restrict__ out_desc, double* __restrict__ out_coor,
@@ -737,7 +820,7 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
   load_exp2f_tab(s_exptab, threadIdx.x);
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int i = 0; i < n_img; ++i) { s_pref[i] = acc; acc += min(n_desc[i], SIFT_DESC_CAP); }
+    for (int i = 0; i < n_img; ++i) { s_pref[i] = acc; acc += min(n_desc[i], cap); }
     s_pref[n_img] = acc;
   }
   __syncthreads();
@@ -763,8 +846,8 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
       while (flat >= s_pref[img + 1]) ++img;          // indices only grow: resume from the last image
       const int d = flat - s_pref[img];
       const ImgMeta im = imgs[img];
-      const size_t dslot = (size_t)img * SIFT_DESC_CAP + d;
-      const pano_sspoint p = pts[(size_t)img * SIFT_CAND_CAP + desc_cand[dslot]];
+      const size_t dslot = (size_t)img * cap + d;
+      const pano_sspoint p = pts[(size_t)img * cap + desc_cand[dslot]];
       const float ort = desc_dir[dslot];
       const OctMeta om = octs[img * n_oct + p.pyr_id];
       const float* lvl = arena + om.gauss_off + (size_t)p.scale_id * om.plane;
@@ -834,7 +917,7 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
           const float xbin = (float)((double)(x_rot + 2.f) - 0.5);
           if (ybin >= -1.f && ybin <= 3.f && xbin >= -1.f && xbin <= 3.f) {
             float now_mag, now_ort;
-            mag_ort_at(lvl, w, p.x + xx, p.y + yy, &now_mag, &now_ort);
+            mag_ort_at(lvl, om.pitch, p.x + xx, p.y + yy, &now_mag, &now_ort);
             float weight = glibc_expf(-(x_rot * x_rot + y_rot * y_rot) / exp_denom, s_exptab);
             weight = weight * now_mag;
             now_ort -= ort;
@@ -956,7 +1039,7 @@ int host_gauss_kernel(float sigma, int window_factor, float* taps, int cap) {
 
 void sift_work_free(pano_ctx* ctx, SiftWork* wk) {
   if (!wk) return;
-  ctx_free(ctx, wk->arena); ctx_free(ctx, wk->d_img); ctx_free(ctx, wk->d_oct); ctx_free(ctx, wk->d_tiles); ctx_free(ctx, wk->d_tilespan);
+  ctx_free(ctx, wk->arena); ctx_free(ctx, wk->d_img); ctx_free(ctx, wk->d_oct); ctx_free(ctx, wk->d_maps); ctx_free(ctx, wk->d_tilespan);
   ctx_free(ctx, wk->cand_count); ctx_free(ctx, wk->cand_keys); ctx_free(ctx, wk->sorted_keys);
   ctx_free(ctx, wk->refined); ctx_free(ctx, wk->kp_valid); ctx_free(ctx, wk->npeaks);
   ctx_free(ctx, wk->dirs); ctx_free(ctx, wk->n_refined);
@@ -964,16 +1047,45 @@ void sift_work_free(pano_ctx* ctx, SiftWork* wk) {
   delete wk;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup: the library links
+// cudart statically and has no link-time dependency on libcuda.
+typedef CUresult (*tma_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int ctx_tma_encode(pano_ctx* ctx, TmaDesc* out, void* base, int rank, const unsigned long long* dims,
+                   const unsigned long long* strides_bytes, const unsigned* box) {
+  if (!ctx->tma_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+      return ctx_fail(ctx, PANO_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    ctx->tma_encode = fn;
+  }
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  static_assert(sizeof(TmaDesc) == sizeof(CUtensorMap), "CUtensorMap is 128 bytes");
+  CUresult r = ((tma_encode_fn)ctx->tma_encode)((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, gd,
+                                                gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return ctx_fail(ctx, PANO_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return PANO_OK;
+}
+
 int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w, const int* h,
-                   const pano_params* p, pano_featureset* fs, SiftWork** keep) {
+                   const pano_params* p, pano_featureset* fs, SiftWork** keep, int cap) {
   if (n <= 0 || !d_src || !w || !h || !p || !fs) return ctx_fail(ctx, PANO_ERR_INVALID, "sift: bad argument");
-  if (n > DESC_MAX_IMG) return ctx_fail(ctx, PANO_ERR_INVALID, "sift: %d images in one batch (limit %d): split the batch", n, DESC_MAX_IMG);
+  if (n > SIFT_MAX_IMG) return ctx_fail(ctx, PANO_ERR_INVALID, "sift: %d images in one batch (limit %d): split the batch", n, SIFT_MAX_IMG);
   const int n_oct = p->num_octave, n_scale = p->num_scale;
   if (n_oct < 1 || n_oct > SIFT_MAX_OCT || n_scale < 4 || n_scale - 1 > SIFT_MAX_LEVELS || n_scale - 2 > 7)
     return ctx_fail(ctx, PANO_ERR_INVALID, "sift: NUM_OCTAVE/NUM_SCALE out of supported range");
+  if (cap < 256 || cap > SIFT_CAP_MAX) return ctx_fail(ctx, PANO_ERR_INVALID, "sift: list capacity %d out of range", cap);
 
   SiftWork* wk = new SiftWork;
-  wk->n_img = n; wk->n_oct = n_oct; wk->n_scale = n_scale;
+  wk->n_img = n; wk->n_oct = n_oct; wk->n_scale = n_scale; wk->cap = cap;
   wk->h_img.resize(n);
   wk->h_oct.resize((size_t)n * n_oct);
   size_t off = 0;
@@ -1006,7 +1118,8 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
         float ofx = (float)om.h / im.h0, ofy = (float)om.w / im.w0;
         om.ifx = 1.f / ofx; om.ify = 1.f / ofy;
       }
-      om.plane = (long long)align_up((size_t)om.w * om.h, 32);
+      om.pitch = (int)align_up((size_t)om.w, 32);
+      om.plane = (long long)om.pitch * om.h;
       om.gauss_off = (long long)off; off += (size_t)om.plane * n_scale;
       om.dog_off = (long long)off; off += (size_t)om.plane * (n_scale - 1);
       tilespan[(size_t)i * n_oct + o] = make_int2(n_tiles, ceil_div(om.w, BT_W));
@@ -1029,42 +1142,58 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
       sigma *= p->scale_factor;
     }
   }
+  bool fast = true;
+  for (int s = 0; s < gt.nlev; ++s) fast = fast && (gt.center[s] == 3 || gt.center[s] == 6);
 
 #define SIFT_TRY(call) do { int _rc = (call); if (_rc != 0) { sift_work_free(ctx, wk); return _rc; } } while (0)
 #define SIFT_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { int _rc = ctx_cuda(ctx, _e, #call); sift_work_free(ctx, wk); return _rc; } } while (0)
 
-  const size_t ncand = (size_t)n * SIFT_CAND_CAP, ndesc = (size_t)n * SIFT_DESC_CAP;
+  const size_t nlist = (size_t)n * cap;
+  const int n_om = n * n_oct;
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->arena, off * sizeof(float)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_img, n * sizeof(ImgMeta)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_oct, wk->h_oct.size() * sizeof(OctMeta)));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_tiles, (size_t)std::max(n_tiles, 1) * sizeof(BlurTile)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_maps, (size_t)n_om * sizeof(TmaDesc)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->d_tilespan, tilespan.size() * sizeof(int2)));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->cand_count, (n + 1) * sizeof(int)));   // [n] = descriptor work counter
-  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->cand_keys, ncand * sizeof(uint32_t)));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->sorted_keys, ncand * sizeof(uint32_t)));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->refined, ncand * sizeof(pano_sspoint)));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->kp_valid, ncand));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->npeaks, ncand * sizeof(int)));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->dirs, ncand * SIFT_MAX_PEAKS * sizeof(float)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->cand_count, (n + 2) * sizeof(int)));   // [n], [n+1] = work counters
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->cand_keys, nlist * sizeof(uint32_t)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->sorted_keys, nlist * sizeof(uint32_t)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->refined, nlist * sizeof(pano_sspoint)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->kp_valid, nlist));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->npeaks, nlist * sizeof(int)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->dirs, nlist * SIFT_MAX_PEAKS * sizeof(float)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->n_refined, n * sizeof(int)));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->desc_cand, ndesc * sizeof(int)));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->desc_dir, ndesc * sizeof(float)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->desc_cand, nlist * sizeof(int)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->desc_dir, nlist * sizeof(float)));
 
-  // featureset outputs (fixed per-image capacity; compact on download)
-  fs->ctx = ctx; fs->n_images = n;
-  SIFT_TRY(ctx_alloc(ctx, (void**)&fs->d_desc, ndesc * 128 * sizeof(float)));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&fs->d_coor, ndesc * 2 * sizeof(double)));
+  // featureset outputs (per-image capacity `cap`; compact on download)
+  fs->ctx = ctx; fs->n_images = n; fs->cap = cap;
+  SIFT_TRY(ctx_alloc(ctx, (void**)&fs->d_desc, nlist * 128 * sizeof(float)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&fs->d_coor, nlist * 2 * sizeof(double)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&fs->d_count, n * sizeof(int)));
   fs->base.resize(n);
-  for (int i = 0; i < n; ++i) fs->base[i] = (long long)i * SIFT_DESC_CAP;
+  for (int i = 0; i < n; ++i) fs->base[i] = (long long)i * cap;
 
-  // metadata upload + candidate-counter reset: one launch through the pinned ring
+  // metadata upload + counter reset: one launch through the pinned ring
   {
     void* dsts[4] = {wk->d_img, wk->d_oct, wk->d_tilespan, wk->cand_count};
     const void* srcs[4] = {wk->h_img.data(), wk->h_oct.data(), tilespan.data(), nullptr};
     size_t sizes[4] = {n * sizeof(ImgMeta), wk->h_oct.size() * sizeof(OctMeta), tilespan.size() * sizeof(int2),
-                       (n + 1) * sizeof(int)};
+                       (n + 2) * sizeof(int)};
     SIFT_TRY(ctx_put_many(ctx, 4, dsts, srcs, sizes));
+  }
+  if (fast) {
+    // one TMA descriptor per grey plane: f32 tensor (w, h), row stride pitch*4, box = tile + halo
+    std::vector<TmaDesc> maps(n_om);
+    const int R = gt.rmax;
+    for (int k = 0; k < n_om; ++k) {
+      const OctMeta& om = wk->h_oct[k];
+      unsigned long long dims[2] = {(unsigned long long)om.w, (unsigned long long)om.h};
+      unsigned long long strides[1] = {(unsigned long long)om.pitch * sizeof(float)};
+      unsigned box[2] = {(unsigned)(BT_W + 2 * R), (unsigned)(BT_H + 2 * R)};
+      SIFT_TRY(ctx_tma_encode(ctx, &maps[k], wk->arena + om.gauss_off, 2, dims, strides, box));
+    }
+    SIFT_TRY(ctx_put(ctx, wk->d_maps, maps.data(), maps.size() * sizeof(TmaDesc)));
   }
 
 #define SIFT_LAUNCH(name, kernel, grid, block, smem, ...)                                   \
@@ -1082,46 +1211,49 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     dim3 g2(ceil_div(max_w0, 32), ceil_div(max_h0, 8), n * n_oct);
     SIFT_LAUNCH("k_octave_grey", k_octave_grey, g2, b, 0, wk->d_img, wk->d_oct, wk->arena);
   }
-  SIFT_LAUNCH("k_make_tiles", k_make_tiles, ceil_div(wk->n_tiles, 256), 256, 0, wk->d_tilespan, n * n_oct, wk->n_tiles, wk->d_tiles);
   {
     const int R = gt.rmax;
     size_t smem = ((size_t)(BT_H + 2 * R) * (BT_W + 2 * R) + (size_t)BT_H * (BT_W + 2 * R)) * sizeof(float);
     if (smem > 200 * 1024) { sift_work_free(ctx, wk); return ctx_fail(ctx, PANO_ERR_INVALID, "sift: blur halo too large"); }
-    bool fast = true;
-    for (int s = 0; s < gt.nlev; ++s) fast = fast && (gt.center[s] == 3 || gt.center[s] == 6);
     if (fast) {
       const int GW = BT_W + 2 * R, GH = BT_H + 2 * R, CS = GW | 1;
-      size_t smf = ((size_t)GH * GW + (size_t)BT_H * CS + (size_t)BT_H * (BT_W + 1)) * sizeof(float);
-      SIFT_LAUNCH("k_blur_dog", k_blur_dog_fast, wk->n_tiles, BT_THREADS, smf, wk->d_oct, wk->d_tiles, wk->arena, gt);
+      const size_t gsz = ((size_t)GH * GW + 31) & ~(size_t)31;
+      size_t smf = (2 * gsz + (size_t)BT_H * CS + (size_t)BT_H * (BT_W + 1)) * sizeof(float);
+      SIFT_CUDA(cudaFuncSetAttribute(k_blur_dog_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
+      const int grid = std::min(wk->n_tiles, ctx->num_sms * 3);
+      SIFT_LAUNCH("k_blur_dog", k_blur_dog_fast, grid, BT_THREADS, smf, wk->d_oct, wk->d_tilespan, n_om, wk->n_tiles, wk->d_maps,
+                  wk->arena, gt);
     } else {
       if (smem > 48 * 1024)
         SIFT_CUDA(cudaFuncSetAttribute(k_blur_dog, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      SIFT_LAUNCH("k_blur_dog_generic", k_blur_dog, wk->n_tiles, BT_THREADS, smem, wk->d_oct, wk->d_tiles, wk->arena, gt);
+      SIFT_LAUNCH("k_blur_dog_generic", k_blur_dog, wk->n_tiles, BT_THREADS, smem, wk->d_oct, wk->d_tilespan, n_om, wk->arena, gt);
     }
   }
   {
-    dim3 b(32, 8), g(ceil_div(max_w0 - 2, 32), ceil_div(max_h0 - 2, 8 * EX_ROWS), n * n_oct);
+    dim3 b(32, 8), g(ceil_div(max_w0 - 1, 32), ceil_div(max_h0 - 2, 8 * EX_ROWS), n * n_oct);
     SIFT_LAUNCH("k_extrema_scan", k_extrema_scan, g, b, 0, wk->d_oct, wk->arena, n_scale, p->pre_color_thres,
-                p->judge_extrema_diff_thres, wk->cand_count, wk->cand_keys);
+                p->judge_extrema_diff_thres, cap, wk->cand_count, wk->cand_keys);
   }
   {
-    dim3 g(SIFT_CAND_CAP / 256, n);
-    SIFT_LAUNCH("k_rank_sort", k_rank_sort, g, 256, 0, wk->cand_count, wk->cand_keys, wk->sorted_keys);
+    // latency kernels: grids sized for typical counts (a few thousand candidates per image);
+    // they stride over the real device-side count, so nothing is launched per capacity slot
+    dim3 g(8, n);
+    SIFT_LAUNCH("k_rank_sort", k_rank_sort, g, 256, 0, wk->cand_count, wk->cand_keys, wk->sorted_keys, cap);
     RefineParams rp{n_scale, p->calc_offset_depth, p->offset_thres, p->contrast_thres, p->edge_ratio,
                     p->gauss_sigma, p->scale_factor};
-    dim3 g4(SIFT_CAND_CAP / 128, n);
-    SIFT_LAUNCH("k_refine", k_refine, g4, 128, 0, wk->d_oct, wk->arena, n_oct, wk->cand_count, wk->sorted_keys, rp,
+    dim3 g4(16, n);
+    SIFT_LAUNCH("k_refine", k_refine, g4, 128, 0, wk->d_oct, wk->arena, n_oct, wk->cand_count, wk->sorted_keys, rp, cap,
                 wk->refined, wk->kp_valid);
-    dim3 g5(SIFT_CAND_CAP / ORI_WARPS, n);
-    SIFT_LAUNCH("k_orientation", k_orientation, g5, ORI_WARPS * 32, 0, wk->d_oct, wk->arena, n_oct, wk->cand_count,
-                wk->refined, wk->kp_valid, p->ori_radius, p->ori_hist_smooth_count, wk->npeaks, wk->dirs);
+    SIFT_LAUNCH("k_orientation", k_orientation, ctx->num_sms * 8, ORI_WARPS * 32, 0, wk->d_oct, wk->arena, n_oct, n, cap,
+                wk->cand_count, wk->refined, wk->kp_valid, p->ori_radius, p->ori_hist_smooth_count, wk->npeaks, wk->dirs,
+                wk->cand_count + n + 1);
     SIFT_LAUNCH("k_expand_scan", k_expand_scan, n, SCAN_THREADS, 0, wk->cand_count, wk->kp_valid, wk->npeaks,
-                wk->dirs, fs->d_count, wk->n_refined, wk->desc_cand, wk->desc_dir);
+                wk->dirs, cap, fs->d_count, wk->n_refined, wk->desc_cand, wk->desc_dir);
     DescParams dp{p->desc_hist_scale_factor, p->desc_int_factor};
     const size_t dsm = sizeof(DescWarpSmem) * DESC_WARPS;
     SIFT_CUDA(cudaFuncSetAttribute(k_descriptor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
     int grid = ctx->num_sms * DESC_CTAS_PER_SM;
-    SIFT_LAUNCH("k_descriptor", k_descriptor, grid, DESC_THREADS, dsm, wk->d_oct, wk->d_img, wk->arena, n_oct, n,
+    SIFT_LAUNCH("k_descriptor", k_descriptor, grid, DESC_THREADS, dsm, wk->d_oct, wk->d_img, wk->arena, n_oct, n, cap,
                 wk->refined, fs->d_count, wk->desc_cand, wk->desc_dir, dp, fs->d_desc, fs->d_coor, wk->cand_count + n);
   }
   wk->n_desc = fs->d_count;
@@ -1146,22 +1278,38 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
   return PANO_OK;
 }
 
+// First consumer of a SIFT featureset: waits for the counts.  A list that overflowed its
+// capacity (the reference's vectors are unbounded, extrema.cc:56-57) makes the batch run
+// again with doubled lists — the sources are still there (pano_b200.h) — and the larger
+// capacity becomes this context's starting point.  A failure is sticky.
 int featureset_sync_counts(pano_featureset* fs) {
+  if (fs->error) return fs->error;
   if (fs->counts_on_host) return PANO_OK;
   pano_ctx* ctx = fs->ctx;
-  if (fs->counts_pending) {
-    PANO_CUDA(ctx, ctx_wait_signal(ctx, fs->counts_token));
+  while (fs->counts_pending) {
+    cudaError_t e = ctx_wait_signal(ctx, fs->counts_token);
+    if (e != cudaSuccess) return fs->error = ctx_cuda(ctx, e, "feature count read-back");
     fs->counts_pending = false;
-    fs->h_count.assign(fs->h_count_pinned, fs->h_count_pinned + fs->n_images);
-    for (int i = 0; i < fs->n_images; ++i) {
-      if (fs->h_count_pinned[fs->n_images + i] > SIFT_CAND_CAP)
-        return ctx_fail(ctx, PANO_ERR_CAPACITY, "image %d: %d raw extrema exceed capacity %d", i,
-                        fs->h_count_pinned[fs->n_images + i], SIFT_CAND_CAP);
-      if (fs->h_count[i] > SIFT_DESC_CAP)
-        return ctx_fail(ctx, PANO_ERR_CAPACITY, "image %d: %d descriptors exceed capacity %d", i, fs->h_count[i],
-                        SIFT_DESC_CAP);
+    const int n = fs->n_images;
+    int worst = 0;
+    for (int i = 0; i < n; ++i) worst = std::max(worst, std::max(fs->h_count_pinned[i], fs->h_count_pinned[n + i]));
+    if (worst <= fs->cap) {
+      fs->h_count.assign(fs->h_count_pinned, fs->h_count_pinned + n);
+      break;
     }
+    int cap = fs->cap;
+    while (cap < worst && cap < SIFT_CAP_MAX) cap *= 2;
+    if (cap < worst || fs->src.empty())
+      return fs->error = ctx_fail(ctx, PANO_ERR_CAPACITY, "sift: %d list entries in one image exceed the capacity %d", worst, fs->cap);
+    // run again with larger lists; the old outputs go back to the pool in stream order
+    ctx_free(ctx, fs->d_desc); ctx_free(ctx, fs->d_coor); ctx_free(ctx, fs->d_count);
+    fs->d_desc = nullptr; fs->d_coor = nullptr; fs->d_count = nullptr;
+    ctx->sift_cap = cap;
+    const std::vector<const float*> src = fs->src;
+    int rc = sift_run_batch(ctx, n, src.data(), fs->src_w.data(), fs->src_h.data(), &fs->src_params, fs, nullptr, cap);
+    if (rc) return fs->error = rc;
   }
+  if (fs->owned_block) { ctx_free(ctx, fs->owned_block); fs->owned_block = nullptr; }
   fs->counts_on_host = true;
   return PANO_OK;
 }

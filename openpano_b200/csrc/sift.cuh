@@ -6,8 +6,10 @@
 #define SIFT_MAX_OCT 8
 #define SIFT_MAX_LEVELS 8        // nscale-1 blurred levels
 #define SIFT_MAX_TAPS 32         // kw <= 31
-#define SIFT_CAND_CAP 8192       // raw extrema per image
-#define SIFT_DESC_CAP 8192       // descriptors per image
+#define SIFT_CAP_DEFAULT 8192    // raw extrema / descriptors per image a batch starts with; the
+                                 // capacity is a RUNTIME value that doubles on overflow (the reference's
+                                 // vectors are unbounded, extrema.cc:56-57): see featureset_sync_counts
+#define SIFT_CAP_MAX (1 << 20)
 #define SIFT_MAX_PEAKS 18        // a peak needs two lower neighbours: <= 36/2
 
 struct ImgMeta {
@@ -21,10 +23,12 @@ struct ImgMeta {
 struct OctMeta {
   int img, oct;
   int w, h;
+  int pitch;            // floats per plane row: w rounded up to 32, so rows start on 128-byte lines
+                        // (TMA needs 16-byte global strides; warps read / write whole lines)
   float ifx, ify;       // octave resize from the working image (oct > 0)
   long long gauss_off;  // nscale planes: grey + blurred levels
   long long dog_off;    // nscale-1 planes
-  long long plane;      // floats per plane (padded to 32)
+  long long plane;      // floats per plane = pitch * h
 };
 
 struct BlurTile { int om; int tx, ty; };
@@ -64,21 +68,22 @@ struct SiftWork {
   size_t arena_floats = 0;
   ImgMeta* d_img = nullptr;
   OctMeta* d_oct = nullptr;
-  BlurTile* d_tiles = nullptr;
   int2* d_tilespan = nullptr;
+  TmaDesc* d_maps = nullptr;      // [n_img * n_oct]
   int n_tiles = 0;
-  // keypoint state, all [n_img * SIFT_CAND_CAP] unless noted
-  int* cand_count = nullptr;      // [n_img]
+  int cap = SIFT_CAP_DEFAULT;     // per-image capacity of every candidate / descriptor list below
+  // keypoint state, all [n_img * cap] unless noted
+  int* cand_count = nullptr;      // [n_img] + work counters (see sift.cu)
   uint32_t* cand_keys = nullptr;
   uint32_t* sorted_keys = nullptr;
   pano_sspoint* refined = nullptr;  // valid flag in .dir < 0 ? no: see kp_valid
   unsigned char* kp_valid = nullptr;
   int* npeaks = nullptr;
-  float* dirs = nullptr;            // [n_img * CAP * SIFT_MAX_PEAKS]
+  float* dirs = nullptr;            // [n_img * cap * SIFT_MAX_PEAKS]
   int* n_desc = nullptr;            // [n_img]
   int* n_refined = nullptr;         // [n_img] (for traces)
-  int* desc_cand = nullptr;         // [n_img * DESC_CAP] candidate index of descriptor
-  float* desc_dir = nullptr;        // [n_img * DESC_CAP]
+  int* desc_cand = nullptr;         // [n_img * cap] candidate index of descriptor
+  float* desc_dir = nullptr;        // [n_img * cap]
 };
 
 struct pano_featureset {
@@ -97,9 +102,17 @@ struct pano_featureset {
   size_t h_count_cap = 0;
   TcOperands tc;              // fp16 tensor-core operands of the descriptors (lazy)
   bool tc_ready = false;
+  int error = 0;              // sticky failure of the count read-back (returned by every later use)
+  // What a capacity overflow needs to run the batch again with larger lists (SIFT sets only):
+  // the sources must stay valid until the counts have been read once (pano_b200.h).
+  int cap = 0;                          // per-image row capacity of d_desc / d_coor (0: not a SIFT set)
+  std::vector<const float*> src;        // device images
+  std::vector<int> src_w, src_h;
+  pano_params src_params;
+  float* owned_block = nullptr;         // staged upload of pano_sift_detect_batch, freed after the count sync
 };
 
 int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w, const int* h,
-                   const pano_params* p, pano_featureset* fs, SiftWork** keep);
+                   const pano_params* p, pano_featureset* fs, SiftWork** keep, int cap);
 void sift_work_free(pano_ctx* ctx, SiftWork* wk);
 int featureset_sync_counts(pano_featureset* fs);

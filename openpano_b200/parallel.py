@@ -164,19 +164,24 @@ class DistributedStitcher:
       SIFT      owned images (k mod G)                              no collective
       C1        descriptors + coordinates: export_dev -> ncclAllGather -> import_dev
       match     the dealt pair tasks against the gathered featureset  no collective
-      results   match lists -> rank 0 (host objects, a few KB)
-      images    every rank blends a strip of every image: ncclAllGather of the inputs
+      results   match lists -> every rank (one padded int32 all-gather, a few KB)
+      images    every rank blends a strip of every image: ncclAllGather of the 8-bit
+                sources (3 B/px; run_rgb8) or of the f32 images (run), issued on a side
+                stream BEFORE SIFT so that it overlaps SIFT + C1 + matching
       blend     rows [r·H/G, (r+1)·H/G) of the canvas (LinearBlender pixels are
                 independent, blender.cc:37-96; MultiBandBlender strips are computed
                 from ROIs clipped to the strip + the summed blur half-widths)   no collective
       C2        strips -> ncclAllGather -> the mosaic (bit-identical to one GPU)
     """
 
+    PHASES = ("sift", "exchange_descriptors", "match", "gather_matches", "exchange_images", "blend_strip", "gather_strips")
+
     def __init__(self, engine, params=None):
         from ._abi import default_params
         self.eng = engine
         self.params = params or default_params()
         self.ms = {}
+        self._side = None
 
     def _timed(self, name, fn):
         import torch
@@ -190,6 +195,15 @@ class DistributedStitcher:
     def run(self, owned: dict, n_images: int, shapes, pairs, items, geom, bands: int = 0):
         """owned: {image index: cuda float32 tensor H×W×3} following shard_images().
         Returns (matches on rank 0 / None elsewhere, mosaic tensor th×tw×3 on every rank)."""
+        return self._run(owned, None, n_images, shapes, pairs, items, geom, bands)
+
+    def run_rgb8(self, owned_pix: dict, n_images: int, shapes, pairs, items, geom, bands: int = 0):
+        """The same from decoded 8-bit pixels (what read_img starts from, imgio.cc:72): owned_pix =
+        {image index: cuda uint8 tensor H×W×3}.  The u8 -> f32 conversion (read_img's arithmetic)
+        runs on the device, and the image exchange moves 3 B/px instead of 12."""
+        return self._run(None, owned_pix, n_images, shapes, pairs, items, geom, bands)
+
+    def _run(self, owned, owned_pix, n_images, shapes, pairs, items, geom, bands):
         import torch
         dist = _dist()
         eng, params = self.eng, self.params
@@ -197,13 +211,47 @@ class DistributedStitcher:
         dev = torch.device("cuda", torch.cuda.current_device())
         owners = [shard_images(n_images, world, r) for r in range(world)]
         mine = owners[rank]
-        assert sorted(owned) == mine, "images must follow shard_images()"
+        rgb8 = owned_pix is not None
+        assert sorted(owned_pix if rgb8 else owned) == mine, "images must follow shard_images()"
         self._events = []
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+
+        # ---- inputs of the blend: every image on every rank.  Depends on the inputs only, so it is
+        # queued first on a side stream and runs under SIFT / C1 / matching.
+        max_el = max(h * w * 3 for (h, w) in shapes)
+        per_rank = max(len(o) for o in owners)
+        src = owned_pix if rgb8 else owned
+        dt = torch.uint8 if rgb8 else torch.float32
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            ev_i0 = torch.cuda.Event(enable_timing=True)
+            ev_i1 = torch.cuda.Event(enable_timing=True)
+            ev_i0.record()
+            my_i = torch.zeros((per_rank, max_el), dtype=dt, device=dev)
+            for q, k in enumerate(mine):
+                my_i[q, :src[k].numel()] = src[k].reshape(-1)
+            all_i = torch.empty((world * per_rank, max_el), dtype=dt, device=dev)
+            dist.all_gather_into_tensor(all_i, my_i)
+            ev_i1.record()
+        self._events.append(("exchange_images", ev_i0, ev_i1))
 
         # ---- SIFT on the owned images
+        own_f32 = owned
+        if rgb8 and mine:
+            own_f32 = {k: torch.empty(tuple(shapes[k]) + (3,), dtype=torch.float32, device=dev) for k in mine}
+
         def sift():
-            return eng.sift_detect_batch_ptr([owned[k].data_ptr() for k in mine], [shapes[k][1] for k in mine],
-                                             [shapes[k][0] for k in mine], params, device=True) if mine else None
+            if not mine:
+                return None
+            if rgb8:
+                eng.rgb8_to_mat32f_batch_dev([owned_pix[k].data_ptr() for k in mine], [shapes[k][1] for k in mine],
+                                             [shapes[k][0] for k in mine], [3] * len(mine),
+                                             [own_f32[k].data_ptr() for k in mine])
+            return eng.sift_detect_batch_ptr([own_f32[k].data_ptr() for k in mine], [shapes[k][1] for k in mine],
+                                             [shapes[k][0] for k in mine], params, device=True)
         fs_local = self._timed("sift", sift)
 
         # ---- C1: all-gather of the descriptor sets
@@ -270,35 +318,46 @@ class DistributedStitcher:
             return full
         matches = self._timed("gather_matches", gather_lists)
 
-        # ---- inputs of the blend: every image on every rank
-        def exchange_images():
-            max_px = max(h * w * 3 for (h, w) in shapes)
-            per_rank = max(len(o) for o in owners)
-            my_i = torch.zeros((per_rank, max_px), dtype=torch.float32, device=dev)
-            for q, k in enumerate(mine):
-                my_i[q, :owned[k].numel()] = owned[k].reshape(-1)
-            all_i = torch.empty((world * per_rank, max_px), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(all_i, my_i)
-            ptrs = [0] * n_images
-            for r in range(world):
-                for q, k in enumerate(owners[r]):
-                    ptrs[k] = all_i.data_ptr() + (r * per_rank + q) * max_px * 4
-            return ptrs, all_i
-        img_ptrs, keep_i = self._timed("exchange_images", exchange_images)
-
         # ---- strip of the canvas, then C2
+        main.wait_stream(side)                              # the image exchange has landed
         tw, th = max(it[2] for it in items), max(it[3] for it in items)
         rows_per = (th + world - 1) // world
         row0, row1 = min(th, rank * rows_per), min(th, (rank + 1) * rows_per)
         strip = torch.empty((rows_per, tw, 3), dtype=torch.float32, device=dev)
-        self._timed("blend_strip", lambda: eng.blend_rows_dev(img_ptrs, shapes, items, geom, strip.data_ptr(), tw, th,
-                                                              row0, row1, bands, params))
+        keep_f = None
+
+        def blend_strip():
+            nonlocal keep_f
+            el = 1 if rgb8 else 4
+            src_ptrs = [0] * n_images
+            for r in range(world):
+                for q, k in enumerate(owners[r]):
+                    src_ptrs[k] = all_i.data_ptr() + (r * per_rank + q) * max_el * el
+            if rgb8:
+                # read_img's conversion of the gathered 8-bit sources (only images that reach this strip)
+                need = [k for k in range(n_images) if items[k][1] <= row1 + 256 and items[k][3] >= row0 - 256]   # strip + multiband halo
+                keep_f = torch.empty((max(len(need), 1), max_el), dtype=torch.float32, device=dev)
+                img_ptrs = list(src_ptrs)
+                if need:
+                    dst = [keep_f.data_ptr() + q * max_el * 4 for q in range(len(need))]
+                    eng.rgb8_to_mat32f_batch_dev([src_ptrs[k] for k in need], [shapes[k][1] for k in need],
+                                                 [shapes[k][0] for k in need], [3] * len(need), dst)
+                    for q, k in enumerate(need):
+                        img_ptrs[k] = dst[q]
+                # images that cannot reach the strip are never dereferenced: any valid pointer will do
+                spare, needed = keep_f.data_ptr(), set(need)
+                img_ptrs = [p if k in needed else spare for k, p in enumerate(img_ptrs)]
+            else:
+                img_ptrs = src_ptrs
+            eng.blend_rows_dev(img_ptrs, shapes, items, geom, strip.data_ptr(), tw, th, row0, row1, bands, params)
+        self._timed("blend_strip", blend_strip)
         mosaic = torch.empty((world * rows_per, tw, 3), dtype=torch.float32, device=dev)
         self._timed("gather_strips", lambda: dist.all_gather_into_tensor(mosaic, strip))
         torch.cuda.current_stream().synchronize()
+        side.synchronize()
         self.ms = {}
         for name, e0, e1 in self._events:
             self.ms[name] = self.ms.get(name, 0.0) + e0.elapsed_time(e1)
         fs_all.free()
-        del keep, keep_i
+        del keep, my_i, all_i, keep_f
         return matches, mosaic[:th]

@@ -20,14 +20,7 @@ from ._abi import default_params
 from .capi import Engine
 
 
-def ordered_pairs(n: int):
-    """linear_pairwise_match task list: (i, (i+1) % n) (stitcher.cc:116-123)."""
-    return [(i, (i + 1) % n) for i in range(n)]
-
-
-def all_pairs(n: int):
-    """pairwise_match task list (stitcher.cc:98-100)."""
-    return [(i, j) for i in range(n) for j in range(i + 1, n)]
+from .synth import all_pairs, ordered_pairs  # noqa: F401  (task lists live with the workload generator)
 
 
 class Stitcher:
@@ -151,7 +144,9 @@ class PipelinedStitcher:
         self._next = 0
 
     def _ensure(self, s, shapes, out_wh):
+        realloc = False
         if s["shapes"] != shapes:
+            realloc = True
             if s["imgs"]:
                 self.cmp.dev_free(s["imgs"])
             offs, total = [], 0
@@ -178,6 +173,12 @@ class PipelinedStitcher:
                     self.cmp.dev_free(s["out8"])
                 s["out8"] = self.cmp.dev_alloc(self.out_bytes(out_wh))
             s["out_wh"] = tuple(out_wh)
+            realloc = True
+        if realloc:
+            # The buffers come stream-ordered from the compute context's pool, but the upload
+            # stream writes them first: a block the pool hands out may still be in use by work
+            # queued on cmp (the other slot's featureset, a SIFT arena freed in stream order).
+            # Drain cmp so that the allocation is complete and the block idle before `up` touches it.
             self.cmp.sync()
 
     RGB8_HEADER = 256

@@ -13,7 +13,52 @@ from __future__ import annotations
 import numpy as np
 
 
+def ordered_pairs(n: int):
+    """linear_pairwise_match task list: (i, (i+1) % n) (stitcher.cc:116-123)."""
+    return [(i, (i + 1) % n) for i in range(n)]
+
+
+def all_pairs(n: int):
+    """pairwise_match task list (stitcher.cc:98-100)."""
+    return [(i, j) for i in range(n) for j in range(i + 1, n)]
+
+
+def _noise_rows(grid: np.ndarray, r0: int, r1: int, w: int, cell: int, out: np.ndarray, scale: float):
+    """Rows [r0, r1) of one octave of bilinear value noise, added to `out` as
+    (v - 0.5) * scale.  Element arithmetic (float32, left to right):
+    g00*(1-fy)*(1-fx) + g01*(1-fy)*fx + g10*fy*(1-fx) + g11*fy*fx."""
+    ys = np.arange(r0, r1, dtype=np.float32) / cell
+    xs = np.arange(w, dtype=np.float32) / cell
+    y0 = ys.astype(np.int64)
+    fy = (ys - y0)[:, None, None]
+    fx = (xs - xs.astype(np.int64))[None, :, None]
+    nx = (w - 1) // cell + 1
+    top, bot = grid[y0], grid[y0 + 1]                      # (rows, gw, 3)
+    # x0 = i // cell runs in blocks of `cell` equal indices: a repeat, not a gather
+    g00 = np.repeat(top[:, :nx], cell, axis=1)[:, :w]
+    g01 = np.repeat(top[:, 1:nx + 1], cell, axis=1)[:, :w]
+    g10 = np.repeat(bot[:, :nx], cell, axis=1)[:, :w]
+    g11 = np.repeat(bot[:, 1:nx + 1], cell, axis=1)[:, :w]
+    v = g00 * (1 - fy) * (1 - fx) + g01 * (1 - fy) * fx + g10 * fy * (1 - fx) + g11 * fy * fx
+    out[r0:r1] += (v - 0.5) * scale
+
+
+def _add_value_noise(rng: np.random.RandomState, img: np.ndarray, cell: int, scale: float, pool=None) -> None:
+    h, w = img.shape[:2]
+    gh, gw = h // cell + 2, w // cell + 2
+    grid = rng.rand(gh, gw, 3).astype(np.float32)
+    step = 128
+    blocks = [(r, min(h, r + step)) for r in range(0, h, step)]
+    if pool is None or len(blocks) == 1:
+        for r0, r1 in blocks:
+            _noise_rows(grid, r0, r1, w, cell, img, scale)
+    else:                                                   # numpy releases the GIL inside these array ops
+        list(pool.map(lambda b: _noise_rows(grid, b[0], b[1], w, cell, img, scale), blocks))
+
+
 def _value_noise(rng: np.random.RandomState, h: int, w: int, cell: int) -> np.ndarray:
+    """One octave on its own (h×w×3 float32 in [0,1])."""
+    img = np.zeros((h, w, 3), np.float32)
     gh, gw = h // cell + 2, w // cell + 2
     grid = rng.rand(gh, gw, 3).astype(np.float32)
     ys = np.arange(h, dtype=np.float32) / cell
@@ -33,9 +78,16 @@ def make_canvas(h: int, w: int, seed: int) -> np.ndarray:
     """H×W×3 float32 in [0,1]."""
     rng = np.random.RandomState(seed)
     img = np.full((h, w, 3), 0.5, np.float32)
+    pool = None
+    if h * w > (1 << 21):
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        pool = ThreadPoolExecutor(max(1, min(32, len(os.sched_getaffinity(0)))))
     for o, cell in enumerate((128, 64, 32, 16, 8)):
         amp = 0.375 / (2 ** o)
-        img += (_value_noise(rng, h, w, cell) - 0.5) * (2 * amp)
+        _add_value_noise(rng, img, cell, 2 * amp, pool)
+    if pool is not None:
+        pool.shutdown()
     n_shapes = (h * w) // 900
     cy = rng.randint(0, h, n_shapes)
     cx = rng.randint(0, w, n_shapes)

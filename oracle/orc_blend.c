@@ -55,6 +55,7 @@ static int linear_blend(int n, const pano_blend_image* imgs, const pano_blend_ge
     memset(out, 0, sizeof(float) * (size_t)tw * th * 3);
     for (k = 0; k < n; ++k) {
       const pano_blend_image* im = &imgs[k];
+      ORC_PAR_FOR(private(j))
       for (i = im->y0; i < im->y1; ++i)
         for (j = im->x0; j < im->x1; ++j) {
           float color[3], w;
@@ -65,6 +66,7 @@ static int linear_blend(int n, const pano_blend_image* imgs, const pano_blend_ge
           weight[(size_t)i * tw + j] += w;
         }
     }
+    ORC_PAR_FOR(private(j))
     for (i = 0; i < th; ++i)
       for (j = 0; j < tw; ++j) {
         float* p = out + ((size_t)i * tw + j) * 3;
@@ -74,6 +76,7 @@ static int linear_blend(int n, const pano_blend_image* imgs, const pano_blend_ge
       }
     free(weight);
   } else {
+    ORC_PAR_FOR(private(j, k))
     for (i = 0; i < th; ++i)
       for (j = 0; j < tw; ++j) {
         float isum[3] = {0, 0, 0}, wsum = 0;
@@ -118,6 +121,7 @@ static int multiband_blend(int n, const pano_blend_image* imgs, const pano_blend
     m->cur = (float*)malloc(sizeof(float) * 4 * (size_t)m->rw * m->rh);
     m->next = NULL;
     m->mask = (unsigned char*)calloc((size_t)m->rw * m->rh, 1);
+    ORC_PAR_FOR(private(j))
     for (i = 0; i < m->rh; ++i)
       for (j = 0; j < m->rw; ++j) {
         double x, y;
@@ -139,6 +143,7 @@ static int multiband_blend(int n, const pano_blend_image* imgs, const pano_blend
         }
       }
   }
+  ORC_PAR_FOR(private(j, k))
   for (i = 0; i < th; ++i) /* update_weight_map */
     for (j = 0; j < tw; ++j) {
       float mx = 0.f;
@@ -158,11 +163,13 @@ static int multiband_blend(int n, const pano_blend_image* imgs, const pano_blend
       float sigma = (float)(sqrt(level * 2 + 1.0) * 4);
       float kernel[256];
       int kw = orc_gauss_kernel(sigma, P->gauss_window_factor, kernel);
+      ORC_PAR_FOR(schedule(dynamic, 1))   /* images are independent (multiband.cc:145-151) */
       for (k = 0; k < n; ++k) {
         if (!M[k].next) M[k].next = (float*)malloc(sizeof(float) * 4 * (size_t)M[k].rw * M[k].rh);
         orc_blur(M[k].cur, M[k].next, M[k].rw, M[k].rh, 4, kernel, kw);
       }
     }
+    ORC_PAR_FOR(private(j, k))
     for (i = 0; i < th; ++i)
       for (j = 0; j < tw; ++j) {
         float isum[3] = {0, 0, 0}, wsum = 0;

@@ -31,6 +31,16 @@
 
 /* lib/utils.hh:27  between(a,b,c) == (a >= b) && (a <= c - 1) */
 #define ORC_BETWEEN(a, b, c) (((a) >= (b)) && ((a) <= (c) - 1))
+/* ORC_MT (liboracle_mt.so, -fopenmp): loops whose iterations write disjoint outputs run
+ * on all host threads; each output element is still computed by the same sequential
+ * arithmetic, so results are bit-identical to the single-thread build (checked by
+ * tests/test_oracle_vs_ref.py::test_oracle_mt_equals_oracle). */
+#ifdef ORC_MT
+#define ORC_PRAGMA(x) _Pragma(#x)
+#define ORC_PAR_FOR(clauses) ORC_PRAGMA(omp parallel for clauses)
+#else
+#define ORC_PAR_FOR(clauses)
+#endif
 #define ORC_EPS 1e-6 /* lib/utils.hh:23 (real_t = double) */
 
 static inline float orc_sqrf(float x) { return x * x; } /* lib/utils.hh:26 */

@@ -25,18 +25,25 @@ static float euclidean_sqr(const float* x, const float* y, int n, float now_thre
   return (l0 + l1) + (l2 + l3);
 }
 
-/* feature/matcher.cc:15-71 FeatureMatcher::match, single-thread order */
+/* feature/matcher.cc:15-71 FeatureMatcher::match.  The decision of row k depends on
+ * nothing but k, so the loop body is written as "decide row k -> idx[k]" followed by
+ * the single-thread emission order (ascending k); the ORC_MT build (liboracle_mt.so,
+ * a faster checker for the BASELINE-size configs) runs the rows on all host threads. */
 int orc_match(const float* a, int n, const float* b, int m, const pano_params* P,
               int* pairs, int* npairs) {
   const float REJECT_RATIO_SQR = P->match_reject_next_ratio * P->match_reject_next_ratio;
-  int l1 = n, l2 = m, rev = l1 > l2, k, kk, cnt = 0;
+  int l1 = n, l2 = m, rev = l1 > l2, k, cnt = 0;
   const float *f1 = a, *f2 = b;
+  int* idx;
   if (rev) { l1 = m; l2 = n; f1 = b; f2 = a; }
+  idx = (int*)malloc(sizeof(int) * (size_t)(l1 > 0 ? l1 : 1));
+  ORC_PAR_FOR(schedule(dynamic, 16))
   for (k = 0; k < l1; ++k) {
     const float* dsc1 = f1 + (size_t)128 * k;
     const float* dsc2;
-    int min_idx = -1;
+    int min_idx = -1, kk;
     float mn = FLT_MAX, next_min = FLT_MAX;
+    idx[k] = -1;
     for (kk = 0; kk < l2; ++kk) {
       float dist = euclidean_sqr(dsc1, f2 + (size_t)128 * kk, 128, next_min);
       if (dist < mn) { next_min = mn; mn = dist; min_idx = kk; }
@@ -50,10 +57,15 @@ int orc_match(const float* a, int n, const float* b, int m, const pano_params* P
         if (dist < next_min) next_min = dist;
       }
     if (mn > REJECT_RATIO_SQR * next_min) continue;
-    if (rev) { pairs[2 * cnt] = min_idx; pairs[2 * cnt + 1] = k; }
-    else { pairs[2 * cnt] = k; pairs[2 * cnt + 1] = min_idx; }
+    idx[k] = min_idx;
+  }
+  for (k = 0; k < l1; ++k) {
+    if (idx[k] < 0) continue;
+    if (rev) { pairs[2 * cnt] = idx[k]; pairs[2 * cnt + 1] = k; }
+    else { pairs[2 * cnt] = k; pairs[2 * cnt + 1] = idx[k]; }
     ++cnt;
   }
+  free(idx);
   *npairs = cnt;
   return 0;
 }

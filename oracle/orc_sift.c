@@ -478,4 +478,9 @@ int orc_sift_detect(const float* rgb, int w, int h, const pano_params* P, int ca
   return n <= cap ? n : -1;
 }
 
+#ifdef ORC_MT
+#include <omp.h>
+int orc_num_threads(void) { return omp_get_max_threads(); }
+#else
 int orc_num_threads(void) { return 1; }
+#endif

@@ -14,6 +14,7 @@ from openpano_b200._abi import (PanoBlendGeom, PanoBlendImage, PanoParams, PanoS
 
 ROOT = Path(__file__).resolve().parent.parent
 ORACLE_SO = ROOT / "oracle" / "liboracle.so"
+ORACLE_MT_SO = ROOT / "oracle" / "liboracle_mt.so"
 REF_SO = ROOT / "oracle" / "_ref" / "libopenpano_ref.so"
 REF_FAST_SO = ROOT / "oracle" / "_ref" / "libopenpano_ref_fast.so"
 
@@ -272,11 +273,14 @@ _cache = {}
 
 
 def get_checker(kind: str) -> Checker:
-    """kind: 'orc' (C restatement), 'ref' (reference TUs, parity flags) or
+    """kind: 'orc' (C restatement), 'orc_mt' (the same with independent loops under
+    OpenMP: bit-identical, for BASELINE-size inputs), 'ref' (reference TUs, parity flags) or
     'ref_fast' (reference TUs, perf flags + OpenMP)."""
     if kind not in _cache:
         if kind == "orc":
             _cache[kind] = Checker(ORACLE_SO, "orc")
+        elif kind == "orc_mt":
+            _cache[kind] = Checker(ORACLE_MT_SO, "orc")
         elif kind == "ref":
             _cache[kind] = Checker(REF_SO, "ref")
         elif kind == "ref_fast":
@@ -287,4 +291,4 @@ def get_checker(kind: str) -> Checker:
 
 
 def have(kind: str) -> bool:
-    return {"orc": ORACLE_SO, "ref": REF_SO, "ref_fast": REF_FAST_SO}[kind].exists()
+    return {"orc": ORACLE_SO, "orc_mt": ORACLE_MT_SO, "ref": REF_SO, "ref_fast": REF_FAST_SO}[kind].exists()

@@ -186,3 +186,23 @@ def test_cyl_warp_other_focal(orc, ref):
     oa, ka = orc.cyl_warp(img, k, 1.0, p)
     ob, kb = ref.cyl_warp(img, k, 1.0, p)
     assert gu.same_bits(oa, ob) and gu.same_bits(ka, kb)
+
+
+def test_oracle_mt_equals_oracle(orc):
+    """oracle/liboracle_mt.so (independent loops under OpenMP, used by the BASELINE-size GPU
+    parity tests) must be bit-identical to the single-thread restatement."""
+    from tests.checker import get_checker, have
+    if not have("orc_mt"):
+        pytest.skip("oracle/liboracle_mt.so not built")
+    mt = get_checker("orc_mt")
+    rng = np.random.RandomState(21)
+    a = synth.rootsift_like(900, 4)
+    b = a[rng.permutation(900)][:700] + rng.randn(700, 128).astype(np.float32) * 25.0
+    for x, y in ((a, b), (b, a), (a[:1], b), (a, a)):
+        assert np.array_equal(orc.match(x, y), mt.match(x, y))
+    imgs, org = synth.make_stack(5, 260, 200, 90, 77, rows=2, step_y=70)
+    items, geom = synth.translation_blend_setup(org, 260, 200)
+    for bands in (0, 2, 5):
+        for lazy in (0, 1):
+            p = default_params(lazy_read=lazy, multiband=bands)
+            assert gu.same_bits(orc.blend(imgs, items, geom, bands, p), mt.blend(imgs, items, geom, bands, p)), (bands, lazy)

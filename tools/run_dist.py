@@ -58,7 +58,7 @@ def main():
             dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            matches, mosaic = ds.run(owned, n, shapes, pairs, items, geom, bands)
+            matches, mosaic = ds.run(owned, n, shapes, pairs, items, geom, bands)  # f32 inputs (run_rgb8: 8-bit inputs)
             e1.record()
             torch.cuda.synchronize()
             t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
