@@ -154,7 +154,7 @@ k_blur_dog(const OctMeta* __restrict__ octs, const int2* __restrict__ span, int 
 template <int C>
 __device__ __forceinline__ void blur_level(const float* __restrict__ grey, float* __restrict__ colbuf,
                                            float* __restrict__ outT, const float* __restrict__ taps_g,
-                                           int R, int GW, int CS, int tid) {
+                                           int R, int RX, int GW, int CS, int tid) {
   constexpr int KW = 2 * C + 1;
   float tap[KW];
 #pragma unroll
@@ -163,7 +163,7 @@ __device__ __forceinline__ void blur_level(const float* __restrict__ grey, float
   // column pass: items = (BT_H/8 row strips) x cw columns
   for (int item = tid; item < (BT_H / 8) * cw; item += BT_THREADS) {
     const int strip = item / cw, xx = item - strip * cw;
-    const float* col = grey + (strip * 8 + R - C) * GW + (xx + R - C);
+    const float* col = grey + (strip * 8 + R - C) * GW + (xx + RX - C);
     float win[8 + 2 * C];
 #pragma unroll
     for (int j = 0; j < 8 + 2 * C; ++j) win[j] = col[j * GW];
@@ -236,7 +236,10 @@ k_blur_dog_fast(const OctMeta* __restrict__ octs, const int2* __restrict__ span,
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t s_bar[2];
   const int R = gt.rmax;
-  const int GW = BT_W + 2 * R, GH = BT_H + 2 * R;
+  // TMA wants the box origin on a 16-byte boundary of the innermost dimension (a box starting
+  // at x0 - 6 faults): the staged tile carries a column halo rounded up to 4 floats.
+  const int RX = (R + 3) & ~3;
+  const int GW = BT_W + 2 * RX, GH = BT_H + 2 * R;
   const int GSZ = (GH * GW + 31) & ~31;  // floats per grey buffer, 128-byte multiple
   const int CS = GW | 1;                 // odd stride: row-pass lanes (rows) hit distinct banks
   float* grey0 = smem;                   // [2][GH][GW]
@@ -254,7 +257,7 @@ k_blur_dog_fast(const OctMeta* __restrict__ octs, const int2* __restrict__ span,
   if (tid == 0 && t < n_tiles) {
     const BlurTile tl = find_blur_tile(span, n_om, t);
     sbar_expect_tx(sm_u32(&s_bar[0]), tile_bytes);
-    tma_load_2d(sm_u32(grey0), maps + tl.om, tl.tx * BT_W - R, tl.ty * BT_H - R, sm_u32(&s_bar[0]));
+    tma_load_2d(sm_u32(grey0), maps + tl.om, tl.tx * BT_W - RX, tl.ty * BT_H - R, sm_u32(&s_bar[0]));
   }
   for (int it = 0; t < n_tiles; t += gridDim.x, ++it) {
     const int b = it & 1;
@@ -268,15 +271,15 @@ k_blur_dog_fast(const OctMeta* __restrict__ octs, const int2* __restrict__ span,
       const BlurTile nx = find_blur_tile(span, n_om, t + gridDim.x);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       sbar_expect_tx(sm_u32(&s_bar[b ^ 1]), tile_bytes);
-      tma_load_2d(sm_u32(grey0 + (b ^ 1) * GSZ), maps + nx.om, nx.tx * BT_W - R, nx.ty * BT_H - R, sm_u32(&s_bar[b ^ 1]));
+      tma_load_2d(sm_u32(grey0 + (b ^ 1) * GSZ), maps + nx.om, nx.tx * BT_W - RX, nx.ty * BT_H - R, sm_u32(&s_bar[b ^ 1]));
     }
     sbar_wait(sm_u32(&s_bar[b]), (uint32_t)(it >> 1) & 1u);
-    if (x0 - R < 0 || y0 - R < 0 || x0 + BT_W + R > om.w || y0 + BT_H + R > om.h) {   // uniform per CTA
+    if (x0 - RX < 0 || y0 - R < 0 || x0 + BT_W + RX > om.w || y0 + BT_H + R > om.h) {   // uniform per CTA
       for (int i = tid; i < GH * GW; i += BT_THREADS) {
         const int yy = i / GW, xx = i - yy * GW;
-        const int gy = y0 + yy - R, gx = x0 + xx - R;
+        const int gy = y0 + yy - R, gx = x0 + xx - RX;
         const int cy = min(max(gy, 0), om.h - 1), cx = min(max(gx, 0), om.w - 1);
-        if (cy != gy || cx != gx) grey[i] = grey[(cy - y0 + R) * GW + (cx - x0 + R)];
+        if (cy != gy || cx != gx) grey[i] = grey[(cy - y0 + R) * GW + (cx - x0 + RX)];
       }
       __syncthreads();
     }
@@ -284,10 +287,10 @@ k_blur_dog_fast(const OctMeta* __restrict__ octs, const int2* __restrict__ span,
     const int gx = x0 + tx;
     float prev[BT_H / 4];
 #pragma unroll
-    for (int i = 0; i < BT_H / 4; ++i) prev[i] = grey[(ty + 4 * i + R) * GW + tx + R];
+    for (int i = 0; i < BT_H / 4; ++i) prev[i] = grey[(ty + 4 * i + R) * GW + tx + RX];
     for (int s = 0; s < gt.nlev; ++s) {
-      if (gt.center[s] == 3) blur_level<3>(grey, colbuf, outT, gt.taps[s], R, GW, CS, tid);
-      else blur_level<6>(grey, colbuf, outT, gt.taps[s], R, GW, CS, tid);
+      if (gt.center[s] == 3) blur_level<3>(grey, colbuf, outT, gt.taps[s], R, RX, GW, CS, tid);
+      else blur_level<6>(grey, colbuf, outT, gt.taps[s], R, RX, GW, CS, tid);
       float* lvl = arena + om.gauss_off + (size_t)(s + 1) * om.plane;
       float* dog = arena + om.dog_off + (size_t)s * om.plane;
 #pragma unroll
@@ -1190,7 +1193,7 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
       const OctMeta& om = wk->h_oct[k];
       unsigned long long dims[2] = {(unsigned long long)om.w, (unsigned long long)om.h};
       unsigned long long strides[1] = {(unsigned long long)om.pitch * sizeof(float)};
-      unsigned box[2] = {(unsigned)(BT_W + 2 * R), (unsigned)(BT_H + 2 * R)};
+      unsigned box[2] = {(unsigned)(BT_W + 2 * ((R + 3) & ~3)), (unsigned)(BT_H + 2 * R)};
       SIFT_TRY(ctx_tma_encode(ctx, &maps[k], wk->arena + om.gauss_off, 2, dims, strides, box));
     }
     SIFT_TRY(ctx_put(ctx, wk->d_maps, maps.data(), maps.size() * sizeof(TmaDesc)));
@@ -1216,7 +1219,7 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     size_t smem = ((size_t)(BT_H + 2 * R) * (BT_W + 2 * R) + (size_t)BT_H * (BT_W + 2 * R)) * sizeof(float);
     if (smem > 200 * 1024) { sift_work_free(ctx, wk); return ctx_fail(ctx, PANO_ERR_INVALID, "sift: blur halo too large"); }
     if (fast) {
-      const int GW = BT_W + 2 * R, GH = BT_H + 2 * R, CS = GW | 1;
+      const int GW = BT_W + 2 * ((R + 3) & ~3), GH = BT_H + 2 * R, CS = GW | 1;
       const size_t gsz = ((size_t)GH * GW + 31) & ~(size_t)31;
       size_t smf = (2 * gsz + (size_t)BT_H * CS + (size_t)BT_H * (BT_W + 1)) * sizeof(float);
       SIFT_CUDA(cudaFuncSetAttribute(k_blur_dog_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
