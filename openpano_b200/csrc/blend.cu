@@ -9,6 +9,7 @@
 // (tan of c.y), so they are tabulated on the host with the reference's libm and
 // the kernels do IEEE f64 arithmetic only -> bit-identical coordinates.
 #include "common.cuh"
+#include "blur_tile.cuh"
 #include <math.h>
 #include <string.h>
 #include <vector>
@@ -19,8 +20,13 @@ struct BlendImg {
   int w, h;
   int x0, y0, x1, y1;
   double hi[9];
-  long long roi_off;      // multiband: first float4 of this image's ROI buffers
-  int rw, rh;
+  // multiband: the ROI is kept as FOUR PLANES (r, g, b, weight) of rh x pitch floats — the
+  // reference's WeightedPixel (multiband.hh:13-23) de-interleaved, so that the weight map, the
+  // blur and the accumulation each touch only the bytes they use and rows start on 128-byte lines
+  long long roi_off;      // first float of plane 0 in the level buffers
+  long long plane;        // floats per plane (pitch * rh)
+  long long mask_off;     // first byte of the validity mask (same pitch)
+  int rw, rh, pitch;
 };
 
 struct BlendGeom {
@@ -128,7 +134,7 @@ __global__ void k_linear_blend(const BlendImg* __restrict__ imgs, int n, BlendGe
 
 // ============================================================ multiband
 // multiband.cc:19-57 create_first_level
-__global__ void k_mb_first_level(const BlendImg* __restrict__ imgs, BlendGeom g, float4* __restrict__ cur,
+__global__ void k_mb_first_level(const BlendImg* __restrict__ imgs, BlendGeom g, float* __restrict__ cur,
                                  unsigned char* __restrict__ mask) {
   const BlendImg& im = imgs[blockIdx.z];
   int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,21 +145,22 @@ __global__ void k_mb_first_level(const BlendImg* __restrict__ imgs, BlendGeom g,
   float c0, c1, c2;
   bool ok = interpolate_rgb(im.rgb, im.w, im.h, (float)y, (float)x, &c0, &c1, &c2);
   if (ok && fminf(c0, fminf(c1, c2)) < 0) ok = false;
-  size_t o = (size_t)im.roi_off + (size_t)i * im.rw + j;
-  if (!ok) {
-    cur[o] = make_float4(0.f, 0.f, 0.f, 0.f);
-    mask[o] = 1;
-  } else {
+  const size_t o = (size_t)i * im.pitch + j;
+  float* p = cur + im.roi_off + o;
+  float ww = 0.f;
+  if (!ok) { c0 = 0.f; c1 = 0.f; c2 = 0.f; }
+  else {
     double ox = x / im.w - 0.5, oy = y / im.h - 0.5;
-    double ww = (0.5 - fabs(ox)) * (0.5 - fabs(oy));
-    if (ww < 0.0) ww = 0.0;
-    cur[o] = make_float4(c0, c1, c2, (float)(ww + 1e-6));
-    mask[o] = 0;
+    double wd = (0.5 - fabs(ox)) * (0.5 - fabs(oy));
+    if (wd < 0.0) wd = 0.0;
+    ww = (float)(wd + 1e-6);
   }
+  p[0] = c0; p[im.plane] = c1; p[2 * im.plane] = c2; p[3 * im.plane] = ww;
+  mask[im.mask_off + o] = ok ? 0 : 1;
 }
 
 // multiband.cc:125-143 update_weight_map (first image with the largest weight wins)
-__global__ void k_mb_weight_argmax(const BlendImg* __restrict__ imgs, int n, float4* __restrict__ cur, int tw,
+__global__ void k_mb_weight_argmax(const BlendImg* __restrict__ imgs, int n, float* __restrict__ cur, int tw,
                                    int row0, int row1) {
   __shared__ TileList tl;
   {
@@ -165,81 +172,138 @@ __global__ void k_mb_weight_argmax(const BlendImg* __restrict__ imgs, int n, flo
   if (j >= tw || i >= row1) return;
   const int nl = tl.n < 0 ? n : tl.n;
   float mx = 0.f;
-  long long best = -1;
+  float* best = nullptr;
   for (int q = 0; q < nl; ++q) {
     const BlendImg& im = imgs[tl.n < 0 ? q : (int)tl.idx[q]];
     if (i >= im.y0 && i <= im.y1 && j >= im.x0 && j <= im.x1) {
-      size_t o = (size_t)im.roi_off + (size_t)(i - im.y0) * im.rw + (j - im.x0);
-      float w = cur[o].w;
-      if (w > mx) { mx = w; best = (long long)o; }
-      cur[o].w = 0.f;
+      float* wp = cur + im.roi_off + 3 * im.plane + (size_t)(i - im.y0) * im.pitch + (j - im.x0);
+      const float w = *wp;
+      if (w > mx) { mx = w; best = wp; }
+      *wp = 0.f;
     }
   }
-  if (best >= 0) cur[best].w = 1.f;
+  if (best) *best = 1.f;
 }
 
-// gaussian.hh:29-90 on WeightedPixel (4 floats): column pass ...
+// gaussian.hh:29-90 on WeightedPixel: every channel of the pixel goes through the same
+// column-then-row passes, i.e. four independent scalar planes.
 struct BlurTaps { int center; float taps[64]; };
+struct MbPlane { long long off; int w, h, pitch, pad; };   // one (image, channel) plane of a level buffer
 
+// Both passes of one blur level on 64x32 tiles of every plane (blur_tile.cuh), PERSISTENT CTAs:
+// the tile + halo of the next work item is fetched by TMA into the other half of a double
+// buffer while this one is computed.  TMA zero-fills outside the ROI where the reference's
+// line buffers replicate the ROI edge (gaussian.hh:52-58,74-81): border tiles patch those cells
+// from the staged in-range ones.
+template <int C>
+__global__ void __launch_bounds__(BT_THREADS, 3)
+k_mb_blur_tma(const MbPlane* __restrict__ planes, const int2* __restrict__ span, int n_planes, int n_tiles,
+              const TmaDesc* __restrict__ maps, float* __restrict__ dst, const __grid_constant__ BlurTaps bt) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  constexpr int RX = (C + 3) & ~3;                 // TMA box origin: 16-byte aligned columns
+  constexpr int GW = BT_W + 2 * RX, GH = BT_H + 2 * C;
+  constexpr int GSZ = (GH * GW + 31) & ~31;
+  constexpr int CS = GW | 1;
+  float* grey0 = smem;
+  float* colbuf = smem + 2 * GSZ;
+  float* outT = colbuf + BT_H * CS;
+  const int tid = threadIdx.x;
+  constexpr uint32_t tile_bytes = (uint32_t)(GH * GW * sizeof(float));
+  if (tid == 0) {
+    sbar_init(sm_u32(&s_bar[0]), 1);
+    sbar_init(sm_u32(&s_bar[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int t = blockIdx.x;
+  if (tid == 0 && t < n_tiles) {
+    const BlurTile tl = find_blur_tile(span, n_planes, t);
+    sbar_expect_tx(sm_u32(&s_bar[0]), tile_bytes);
+    tma_load_2d(sm_u32(grey0), maps + tl.om, tl.tx * BT_W - RX, tl.ty * BT_H - C, sm_u32(&s_bar[0]));
+  }
+  for (int it = 0; t < n_tiles; t += gridDim.x, ++it) {
+    const int b = it & 1;
+    float* grey = grey0 + b * GSZ;
+    const BlurTile tl = find_blur_tile(span, n_planes, t);
+    const MbPlane pl = planes[tl.om];
+    const int x0 = tl.tx * BT_W, y0 = tl.ty * BT_H;
+    if (tid == 0 && t + (int)gridDim.x < n_tiles) {
+      const BlurTile nx = find_blur_tile(span, n_planes, t + gridDim.x);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      sbar_expect_tx(sm_u32(&s_bar[b ^ 1]), tile_bytes);
+      tma_load_2d(sm_u32(grey0 + (b ^ 1) * GSZ), maps + nx.om, nx.tx * BT_W - RX, nx.ty * BT_H - C, sm_u32(&s_bar[b ^ 1]));
+    }
+    sbar_wait(sm_u32(&s_bar[b]), (uint32_t)(it >> 1) & 1u);
+    if (x0 - RX < 0 || y0 - C < 0 || x0 + BT_W + RX > pl.w || y0 + BT_H + C > pl.h) {   // uniform per CTA
+      for (int i = tid; i < GH * GW; i += BT_THREADS) {
+        const int yy = i / GW, xx = i - yy * GW;
+        const int gy = y0 + yy - C, gx = x0 + xx - RX;
+        const int cy = min(max(gy, 0), pl.h - 1), cx = min(max(gx, 0), pl.w - 1);
+        if (cy != gy || cx != gx) grey[i] = grey[(cy - y0 + C) * GW + (cx - x0 + RX)];
+      }
+      __syncthreads();
+    }
+    blur_level<C>(grey, colbuf, outT, bt.taps, C, RX, GW, CS, tid);
+    const int tx = tid & (BT_W - 1), ty = tid / BT_W;   // 64 x 4
+    const int gx = x0 + tx;
+    float* out = dst + pl.off;
+#pragma unroll
+    for (int i = 0; i < BT_H / 4; ++i) {
+      const int y = ty + 4 * i, gy = y0 + y;
+      if (gx < pl.w && gy < pl.h) out[(size_t)gy * pl.pitch + gx] = outT[y * (BT_W + 1) + tx];
+    }
+    __syncthreads();   // colbuf / outT / this staging buffer are free for the next tiles
+  }
+}
+
+// Any other window width (GAUSS_WINDOW_FACTOR != 6, more than 5 bands): one tile per CTA,
+// clamped loads, taps looped from the table.
 #define MB_TW 64
 #define MB_TH 32
-
-// Both passes of GaussianBlur::blur on one ROI tile (gaussian.hh:29-90 on WeightedPixel):
-// the tile plus a halo of `center` pixels (replicated at the ROI border, exactly the
-// clamp of the reference's column/row buffers) is staged in shared memory, the column
-// pass writes an intermediate strip to shared memory, the row pass reads it — one read
-// and one write of the level per ROI pixel instead of two of each through HBM.
 __global__ void __launch_bounds__(256)
-k_mb_blur(const BlendImg* __restrict__ imgs, const float4* __restrict__ src, float4* __restrict__ dst,
-          const __grid_constant__ BlurTaps bt) {
-  extern __shared__ float4 mb_smem[];
-  const BlendImg& im = imgs[blockIdx.z];
-  const int tx0 = blockIdx.x * MB_TW, ty0 = blockIdx.y * MB_TH;
-  if (tx0 >= im.rw || ty0 >= im.rh) return;
+k_mb_blur_generic(const MbPlane* __restrict__ planes, const int2* __restrict__ span, int n_planes,
+                  const float* __restrict__ src, float* __restrict__ dst, const __grid_constant__ BlurTaps bt) {
+  extern __shared__ float mb_smem[];
+  const BlurTile tl = find_blur_tile(span, n_planes, blockIdx.x);
+  const MbPlane pl = planes[tl.om];
+  const int tx0 = tl.tx * MB_TW, ty0 = tl.ty * MB_TH;
   const int c = bt.center, kw = 2 * c + 1;
   const int SW = MB_TW + 2 * c, SH = MB_TH + 2 * c;
-  float4* tile = mb_smem;                 // [SH][SW]
-  float4* colres = mb_smem + SH * SW;     // [MB_TH][SW]
-  const float4* base = src + im.roi_off;
+  float* tile = mb_smem;                 // [SH][SW]
+  float* colres = mb_smem + SH * SW;     // [MB_TH][SW]
+  const float* base = src + pl.off;
   const int tid = threadIdx.x;
   for (int idx = tid; idx < SH * SW; idx += 256) {
     const int r = idx / SW, q = idx - r * SW;
-    const int y = min(max(ty0 - c + r, 0), im.rh - 1), x = min(max(tx0 - c + q, 0), im.rw - 1);
-    tile[idx] = __ldg(base + (size_t)y * im.rw + x);
+    const int y = min(max(ty0 - c + r, 0), pl.h - 1), x = min(max(tx0 - c + q, 0), pl.w - 1);
+    tile[idx] = __ldg(base + (size_t)y * pl.pitch + x);
   }
   __syncthreads();
-  // column pass: output row i (tile-local), every staged column
   for (int idx = tid; idx < MB_TH * SW; idx += 256) {
     const int i = idx / SW, q = idx - i * SW;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* col = tile + i * SW + q;
-    for (int k = 0; k < kw; ++k) {
-      const float4 v = col[k * SW];
-      const float t = bt.taps[k];
-      acc.x += v.x * t; acc.y += v.y * t; acc.z += v.z * t; acc.w += v.w * t;
-    }
+    float acc = 0.f;
+    const float* col = tile + i * SW + q;
+    for (int k = 0; k < kw; ++k) acc += col[k * SW] * bt.taps[k];
     colres[idx] = acc;
   }
   __syncthreads();
-  // row pass
   for (int idx = tid; idx < MB_TH * MB_TW; idx += 256) {
     const int i = idx / MB_TW, j = idx - i * MB_TW;
-    if (ty0 + i >= im.rh || tx0 + j >= im.rw) continue;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* row = colres + i * SW + j;
-    for (int k = 0; k < kw; ++k) {
-      const float4 v = row[k];
-      const float t = bt.taps[k];
-      acc.x += v.x * t; acc.y += v.y * t; acc.z += v.z * t; acc.w += v.w * t;
-    }
-    dst[(size_t)im.roi_off + (size_t)(ty0 + i) * im.rw + tx0 + j] = acc;
+    if (ty0 + i >= pl.h || tx0 + j >= pl.w) continue;
+    float acc = 0.f;
+    const float* row = colres + i * SW + j;
+    for (int k = 0; k < kw; ++k) acc += row[k] * bt.taps[k];
+    dst[pl.off + (size_t)(ty0 + i) * pl.pitch + tx0 + j] = acc;
   }
 }
 
-// multiband.cc:75-108 per-level accumulate (+ :113-121 clamp on the last level)
-__global__ void k_mb_accumulate(const BlendImg* __restrict__ imgs, int n, const float4* __restrict__ cur,
-                                const float4* __restrict__ next, const unsigned char* __restrict__ mask,
-                                int is_last, float* __restrict__ out, unsigned char* __restrict__ tmask, int tw,
+// multiband.cc:75-108 per-level accumulate (+ :113-121 clamp on the last level).  `first`: no
+// level has touched the strip yet, so every pixel is written (value, or -1 = Color::NO) and
+// no separate fill pass is needed.
+__global__ void k_mb_accumulate(const BlendImg* __restrict__ imgs, int n, const float* __restrict__ cur,
+                                const float* __restrict__ next, const unsigned char* __restrict__ mask,
+                                int first, int is_last, float* __restrict__ out, unsigned char* __restrict__ tmask, int tw,
                                 int row0, int row1) {
   // rows [row0, row1) of the canvas; out / tmask start at row0
   __shared__ TileList tl;
@@ -255,31 +319,42 @@ __global__ void k_mb_accumulate(const BlendImg* __restrict__ imgs, int n, const 
   for (int q = 0; q < nl; ++q) {
     const BlendImg& im = imgs[tl.n < 0 ? q : (int)tl.idx[q]];
     if (!(i >= im.y0 && i <= im.y1 && j >= im.x0 && j <= im.x1)) continue;
-    size_t o = (size_t)im.roi_off + (size_t)(i - im.y0) * im.rw + (j - im.x0);
-    if (mask[o]) continue;
-    float4 cc = cur[o];
-    float w = cc.w;
+    const size_t o = (size_t)(i - im.y0) * im.pitch + (j - im.x0);
+    // the weight plane decides: colours are fetched only where this image contributes
+    const float w = __ldg(cur + im.roi_off + 3 * im.plane + o);
     if (w <= 0) continue;
+    if (mask[im.mask_off + o]) continue;
+    const float* pc = cur + im.roi_off + o;
+    const float c0 = __ldg(pc), c1 = __ldg(pc + im.plane), c2 = __ldg(pc + 2 * im.plane);
     if (!is_last) {
-      float4 cn = next[o];
-      s0 += (cc.x - cn.x) * w; s1 += (cc.y - cn.y) * w; s2 += (cc.z - cn.z) * w;
+      const float* pn = next + im.roi_off + o;
+      const float n0 = __ldg(pn), n1 = __ldg(pn + im.plane), n2 = __ldg(pn + 2 * im.plane);
+      s0 += (c0 - n0) * w; s1 += (c1 - n1) * w; s2 += (c2 - n2) * w;
     } else {
-      s0 += cc.x * w; s1 += cc.y * w; s2 += cc.z * w;
+      s0 += c0 * w; s1 += c1 * w; s2 += c2 * w;
     }
     wsum += w;
   }
   size_t t = (size_t)(i - row0) * tw + j;
   float* p = out + t * 3;
-  bool touched = tmask[t] != 0;
+  bool touched = first ? false : tmask[t] != 0;
+  float v0 = -1.f, v1 = -1.f, v2 = -1.f;
+  if (touched) { v0 = p[0]; v1 = p[1]; v2 = p[2]; }
+  bool dirty = first != 0;
   if (!((double)wsum < 1e-6)) {
     s0 /= wsum; s1 /= wsum; s2 /= wsum;
-    if (!touched) { p[0] = s0; p[1] = s1; p[2] = s2; tmask[t] = 1; touched = true; }
-    else { p[0] += s0; p[1] += s1; p[2] += s2; }
+    if (!touched) { v0 = s0; v1 = s1; v2 = s2; touched = true; }
+    else { v0 += s0; v1 += s1; v2 += s2; }
+    dirty = true;
   }
   if (is_last && touched) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) { float v = p[c] < 1.0f ? p[c] : 1.0f; p[c] = v > 0.f ? v : 0.f; }
+    v0 = v0 < 1.0f ? v0 : 1.0f; v0 = v0 > 0.f ? v0 : 0.f;
+    v1 = v1 < 1.0f ? v1 : 1.0f; v1 = v1 > 0.f ? v1 : 0.f;
+    v2 = v2 < 1.0f ? v2 : 1.0f; v2 = v2 > 0.f ? v2 : 0.f;
+    dirty = true;
   }
+  if (dirty) { p[0] = v0; p[1] = v1; p[2] = v2; }
+  if (first || touched) tmask[t] = touched ? 1 : 0;
 }
 
 __global__ void k_fill(float* __restrict__ p, size_t n, float v) {
@@ -293,19 +368,31 @@ struct BlendJob {
   std::vector<BlendImg> imgs;
   BlendGeom g;
   int tw = 0, th = 0;
-  long long roi_total = 0;
+  long long roi_floats = 0;   // floats of one level buffer (4 planes per image)
+  long long mask_bytes = 0;
   int max_rw = 0, max_rh = 0;
 };
 
-#define BL_LAUNCH(ctx, name, kernel, grid, block, ...)                              \
+#define BL_LAUNCH(ctx, name, kernel, grid, block, smem, ...)                        \
   do {                                                                              \
     (ctx)->launches++;                                                              \
     if ((ctx)->profiling) ctx_prof_begin((ctx), (name));                            \
-    kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);                     \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                \
     if ((ctx)->profiling) ctx_prof_end((ctx));                                      \
     cudaError_t _e = cudaGetLastError();                                            \
     if (_e != cudaSuccess) { rc = ctx_cuda((ctx), _e, name); goto done; }           \
   } while (0)
+
+template <int C>
+static cudaError_t launch_mb_blur_tma(pano_ctx* ctx, int grid, const MbPlane* planes, const int2* span, int n_planes,
+                                      int n_tiles, const TmaDesc* maps, float* dst, const BlurTaps& bt) {
+  constexpr int RX = (C + 3) & ~3, GW = BT_W + 2 * RX, GH = BT_H + 2 * C, GSZ = (GH * GW + 31) & ~31, CS = GW | 1;
+  const size_t smem = (size_t)(2 * GSZ + BT_H * CS + BT_H * (BT_W + 1)) * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(k_mb_blur_tma<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_mb_blur_tma<C><<<grid, BT_THREADS, smem, ctx->stream>>>(planes, span, n_planes, n_tiles, maps, dst, bt);
+  return cudaGetLastError();
+}
 
 static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, const pano_blend_geom* g, int bands,
                         const pano_params* p, float* d_out, int ow, int oh, int row0, int row1) {
@@ -347,8 +434,12 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
     if (d.y0 > d.y1) continue;                         // no row of this image reaches the strip
     memcpy(d.hi, s.homo_inv, sizeof(d.hi));
     d.rw = d.x1 - d.x0 + 1; d.rh = d.y1 - d.y0 + 1;
-    d.roi_off = job.roi_total;
-    job.roi_total += (long long)align_up((size_t)d.rw * d.rh, 32);
+    d.pitch = (int)align_up((size_t)d.rw, 32);
+    d.plane = (long long)d.pitch * d.rh;
+    d.roi_off = job.roi_floats;
+    d.mask_off = job.mask_bytes;
+    job.roi_floats += 4 * d.plane;
+    job.mask_bytes += d.plane;
     job.max_rw = std::max(job.max_rw, d.rw); job.max_rh = std::max(job.max_rh, d.rh);
     job.imgs.push_back(d);
   }
@@ -378,8 +469,11 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
   int rc = 0;
   BlendImg* d_imgs = nullptr;
   double* d_tab = nullptr;
-  float4 *d_cur = nullptr, *d_next = nullptr, *d_tmp = nullptr;
+  float *d_cur = nullptr, *d_next = nullptr;
   unsigned char *d_mask = nullptr, *d_tmask = nullptr;
+  MbPlane* d_planes = nullptr;
+  int2* d_span = nullptr;
+  TmaDesc* d_maps = nullptr;
   cudaError_t e = cudaSuccess;
   if ((rc = ctx_alloc(ctx, (void**)&d_imgs, n * sizeof(BlendImg)))) goto done;
   if ((rc = ctx_alloc(ctx, (void**)&d_tab, std::max<size_t>(tab.size(), 1) * sizeof(double)))) goto done;
@@ -393,58 +487,99 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
   job.g.min_x = g->proj_min_x; job.g.min_y = g->proj_min_y;
   job.g.col_sin = d_tab; job.g.col_cos = d_tab + ncol; job.g.row_tan = d_tab + 2 * ncol;
   {
-    dim3 b(32, 8), gt(ceil_div(tw, 32), ceil_div(th, 8));
+    dim3 b(32, 8);
     if (bands == 0) {
       dim3 gs(ceil_div(tw, 32), ceil_div(row1 - row0, 8));
-      BL_LAUNCH(ctx, "k_linear_blend", k_linear_blend, gs, b, d_imgs, n, job.g, p->lazy_read, p->ordered_input, d_out, tw,
+      BL_LAUNCH(ctx, "k_linear_blend", k_linear_blend, gs, b, 0, d_imgs, n, job.g, p->lazy_read, p->ordered_input, d_out, tw,
                 row0, row1);
     } else {
-      size_t roi = (size_t)job.roi_total;
-      if ((rc = ctx_alloc(ctx, (void**)&d_cur, roi * sizeof(float4)))) goto done;
-      if ((rc = ctx_alloc(ctx, (void**)&d_next, roi * sizeof(float4)))) goto done;
-      if ((rc = ctx_alloc(ctx, (void**)&d_mask, roi))) goto done;
+      const size_t roi = (size_t)job.roi_floats;
+      if ((rc = ctx_alloc(ctx, (void**)&d_cur, roi * sizeof(float)))) goto done;
+      if ((rc = ctx_alloc(ctx, (void**)&d_next, roi * sizeof(float)))) goto done;
+      if ((rc = ctx_alloc(ctx, (void**)&d_mask, (size_t)job.mask_bytes))) goto done;
       const size_t strip_px = (size_t)tw * (row1 - row0);
       // the weight map is needed wherever a clipped ROI has pixels on the canvas
       const int wrow0 = std::max(0, std::max(row0 - halo, clip0)), wrow1 = std::min(th, strip ? row1 + halo : th);
       if ((rc = ctx_alloc(ctx, (void**)&d_tmask, strip_px))) goto done;
-      if ((rc = ctx_zero(ctx, d_tmask, strip_px))) goto done;
+      // plane table of the blur launches: (image, channel) -> offset, size; tiles of 64x32
+      const int n_planes = 4 * n;
+      std::vector<MbPlane> planes(n_planes);
+      std::vector<int2> span(n_planes);
+      int n_tiles = 0;
+      for (int k = 0; k < n; ++k)
+        for (int ch = 0; ch < 4; ++ch) {
+          const BlendImg& im = job.imgs[k];
+          planes[4 * k + ch] = MbPlane{im.roi_off + ch * im.plane, im.rw, im.rh, im.pitch, 0};
+          span[4 * k + ch] = make_int2(n_tiles, ceil_div(im.rw, BT_W));
+          n_tiles += ceil_div(im.rw, BT_W) * ceil_div(im.rh, BT_H);
+        }
+      if (bands > 1) {
+        if ((rc = ctx_alloc(ctx, (void**)&d_planes, n_planes * sizeof(MbPlane)))) goto done;
+        if ((rc = ctx_alloc(ctx, (void**)&d_span, n_planes * sizeof(int2)))) goto done;
+        if ((rc = ctx_put(ctx, d_planes, planes.data(), n_planes * sizeof(MbPlane)))) goto done;
+        if ((rc = ctx_put(ctx, d_span, span.data(), n_planes * sizeof(int2)))) goto done;
+      }
+      // TMA descriptors: one per (plane, level buffer, distinct window half-width)
+      std::vector<int> centers;
+      for (auto& bt : level_taps)
+        if ((bt.center == 6 || bt.center == 9) && std::find(centers.begin(), centers.end(), bt.center) == centers.end())
+          centers.push_back(bt.center);
+      if (!centers.empty()) {
+        std::vector<TmaDesc> maps((size_t)centers.size() * 2 * n_planes);
+        for (size_t ci = 0; ci < centers.size(); ++ci)
+          for (int buf = 0; buf < 2; ++buf)
+            for (int q = 0; q < n_planes; ++q) {
+              const MbPlane& pl = planes[q];
+              const int C = centers[ci];
+              unsigned long long dims[2] = {(unsigned long long)pl.w, (unsigned long long)pl.h};
+              unsigned long long strides[1] = {(unsigned long long)pl.pitch * sizeof(float)};
+              unsigned box[2] = {(unsigned)(BT_W + 2 * ((C + 3) & ~3)), (unsigned)(BT_H + 2 * C)};
+              if ((rc = ctx_tma_encode(ctx, &maps[(ci * 2 + buf) * n_planes + q], (buf ? d_next : d_cur) + pl.off, 2, dims,
+                                       strides, box)))
+                goto done;
+            }
+        if ((rc = ctx_alloc(ctx, (void**)&d_maps, maps.size() * sizeof(TmaDesc)))) goto done;
+        if ((rc = ctx_put(ctx, d_maps, maps.data(), maps.size() * sizeof(TmaDesc)))) goto done;
+      }
       dim3 gr(ceil_div(job.max_rw, 32), ceil_div(job.max_rh, 8), n);
       dim3 gw(ceil_div(tw, 32), ceil_div(wrow1 - wrow0, 8)), gs(ceil_div(tw, 32), ceil_div(row1 - row0, 8));
-      BL_LAUNCH(ctx, "k_mb_first_level", k_mb_first_level, gr, b, d_imgs, job.g, d_cur, d_mask);
-      BL_LAUNCH(ctx, "k_mb_weight_argmax", k_mb_weight_argmax, gw, b, d_imgs, n, d_cur, tw, wrow0, wrow1);
-      {
-        size_t nfl = strip_px * 3;
-        BL_LAUNCH(ctx, "k_fill", k_fill, (unsigned)((nfl + 255) / 256), 256, d_out, nfl, -1.f);
-      }
+      BL_LAUNCH(ctx, "k_mb_first_level", k_mb_first_level, gr, b, 0, d_imgs, job.g, d_cur, d_mask);
+      BL_LAUNCH(ctx, "k_mb_weight_argmax", k_mb_weight_argmax, gw, b, 0, d_imgs, n, d_cur, tw, wrow0, wrow1);
+      int buf = 0;     // which level buffer `d_cur` currently is (0: the first allocation)
       for (int level = 0; level < bands; ++level) {
         int is_last = level == bands - 1;
         if (!is_last) {
           const BlurTaps& bt = level_taps[level];
-          const int kw = 2 * bt.center + 1;
-          {
-            const int c = bt.center;
-            const size_t smem = sizeof(float4) * ((size_t)(MB_TH + 2 * c) * (MB_TW + 2 * c) + (size_t)MB_TH * (MB_TW + 2 * c));
-            if (smem > 200 * 1024) { rc = ctx_fail(ctx, PANO_ERR_INVALID, "blend: gaussian window %d too wide", kw); goto done; }
-            e = cudaFuncSetAttribute(k_mb_blur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) { rc = ctx_cuda(ctx, e, "k_mb_blur attribute"); goto done; }
-            dim3 gb(ceil_div(job.max_rw, MB_TW), ceil_div(job.max_rh, MB_TH), n);
-            ctx->launches++;
-            if (ctx->profiling) ctx_prof_begin(ctx, "k_mb_blur");
-            k_mb_blur<<<gb, 256, smem, ctx->stream>>>(d_imgs, d_cur, d_next, bt);
-            if (ctx->profiling) ctx_prof_end(ctx);
-            e = cudaGetLastError();
-            if (e != cudaSuccess) { rc = ctx_cuda(ctx, e, "k_mb_blur"); goto done; }
+          const int c = bt.center;
+          ctx->launches++;
+          if (ctx->profiling) ctx_prof_begin(ctx, "k_mb_blur");
+          auto ci = std::find(centers.begin(), centers.end(), c);
+          if (ci != centers.end()) {
+            const TmaDesc* maps = d_maps + ((size_t)(ci - centers.begin()) * 2 + buf) * n_planes;
+            const int grid = std::min(n_tiles, ctx->num_sms * 3);
+            e = c == 6 ? launch_mb_blur_tma<6>(ctx, grid, d_planes, d_span, n_planes, n_tiles, maps, d_next, bt)
+                       : launch_mb_blur_tma<9>(ctx, grid, d_planes, d_span, n_planes, n_tiles, maps, d_next, bt);
+          } else {
+            const size_t smem = sizeof(float) * ((size_t)(MB_TH + 2 * c) * (MB_TW + 2 * c) + (size_t)MB_TH * (MB_TW + 2 * c));
+            if (smem > 200 * 1024) { rc = ctx_fail(ctx, PANO_ERR_INVALID, "blend: gaussian window %d too wide", 2 * c + 1); goto done; }
+            e = cudaFuncSetAttribute(k_mb_blur_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) {
+              k_mb_blur_generic<<<n_tiles, 256, smem, ctx->stream>>>(d_planes, d_span, n_planes, d_cur, d_next, bt);
+              e = cudaGetLastError();
+            }
           }
+          if (ctx->profiling) ctx_prof_end(ctx);
+          if (e != cudaSuccess) { rc = ctx_cuda(ctx, e, "k_mb_blur"); goto done; }
         }
-        BL_LAUNCH(ctx, "k_mb_accumulate", k_mb_accumulate, gs, b, d_imgs, n, d_cur, d_next, d_mask, is_last, d_out,
-                  d_tmask, tw, row0, row1);
-        if (!is_last) std::swap(d_cur, d_next);
+        BL_LAUNCH(ctx, "k_mb_accumulate", k_mb_accumulate, gs, b, 0, d_imgs, n, d_cur, d_next, d_mask, level == 0 ? 1 : 0, is_last,
+                  d_out, d_tmask, tw, row0, row1);
+        if (!is_last) { std::swap(d_cur, d_next); buf ^= 1; }
       }
     }
   }
 done:
-  ctx_free(ctx, d_imgs); ctx_free(ctx, d_tab); ctx_free(ctx, d_cur); ctx_free(ctx, d_next); ctx_free(ctx, d_tmp);
-  ctx_free(ctx, d_mask); ctx_free(ctx, d_tmask);
+  ctx_free(ctx, d_imgs); ctx_free(ctx, d_tab); ctx_free(ctx, d_cur); ctx_free(ctx, d_next);
+  ctx_free(ctx, d_mask); ctx_free(ctx, d_tmask); ctx_free(ctx, d_planes); ctx_free(ctx, d_span); ctx_free(ctx, d_maps);
   return rc;
 }
 

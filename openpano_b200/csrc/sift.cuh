@@ -31,26 +31,6 @@ struct OctMeta {
   long long plane;      // floats per plane = pitch * h
 };
 
-struct BlurTile { int om; int tx, ty; };
-
-#ifdef __CUDACC__
-// CTA index -> (octave entry, tile x, tile y): binary search over the ascending tile_base
-// of the n_om octave entries (the table is a few KB and L1-resident), so that no per-tile
-// table has to be uploaded.
-// span[k] = (first tile of octave entry k, tiles per tile row)
-__device__ __forceinline__ BlurTile find_blur_tile(const int2* __restrict__ span, int n_om, int cta) {
-  int lo = 0, hi = n_om - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (span[mid].x <= cta) lo = mid; else hi = mid - 1;
-  }
-  const int local = cta - span[lo].x, tx_n = span[lo].y;
-  BlurTile t;
-  t.om = lo; t.ty = local / tx_n; t.tx = local - t.ty * tx_n;
-  return t;
-}
-#endif
-
 struct GaussTable {
   int nlev;
   int rmax;

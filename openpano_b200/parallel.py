@@ -181,14 +181,18 @@ class DistributedStitcher:
         self.eng = engine
         self.params = params or default_params()
         self.ms = {}
+        self.host_ms = {}         # host wall time spent inside each phase's calls (launch / sync overhead)
         self._side = None
 
     def _timed(self, name, fn):
+        import time
         import torch
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         out = fn()
         e1.record()
+        self.host_ms[name] = self.host_ms.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
         self._events.append((name, e0, e1))
         return out
 
@@ -214,6 +218,7 @@ class DistributedStitcher:
         rgb8 = owned_pix is not None
         assert sorted(owned_pix if rgb8 else owned) == mine, "images must follow shard_images()"
         self._events = []
+        self.host_ms = {}
         main = torch.cuda.current_stream()
         if self._side is None:
             self._side = torch.cuda.Stream()

@@ -392,7 +392,7 @@ def run_sharded(eng, rank, world, params, cfg_name="unordered_38x1300x867", band
         if rep > 0 and (best is None or t.item() < best[0]):
             phases = torch.tensor([ds.ms.get(k, 0.0) for k in ds.PHASES], device="cuda")
             dist.all_reduce(phases, op=dist.ReduceOp.MAX)
-            best = (t.item(), dict(zip(ds.PHASES, [float(x) for x in phases.tolist()])))
+            best = (t.item(), dict(zip(ds.PHASES, [float(x) for x in phases.tolist()])), dict(ds.host_ms))
     res = None
     if rank == 0:
         all_pix = [torch.from_numpy(p).cuda() for p in pix]
@@ -420,7 +420,8 @@ def run_sharded(eng, rank, world, params, cfg_name="unordered_38x1300x867", band
         limiting = max(best[1], key=best[1].get)
         res = {"workload": f"{cfg_name}: {n} images, {len(pairs)} pairs, bands {bands}", "n_gpus": world,
                "partition": "images k mod G -> C1 all-gather(descriptors) -> pairs dealt by N_i*N_j -> canvas row strips -> C2 all-gather(strips)",
-               "ms_sharded": best[0], "phase_ms_max_over_ranks": best[1], "limiting_phase": limiting,
+               "ms_sharded": best[0], "phase_ms_max_over_ranks": best[1], "phase_host_ms_rank0": best[2],
+               "limiting_phase": limiting,
                "ms_one_gpu": one_ms, "efficiency_vs_one_gpu": one_ms / (world * best[0]),
                "speedup_vs_one_gpu": one_ms / best[0], "value": mpx / (best[0] * 1e-3), "unit": "Mpx/s",
                "matches": int(sum(len(m) for m in matches)), "matches_identical": bool(same_m),
