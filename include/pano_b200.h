@@ -167,6 +167,11 @@ int pano_featureset_count(pano_featureset* fs, int image);
 /* Copies image i's results to host: coor_xy (2·n f64) and desc (128·n f32);
  * either may be NULL. */
 int pano_featureset_download(pano_featureset* fs, int image, double* coor_xy, float* desc);
+/* SIFT sets only: image i's keypoints as SIFTDetector::do_detect_feature returns them
+ * (feature/sift.cc:150, Descriptor::coor = SSPoint::real_coor in [0,1)), i.e. BEFORE
+ * FeatureDetector::detect_feature scales them to image-centred pixels (feature.cc:20-28).
+ * A FeatureDetector subclass returns these and lets the base class do its scaling. */
+int pano_featureset_download_real(pano_featureset* fs, int image, double* real_xy);
 void pano_featureset_free(pano_featureset* fs);
 
 /* --------------------------------------------------------------- matching
@@ -196,6 +201,25 @@ int  pano_match_pairs_dev(pano_ctx* ctx, pano_featureset* fs, int n_pairs,
 int  pano_match_bruteforce(pano_ctx* ctx, const float* desc_a, int n,
                            const float* desc_b, int m, const pano_params* p,
                            int* pairs_out, int* n_pairs_out);
+
+/* ------------------------------------------------- RANSAC inlier scoring
+ * Replaces the scoring half of TransformEstimation::get_transform
+ * (stitch/transform_estimate.cc:68-85): get_inliers (:132-148) for every hypothesis
+ * of every pair, the FIRST hypothesis with the largest inlier count (update_max,
+ * lib/utils.hh:58-63) and its inlier flags.  Hypothesis generation (sampling with
+ * the caller's seeded generator + the normalised DLT, :89-130) stays on the host. */
+typedef struct pano_ransac_pair {
+  int n_match;
+  const double* kp1_xy;   /* 2*n_match: kp1[match.data[i].first]  (image-centred pixels) */
+  const double* kp2_xy;   /* 2*n_match: kp2[match.data[i].second] */
+  int n_hyp;
+  const double* homos;    /* 9*n_hyp: Homography::data, row-major, image 2 -> image 1 */
+  float inlier_thres;     /* ransac_inlier_thres (transform_estimate.cc:47) */
+} pano_ransac_pair;
+/* best_hyp[k] (-1 when pair k has no hypothesis), best_count[k]; hyp_counts[k] (n_hyp ints)
+ * and inlier_flags[k] (n_match bytes) are optional per pair (array or entries may be NULL). */
+int pano_ransac_score_pairs(pano_ctx* ctx, int n_pairs, const pano_ransac_pair* pairs, int* best_hyp,
+                            int* best_count, int* const* hyp_counts, unsigned char* const* inlier_flags);
 
 /* ---------------------------------------------------------- cylinder warp
  * Replaces CylinderWarper(h_factor).warp(Mat32f&, vector<Vec2D>&)

@@ -85,4 +85,14 @@ class PanoMatches(C.Structure):
     ]
 
 
+class PanoRansacPair(C.Structure):
+    _fields_ = [
+        ("n_match", C.c_int),
+        ("kp1_xy", C.c_void_p), ("kp2_xy", C.c_void_p),
+        ("n_hyp", C.c_int),
+        ("homos", C.c_void_p),
+        ("inlier_thres", C.c_float),
+    ]
+
+
 PROJ_FLAT, PROJ_CYLINDRICAL, PROJ_SPHERICAL = 0, 1, 2

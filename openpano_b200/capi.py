@@ -11,7 +11,7 @@ from pathlib import Path
 
 import numpy as np
 
-from ._abi import (PanoBlendGeom, PanoBlendImage, PanoMatches, PanoParams, PanoSSPoint,
+from ._abi import (PanoBlendGeom, PanoBlendImage, PanoMatches, PanoParams, PanoRansacPair, PanoSSPoint,
                    default_params)
 
 LIB_PATH = Path(__file__).resolve().parent / "libpano_b200.so"
@@ -59,11 +59,13 @@ def _load():
         "pano_featureset_num_images": (C.c_int, [C.c_void_p]),
         "pano_featureset_count": (C.c_int, [C.c_void_p, C.c_int]),
         "pano_featureset_download": (C.c_int, [C.c_void_p, C.c_int, _dp, _fp]),
+        "pano_featureset_download_real": (C.c_int, [C.c_void_p, C.c_int, _dp]),
         "pano_featureset_free": (None, [C.c_void_p]),
         "pano_match_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _ip, P, C.POINTER(PanoMatches)]),
         "pano_matches_free": (None, [C.POINTER(PanoMatches)]),
         "pano_match_pairs_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _ip, P, _ip]),
         "pano_match_bruteforce": (C.c_int, [C.c_void_p, _fp, C.c_int, _fp, C.c_int, P, _ip, _ip]),
+        "pano_ransac_score_pairs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PanoRansacPair), _ip, _ip, _vpp, _vpp]),
         "pano_cyl_warp_shape": (C.c_int, [C.c_int, C.c_int, C.c_double, P, _ip, _ip, _dp, _dp]),
         "pano_cyl_warp": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, C.c_double, P, _fp, C.c_int,
                                     C.c_int, _dp, C.c_int]),
@@ -433,6 +435,28 @@ class Engine:
         self._check(LIB.pano_match_bruteforce(self._h, _f(a), len(a), _f(b), len(b), C.byref(params),
                                               _i(pairs), C.byref(n)))
         return pairs[:n.value].copy()
+
+    # -- RANSAC inlier scoring
+    def ransac_score_pairs(self, pairs):
+        """pairs: list of (kp1_xy [n,2] f64, kp2_xy [n,2] f64, homos [m,9] f64, inlier_thres).
+        Returns per pair (best_hyp, best_count, hyp_counts int32[m], inlier_flags uint8[n])."""
+        n = len(pairs)
+        arr = (PanoRansacPair * max(n, 1))()
+        keep, counts, flags = [], [], []
+        for k, (a, b, h, thr) in enumerate(pairs):
+            a = np.ascontiguousarray(a, np.float64).reshape(-1, 2)
+            b = np.ascontiguousarray(b, np.float64).reshape(-1, 2)
+            h = np.ascontiguousarray(h, np.float64).reshape(-1, 9)
+            keep.append((a, b, h))
+            arr[k].n_match, arr[k].kp1_xy, arr[k].kp2_xy = len(a), a.ctypes.data, b.ctypes.data
+            arr[k].n_hyp, arr[k].homos, arr[k].inlier_thres = len(h), h.ctypes.data, thr
+            counts.append(np.zeros(max(len(h), 1), np.int32))
+            flags.append(np.zeros(max(len(a), 1), np.uint8))
+        best, bcnt = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+        cp = (C.c_void_p * max(n, 1))(*[c.ctypes.data for c in counts])
+        fp = (C.c_void_p * max(n, 1))(*[f.ctypes.data for f in flags])
+        self._check(LIB.pano_ransac_score_pairs(self._h, n, arr, _i(best), _i(bcnt), cp, fp))
+        return [(int(best[k]), int(bcnt[k]), counts[k][:len(keep[k][2])], flags[k][:len(keep[k][0])]) for k in range(n)]
 
     # -- cylinder warp
     @staticmethod

@@ -171,18 +171,24 @@ __global__ void k_mb_weight_argmax(const BlendImg* __restrict__ imgs, int n, flo
   int i = row0 + blockIdx.y * blockDim.y + threadIdx.y;
   if (j >= tw || i >= row1) return;
   const int nl = tl.n < 0 ? n : tl.n;
+  // Two passes so that the weight loads of all covering images are in flight together: a
+  // store into `cur` between two loads from it would order them (the compiler cannot prove the
+  // planes disjoint), and the kernel then crawls through one DRAM round trip per image.
+  // Every location is read and written by this thread only, so the read-only path is safe.
   float mx = 0.f;
-  float* best = nullptr;
+  int best = -1;
   for (int q = 0; q < nl; ++q) {
     const BlendImg& im = imgs[tl.n < 0 ? q : (int)tl.idx[q]];
     if (i >= im.y0 && i <= im.y1 && j >= im.x0 && j <= im.x1) {
-      float* wp = cur + im.roi_off + 3 * im.plane + (size_t)(i - im.y0) * im.pitch + (j - im.x0);
-      const float w = *wp;
-      if (w > mx) { mx = w; best = wp; }
-      *wp = 0.f;
+      const float w = __ldg(cur + im.roi_off + 3 * im.plane + (size_t)(i - im.y0) * im.pitch + (j - im.x0));
+      if (w > mx) { mx = w; best = q; }
     }
   }
-  if (best) *best = 1.f;
+  for (int q = 0; q < nl; ++q) {
+    const BlendImg& im = imgs[tl.n < 0 ? q : (int)tl.idx[q]];
+    if (i >= im.y0 && i <= im.y1 && j >= im.x0 && j <= im.x1)
+      cur[im.roi_off + 3 * im.plane + (size_t)(i - im.y0) * im.pitch + (j - im.x0)] = q == best ? 1.f : 0.f;
+  }
 }
 
 // gaussian.hh:29-90 on WeightedPixel: every channel of the pixel goes through the same
@@ -196,11 +202,12 @@ struct MbPlane { long long off; int w, h, pitch, pad; };   // one (image, channe
 // line buffers replicate the ROI edge (gaussian.hh:52-58,74-81): border tiles patch those cells
 // from the staged in-range ones.
 template <int C>
-__global__ void __launch_bounds__(BT_THREADS, 3)
+__global__ void __launch_bounds__(BT_THREADS, 4)
 k_mb_blur_tma(const MbPlane* __restrict__ planes, const int2* __restrict__ span, int n_planes, int n_tiles,
               const TmaDesc* __restrict__ maps, float* __restrict__ dst, const __grid_constant__ BlurTaps bt) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ BlurTile s_tile[2];                   // looked up once per tile by thread 0 (binary search)
   constexpr int RX = (C + 3) & ~3;                 // TMA box origin: 16-byte aligned columns
   constexpr int GW = BT_W + 2 * RX, GH = BT_H + 2 * C;
   constexpr int GSZ = (GH * GW + 31) & ~31;
@@ -210,26 +217,28 @@ k_mb_blur_tma(const MbPlane* __restrict__ planes, const int2* __restrict__ span,
   float* outT = colbuf + BT_H * CS;
   const int tid = threadIdx.x;
   constexpr uint32_t tile_bytes = (uint32_t)(GH * GW * sizeof(float));
+  int t = blockIdx.x;
   if (tid == 0) {
     sbar_init(sm_u32(&s_bar[0]), 1);
     sbar_init(sm_u32(&s_bar[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (t < n_tiles) {
+      const BlurTile tl = find_blur_tile(span, n_planes, t);
+      s_tile[0] = tl;
+      sbar_expect_tx(sm_u32(&s_bar[0]), tile_bytes);
+      tma_load_2d(sm_u32(grey0), maps + tl.om, tl.tx * BT_W - RX, tl.ty * BT_H - C, sm_u32(&s_bar[0]));
+    }
   }
   __syncthreads();
-  int t = blockIdx.x;
-  if (tid == 0 && t < n_tiles) {
-    const BlurTile tl = find_blur_tile(span, n_planes, t);
-    sbar_expect_tx(sm_u32(&s_bar[0]), tile_bytes);
-    tma_load_2d(sm_u32(grey0), maps + tl.om, tl.tx * BT_W - RX, tl.ty * BT_H - C, sm_u32(&s_bar[0]));
-  }
   for (int it = 0; t < n_tiles; t += gridDim.x, ++it) {
     const int b = it & 1;
     float* grey = grey0 + b * GSZ;
-    const BlurTile tl = find_blur_tile(span, n_planes, t);
+    const BlurTile tl = s_tile[b];
     const MbPlane pl = planes[tl.om];
     const int x0 = tl.tx * BT_W, y0 = tl.ty * BT_H;
     if (tid == 0 && t + (int)gridDim.x < n_tiles) {
       const BlurTile nx = find_blur_tile(span, n_planes, t + gridDim.x);
+      s_tile[b ^ 1] = nx;      // read by everyone after the barrier that ends this iteration
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       sbar_expect_tx(sm_u32(&s_bar[b ^ 1]), tile_bytes);
       tma_load_2d(sm_u32(grey0 + (b ^ 1) * GSZ), maps + nx.om, nx.tx * BT_W - RX, nx.ty * BT_H - C, sm_u32(&s_bar[b ^ 1]));
@@ -556,7 +565,7 @@ static int blend_device(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
           auto ci = std::find(centers.begin(), centers.end(), c);
           if (ci != centers.end()) {
             const TmaDesc* maps = d_maps + ((size_t)(ci - centers.begin()) * 2 + buf) * n_planes;
-            const int grid = std::min(n_tiles, ctx->num_sms * 3);
+            const int grid = std::min(n_tiles, ctx->num_sms * 4);
             e = c == 6 ? launch_mb_blur_tma<6>(ctx, grid, d_planes, d_span, n_planes, n_tiles, maps, d_next, bt)
                        : launch_mb_blur_tma<9>(ctx, grid, d_planes, d_span, n_planes, n_tiles, maps, d_next, bt);
           } else {

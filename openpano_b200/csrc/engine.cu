@@ -530,7 +530,7 @@ static void featureset_release(pano_featureset* fs) {
   if (!fs) return;
   pano_ctx* ctx = fs->ctx;
   if (ctx) {
-    ctx_free(ctx, fs->d_desc); ctx_free(ctx, fs->d_coor); ctx_free(ctx, fs->d_count);
+    ctx_free(ctx, fs->d_desc); ctx_free(ctx, fs->d_coor); ctx_free(ctx, fs->d_count);   // d_real lives inside d_coor
     ctx_free(ctx, fs->owned_block);
     tc_release(ctx, &fs->tc);
   }
@@ -717,6 +717,21 @@ int pano_featureset_download(pano_featureset* fs, int image, double* coor_xy, fl
   return PANO_OK;
 }
 
+int pano_featureset_download_real(pano_featureset* fs, int image, double* real_xy) {
+  if (fs) ctx_enter(fs->ctx);
+  if (!fs || image < 0 || image >= fs->n_images || !real_xy) return PANO_ERR_INVALID;
+  int rc = featureset_sync_counts(fs);
+  if (rc) return rc;
+  pano_ctx* ctx = fs->ctx;
+  if (!fs->d_real) return ctx_fail(ctx, PANO_ERR_INVALID, "featureset was not produced by pano_sift_detect*");
+  const int n = fs->h_count[image];
+  if (n == 0) return PANO_OK;
+  PANO_CUDA(ctx, cudaMemcpyAsync(real_xy, fs->d_real + fs->base[image] * 2, (size_t)n * 2 * sizeof(double),
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+  PANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PANO_OK;
+}
+
 void pano_featureset_free(pano_featureset* fs) {
   if (fs) ctx_enter(fs->ctx); featureset_release(fs); }
 
@@ -748,7 +763,7 @@ int pano_sift_trace_run(pano_ctx* ctx, const float* rgb, int w, int h, const pan
     if (rc == PANO_ERR_CAPACITY && cap < SIFT_CAP_MAX) {
       sift_work_free(ctx, wk); wk = nullptr;
       ctx_free(ctx, fs->d_desc); ctx_free(ctx, fs->d_coor); ctx_free(ctx, fs->d_count);
-      fs->d_desc = nullptr; fs->d_coor = nullptr; fs->d_count = nullptr; fs->error = 0;
+      fs->d_desc = nullptr; fs->d_coor = nullptr; fs->d_real = nullptr; fs->d_count = nullptr; fs->error = 0;
       continue;
     }
     break;

@@ -275,38 +275,44 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
       const int as = t & 1;
       mbar_wait(smem_u32(&bars->acc_full[as]), (uint32_t)(t >> 1) & 1u);
       tc_fence_after();
+      int k1 = 0x7fffffff, k2 = 0x7fffffff;
 #pragma unroll
       for (int c0 = 0; c0 < 256; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(lane_addr + (uint32_t)(as * 256 + c0), v);
         tmem_ld_wait();
-        // Scores are positive floats (q.t >= ~1), so they order like ints.  Only a score below the
-        // row's running second best (FILTER: below its threshold key) can matter: one subtract and
-        // one funnel shift per element collect those sign bits into a mask (bit 31-j <-> column j);
-        // the rare set bits are then handled one by one.  (A conditional body inside the 32-way
-        // unrolled compare blows the loop up past the instruction cache: measured 3x slower.)
-        const int lim = FILTER ? thr + 1 : g2;            // FILTER keeps `<= thr`; g2 has its low 8 bits clear
-        unsigned hit = 0;
+        if (FILTER) {
+          // branch-free hit mask first: a conditional body inside the 256-way unrolled compare
+          // blows the loop up past the instruction cache (measured 3x slower per tile)
+          unsigned hit = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) hit = __funnelshift_l((unsigned)((int)v[j] - lim), hit, 1);
-        while (hit) {
-          const int j = 31 - (__ffs(hit) - 1);            // ascending j = descending bit
-          hit &= hit - 1;
-          const int col = t * 256 + c0 + j;
-          if (FILTER) {
+          for (int j = 0; j < 32; ++j) hit |= ((int)(v[j] & 0xffffff00u) <= thr) ? (1u << j) : 0u;
+          while (hit) {
+            const int j = __ffs(hit) - 1;
+            hit &= hit - 1;
+            const int col = t * 256 + c0 + j;
             if (col < tk.t_n) {
               const int slot = atomicAdd(&cand_cnt[grow], 1);
               if (slot < TC_CAND_CAP) cand[(size_t)grow * TC_CAND_CAP + slot] = col;
             }
-          } else {
-            const int tv = (int)(v[j] & 0xffffff00u);
-            if (tv < g1) { g2 = g1; g1 = tv; gi = col; }
-            else if (tv < g2) g2 = tv;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int key = (int)((v[j] & 0xffffff00u) | (uint32_t)(c0 + j));
+            k2 = min(k2, max(k1, key));
+            k1 = min(k1, key);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->acc_empty[as]));
+      if (!FILTER) {
+        // merge the tile's top-2 into the running top-2
+        const int v1 = k1 & (int)0xffffff00, v2 = k2 & (int)0xffffff00;
+        if (v1 < g1) { g2 = min(g1, v2); g1 = v1; gi = t * 256 + (k1 & 0xff); }
+        else g2 = min(g2, v1);
+      }
     }
     const int qrow = tk.q_row0 + row;
     if (!FILTER && qrow < tk.q_n) {

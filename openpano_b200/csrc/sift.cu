@@ -152,6 +152,7 @@ k_blur_dog_fast(const OctMeta* __restrict__ octs, const int2* __restrict__ span,
                 const TmaDesc* __restrict__ maps, float* __restrict__ arena, const __grid_constant__ GaussTable gt) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ BlurTile s_tile[2];         // looked up once per tile by thread 0 (binary search)
   const int R = gt.rmax;
   // TMA wants the box origin on a 16-byte boundary of the innermost dimension (a box starting
   // at x0 - 6 faults): the staged tile carries a column halo rounded up to 4 floats.
@@ -164,28 +165,30 @@ k_blur_dog_fast(const OctMeta* __restrict__ octs, const int2* __restrict__ span,
   float* outT = colbuf + BT_H * CS;      // [BT_H][BT_W+1]
   const int tid = threadIdx.x;
   const uint32_t tile_bytes = (uint32_t)(GH * GW * sizeof(float));
+  int t = blockIdx.x;
   if (tid == 0) {
     sbar_init(sm_u32(&s_bar[0]), 1);
     sbar_init(sm_u32(&s_bar[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (t < n_tiles) {
+      const BlurTile tl = find_blur_tile(span, n_om, t);
+      s_tile[0] = tl;
+      sbar_expect_tx(sm_u32(&s_bar[0]), tile_bytes);
+      tma_load_2d(sm_u32(grey0), maps + tl.om, tl.tx * BT_W - RX, tl.ty * BT_H - R, sm_u32(&s_bar[0]));
+    }
   }
   __syncthreads();
-  int t = blockIdx.x;
-  if (tid == 0 && t < n_tiles) {
-    const BlurTile tl = find_blur_tile(span, n_om, t);
-    sbar_expect_tx(sm_u32(&s_bar[0]), tile_bytes);
-    tma_load_2d(sm_u32(grey0), maps + tl.om, tl.tx * BT_W - RX, tl.ty * BT_H - R, sm_u32(&s_bar[0]));
-  }
   for (int it = 0; t < n_tiles; t += gridDim.x, ++it) {
     const int b = it & 1;
     float* grey = grey0 + b * GSZ;
-    const BlurTile tl = find_blur_tile(span, n_om, t);
+    const BlurTile tl = s_tile[b];
     const OctMeta om = octs[tl.om];
     const int x0 = tl.tx * BT_W, y0 = tl.ty * BT_H;
     if (tid == 0 && t + (int)gridDim.x < n_tiles) {
       // the other buffer was last read (and patched) in the previous iteration, which every
       // thread has left through the barrier at the end of the loop body
       const BlurTile nx = find_blur_tile(span, n_om, t + gridDim.x);
+      s_tile[b ^ 1] = nx;      // read by everyone after the barrier that ends this iteration
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       sbar_expect_tx(sm_u32(&s_bar[b ^ 1]), tile_bytes);
       tma_load_2d(sm_u32(grey0 + (b ^ 1) * GSZ), maps + nx.om, nx.tx * BT_W - RX, nx.ty * BT_H - R, sm_u32(&s_bar[b ^ 1]));
@@ -929,6 +932,10 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
       if (lane == 0) {
         out_coor[dslot * 2] = (p.real_x - 0.5) * im.in_w;
         out_coor[dslot * 2 + 1] = (p.real_y - 0.5) * im.in_h;
+        // second half of the coordinate buffer: SSPoint::real_coor, what do_detect_feature returns (sift.cc:150)
+        double* out_real = out_coor + (size_t)n_img * cap * 2;
+        out_real[dslot * 2] = p.real_x;
+        out_real[dslot * 2 + 1] = p.real_y;
       }
       __syncwarp();
     }
@@ -1089,7 +1096,8 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
   // featureset outputs (per-image capacity `cap`; compact on download)
   fs->ctx = ctx; fs->n_images = n; fs->cap = cap;
   SIFT_TRY(ctx_alloc(ctx, (void**)&fs->d_desc, nlist * 128 * sizeof(float)));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&fs->d_coor, nlist * 2 * sizeof(double)));
+  SIFT_TRY(ctx_alloc(ctx, (void**)&fs->d_coor, nlist * 4 * sizeof(double)));   // scaled coordinates, then real_coor
+  fs->d_real = fs->d_coor + nlist * 2;
   SIFT_TRY(ctx_alloc(ctx, (void**)&fs->d_count, n * sizeof(int)));
   fs->base.resize(n);
   for (int i = 0; i < n; ++i) fs->base[i] = (long long)i * cap;
@@ -1223,7 +1231,7 @@ int featureset_sync_counts(pano_featureset* fs) {
       return fs->error = ctx_fail(ctx, PANO_ERR_CAPACITY, "sift: %d list entries in one image exceed the capacity %d", worst, fs->cap);
     // run again with larger lists; the old outputs go back to the pool in stream order
     ctx_free(ctx, fs->d_desc); ctx_free(ctx, fs->d_coor); ctx_free(ctx, fs->d_count);
-    fs->d_desc = nullptr; fs->d_coor = nullptr; fs->d_count = nullptr;
+    fs->d_desc = nullptr; fs->d_coor = nullptr; fs->d_real = nullptr; fs->d_count = nullptr;
     ctx->sift_cap = cap;
     const std::vector<const float*> src = fs->src;
     int rc = sift_run_batch(ctx, n, src.data(), fs->src_w.data(), fs->src_h.data(), &fs->src_params, fs, nullptr, cap);

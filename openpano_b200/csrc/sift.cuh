@@ -71,6 +71,7 @@ struct pano_featureset {
   int n_images = 0;
   float* d_desc = nullptr;    // rows of 128 f32
   double* d_coor = nullptr;   // rows of 2 f64 (may be null for uploaded sets)
+  double* d_real = nullptr;   // SIFT sets: unscaled real_coor in [0,1), rows of 2 f64 (second half of d_coor's block)
   int* d_count = nullptr;     // [n_images]
   std::vector<long long> base;  // first row of image i
   std::vector<int> h_count;

@@ -62,6 +62,13 @@ extern "C" {
   int  P##_crop(const float* mat_hwc, int w, int h, int* rect, float* out_hwc);        \
   /* write_rgb's conversion to 8-bit (imgio.cc:98-113) */                              \
   int  P##_write_rgb8(const float* mat_hwc, int w, int h, unsigned char* out);         \
+  /* RANSAC inlier scoring (transform_estimate.cc:68-85,132-148): inlier count of every   \
+   * hypothesis (9 doubles each, image 2 -> image 1), first hypothesis with the largest   \
+   * count, its inlier flags.  kp*_xy: the matched coordinates, 2 doubles per match. */   \
+  int  P##_ransac_score(int n_match, const double* kp1_xy, const double* kp2_xy,         \
+                        int n_hyp, const double* homos, float inlier_thres,              \
+                        int* hyp_counts, int* best_hyp, int* best_count,                 \
+                        unsigned char* inlier_flags);                                    \
   /* number of host threads the library will use (1 for the scalar port) */            \
   int  P##_num_threads(void);
 

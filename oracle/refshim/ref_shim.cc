@@ -32,6 +32,9 @@
 #include "stitch/multiband.hh"
 #include "stitch/projection.hh"
 #include "stitch/homography.hh"
+#define private public          // get_inliers / ransac_inlier_thres are private members of TransformEstimation
+#include "stitch/transform_estimate.hh"
+#undef private
 
 #include "../oracle_api.h"
 
@@ -329,6 +332,40 @@ int ref_hotpath(int n, const float* const* rgb, const int* w, const int* h, int 
   int rc = ref_blend(n, bimgs, g, bands, p, out, ow, oh);
   seconds[2] = t2.duration();
   return rc;
+}
+
+// TransformEstimation::get_inliers itself (transform_estimate.cc:132-148), driven like the loop
+// of get_transform (:68-85) with caller-supplied hypotheses.
+int ref_ransac_score(int n_match, const double* kp1_xy, const double* kp2_xy, int n_hyp, const double* homos,
+                     float inlier_thres, int* hyp_counts, int* best_hyp, int* best_count, unsigned char* inlier_flags) {
+  MatchData md;
+  std::vector<Vec2D> kp1(n_match), kp2(n_match);
+  for (int i = 0; i < n_match; ++i) {
+    md.data.emplace_back(i, i);
+    kp1[i] = Vec2D(kp1_xy[2 * i], kp1_xy[2 * i + 1]);
+    kp2[i] = Vec2D(kp2_xy[2 * i], kp2_xy[2 * i + 1]);
+  }
+  *best_hyp = -1; *best_count = 0;
+  if (inlier_flags) memset(inlier_flags, 0, n_match);
+  if (n_match < 8) return n_hyp > 0 ? -1 : 0;          // the constructor leaves f2_homo_coor empty below 8 matches
+  TransformEstimation te(md, kp1, kp2, Shape2D{800, 800}, Shape2D{800, 800});
+  te.ransac_inlier_thres = inlier_thres;
+  int maxcnt = -1;
+  for (int k = 0; k < n_hyp; ++k) {
+    double arr[9];
+    memcpy(arr, homos + 9 * (size_t)k, sizeof(arr));
+    int cnt = (int)te.get_inliers(Homography(arr)).size();
+    if (hyp_counts) hyp_counts[k] = cnt;
+    if (update_max(maxcnt, cnt)) *best_hyp = k;
+  }
+  if (*best_hyp >= 0) {
+    double arr[9];
+    memcpy(arr, homos + 9 * (size_t)*best_hyp, sizeof(arr));
+    std::vector<int> in = te.get_inliers(Homography(arr));
+    *best_count = (int)in.size();
+    if (inlier_flags) for (int i : in) inlier_flags[i] = 1;
+  }
+  return 0;
 }
 
 }  // extern "C"

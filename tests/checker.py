@@ -150,6 +150,8 @@ class Checker:
         fn("hotpath").argtypes = [C.c_int, C.POINTER(C.c_void_p), _ip, _ip, C.c_int, _ip, C.c_int,
                                   C.POINTER(PanoBlendImage), C.POINTER(PanoBlendGeom), C.c_int,
                                   C.POINTER(PanoParams), _fp, C.c_int, C.c_int, _ip, _ip, _dp]
+        _ubp = C.POINTER(C.c_ubyte)
+        fn("ransac_score").argtypes = [C.c_int, _dp, _dp, C.c_int, _dp, C.c_float, _ip, _ip, _ip, _ubp]
         fn("num_threads").restype = C.c_int
         _up = C.POINTER(C.c_ubyte)
         fn("read_img_rgb8").argtypes = [_up, C.c_int, C.c_int, C.c_int, _fp]
@@ -186,6 +188,19 @@ class Checker:
         rc = self._fn("write_rgb8")(_f(mat), w, h, out.ctypes.data_as(C.POINTER(C.c_ubyte)))
         assert rc == 0
         return out
+
+    def ransac_score(self, kp1, kp2, homos, thres):
+        """Returns (best_hyp, best_count, hyp_counts, inlier_flags) as TransformEstimation would pick them."""
+        kp1 = np.ascontiguousarray(kp1, np.float64).reshape(-1, 2)
+        kp2 = np.ascontiguousarray(kp2, np.float64).reshape(-1, 2)
+        homos = np.ascontiguousarray(homos, np.float64).reshape(-1, 9)
+        counts = np.zeros(max(len(homos), 1), np.int32)
+        flags = np.zeros(max(len(kp1), 1), np.uint8)
+        best, bcnt = C.c_int(), C.c_int()
+        rc = self._fn("ransac_score")(len(kp1), _d(kp1), _d(kp2), len(homos), _d(homos), thres, _i(counts),
+                                      C.byref(best), C.byref(bcnt), flags.ctypes.data_as(C.POINTER(C.c_ubyte)))
+        assert rc == 0, rc
+        return best.value, bcnt.value, counts[:len(homos)], flags[:len(kp1)]
 
     def num_threads(self):
         return self._fn("num_threads")()

@@ -206,3 +206,15 @@ def test_oracle_mt_equals_oracle(orc):
         for lazy in (0, 1):
             p = default_params(lazy_read=lazy, multiband=bands)
             assert gu.same_bits(orc.blend(imgs, items, geom, bands, p), mt.blend(imgs, items, geom, bands, p)), (bands, lazy)
+
+
+@pytest.mark.parametrize("n_match,n_hyp,seed", [(300, 200, 1), (8, 50, 2), (1200, 64, 3)])
+def test_ransac_scoring(orc, ref, n_match, n_hyp, seed):
+    """TransformEstimation::get_inliers itself (the reference TU, reached through the shim) against
+    the restatement: per-hypothesis counts, first-maximum selection, inlier flags."""
+    from tests.ransac_util import ransac_case
+    kp1, kp2, homos, thres = ransac_case(n_match, n_hyp, seed)
+    a, b = orc.ransac_score(kp1, kp2, homos, thres), ref.ransac_score(kp1, kp2, homos, thres)
+    assert a[0] == b[0] and a[1] == b[1]
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert a[1] > 0.5 * n_match
