@@ -387,6 +387,7 @@ def main():
                 self.h2d = self.lanes.in_bytes(shapes)
                 self.d2h = self.lanes.out_bytes((out_w, out_h)) + nm_e2e * 8 + len(imgs) * 8
                 self.trials = []
+                self.gaps = []        # per trial: the longest pause between two consecutive job completions (ms)
                 self.lanes.map(self.jobs(2 * self.n_out))           # warm-up
 
             def jobs(self, n):
@@ -400,6 +401,8 @@ def main():
                 res = self.lanes.map(self.jobs(args.steps))
                 torch.cuda.synchronize()
                 secs = time.perf_counter() - t0
+                dt = np.diff(np.sort(np.array([t0] + list(self.lanes.done_times))))
+                self.gaps.append(float(dt.max()) * 1e3 if len(dt) else 0.0)
                 nm_pipe = sum(sum(len(x) for x in m) for m in res)
                 assert nm_pipe == args.steps * nm_e2e, (nm_pipe, nm_e2e)      # every job returned the same matches
                 last = self.outs[(args.steps - 1) % self.n_out]
@@ -436,6 +439,7 @@ def main():
         one_lane_per_step = legs["one"].median()
         f32_per_step, f32_h2d, f32_d2h = legs["f32"].median(), legs["f32"].h2d, legs["f32"].d2h
         e2e_trials = {k: [round(x * 1e3, 3) for x in v.trials] for k, v in legs.items()}
+        e2e_gaps = {k: [round(x, 2) for x in v.gaps] for k, v in legs.items()}
         for v in {id(v): v for v in legs.values()}.values():
             v.lanes.close()
 
@@ -445,6 +449,7 @@ def main():
         if rank == 0:
             st.upload(host_ptrs, shapes, (out_w, out_h))
             eng.sync()
+            st._overlap = False                 # per-kernel times: every kernel of the step on the profiled context
             eng.profile(True)
             eng.profile_reset()
             PROF_STEPS = 5
@@ -452,6 +457,7 @@ def main():
                 step_device()
             prof = eng.profile_read()
             eng.profile(False)
+            st._overlap = True
             ab = algorithmic_bytes(imgs, items, params, counts)
             peaks = {}
             pk = ROOT / "MEASURED_PEAKS.json"
@@ -588,7 +594,10 @@ def main():
                     "mat32f_ms_per_step": f32_per_step * 1e3, "mat32f_value": world * mpx / f32_per_step,
                     "mat32f_h2d_bytes_per_step": int(f32_h2d), "mat32f_d2h_bytes_per_step": int(f32_d2h),
                     "single_job_ms": e2e_latency * 1e3, "single_job_value": world * mpx / e2e_latency,
-                    "lanes_trials_ms": e2e_trials["lanes"], "lanes_worst_trial_ms": max(e2e_trials["lanes"])},
+                    "lanes_trials_ms": e2e_trials["lanes"], "lanes_worst_trial_ms": max(e2e_trials["lanes"]),
+                    # a slow trial is ONE long pause between two job completions (a descheduled host thread /
+                    # another tenant's PCIe burst on the shared box), not a uniformly slower pipeline:
+                    "longest_pause_between_jobs_ms": e2e_gaps},
             "gpu_launches": int(launches * world),
             "roofline": roof,
             "cpu_baseline": cpu,

@@ -276,6 +276,32 @@ int pano_blend_rows_dev(pano_ctx* ctx, int n, const pano_blend_image* imgs, cons
                         int bands, const pano_params* p, float* d_out_rows, int out_w, int out_h,
                         int row0, int row1);
 
+/* --------------------------------------------------------- multi-GPU
+ * One process (or host thread) per GPU, one pano_ctx each.  The path shards on
+ * independent units — images k mod G for SIFT (stitcherbase.cc:14), the pair list of
+ * stitcher.cc:98-112 for matching, canvas rows for the blend (blender.cc:79, multiband.cc:75,127)
+ * — and has two exchange steps, both NCCL over NVLink on the context's stream:
+ *   C1  pano_comm_allgather_features   the descriptor sets every pair task needs
+ *   C2  pano_comm_allgather_dev        the row strips of pano_blend_rows_dev -> the mosaic
+ * libnccl.so.2 is loaded at run time by the first pano_comm_* call; single-GPU hosts never need it. */
+typedef struct pano_comm pano_comm;
+/* ncclGetUniqueId: rank 0 calls this and hands the 128 bytes to every rank (file, socket, MPI...). */
+int  pano_comm_unique_id(unsigned char id[128]);
+/* ncclCommInitRank on ctx's device; collective over all `world` ranks. */
+int  pano_comm_create(pano_ctx* ctx, int world, int rank, const unsigned char id[128], pano_comm** out);
+/* Wraps a communicator the host already has (ncclComm_t cast to void*); not destroyed by pano_comm_destroy. */
+int  pano_comm_adopt(pano_ctx* ctx, void* nccl_comm, int world, int rank, pano_comm** out);
+void pano_comm_destroy(pano_comm* c);
+int  pano_comm_world(const pano_comm* c);
+int  pano_comm_rank(const pano_comm* c);
+/* C1: `local` = this rank's images (k = rank, rank + world, ... in ascending k; NULL if it owns none)
+ * of n_images_total; *all receives a featureset of all n_images_total images on every rank,
+ * bit-identical to detecting them on one GPU.  Device to device, no host staging of descriptors. */
+int  pano_comm_allgather_features(pano_comm* c, pano_featureset* local, int n_images_total, pano_featureset** all);
+/* C2 (and any other equal-sized exchange): bytes_per_rank from d_send of every rank, concatenated by
+ * rank into d_recv (world * bytes_per_rank). */
+int  pano_comm_allgather_dev(pano_comm* c, const void* d_send, void* d_recv, size_t bytes_per_rank);
+
 /* ------------------------------------------------ 8-bit image boundary
  * The byte formats either side of the path: decoded 8-bit
  * pixels in, 8-bit mosaic out, so 3 B/px cross PCIe instead of 12.  All

@@ -65,6 +65,14 @@ def _load():
         "pano_matches_free": (None, [C.POINTER(PanoMatches)]),
         "pano_match_pairs_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _ip, P, _ip]),
         "pano_match_bruteforce": (C.c_int, [C.c_void_p, _fp, C.c_int, _fp, C.c_int, P, _ip, _ip]),
+        "pano_comm_unique_id": (C.c_int, [C.c_char_p]),
+        "pano_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, _vpp]),
+        "pano_comm_adopt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, _vpp]),
+        "pano_comm_destroy": (None, [C.c_void_p]),
+        "pano_comm_world": (C.c_int, [C.c_void_p]),
+        "pano_comm_rank": (C.c_int, [C.c_void_p]),
+        "pano_comm_allgather_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _vpp]),
+        "pano_comm_allgather_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
         "pano_ransac_score_pairs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PanoRansacPair), _ip, _ip, _vpp, _vpp]),
         "pano_cyl_warp_shape": (C.c_int, [C.c_int, C.c_int, C.c_double, P, _ip, _ip, _dp, _dp]),
         "pano_cyl_warp": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, C.c_double, P, _fp, C.c_int,

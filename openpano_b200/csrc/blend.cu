@@ -211,10 +211,9 @@ k_mb_blur_tma(const MbPlane* __restrict__ planes, const int2* __restrict__ span,
   constexpr int RX = (C + 3) & ~3;                 // TMA box origin: 16-byte aligned columns
   constexpr int GW = BT_W + 2 * RX, GH = BT_H + 2 * C;
   constexpr int GSZ = (GH * GW + 31) & ~31;
-  constexpr int CS = GW | 1;
   float* grey0 = smem;
   float* colbuf = smem + 2 * GSZ;
-  float* outT = colbuf + BT_H * CS;
+  float* outT = colbuf + BLUR_COLBUF_FLOATS(C);
   const int tid = threadIdx.x;
   constexpr uint32_t tile_bytes = (uint32_t)(GH * GW * sizeof(float));
   int t = blockIdx.x;
@@ -253,7 +252,7 @@ k_mb_blur_tma(const MbPlane* __restrict__ planes, const int2* __restrict__ span,
       }
       __syncthreads();
     }
-    blur_level<C>(grey, colbuf, outT, bt.taps, C, RX, GW, CS, tid);
+    blur_level<C>(grey, colbuf, outT, bt.taps, C, RX, GW, tid);
     const int tx = tid & (BT_W - 1), ty = tid / BT_W;   // 64 x 4
     const int gx = x0 + tx;
     float* out = dst + pl.off;
@@ -395,8 +394,8 @@ struct BlendJob {
 template <int C>
 static cudaError_t launch_mb_blur_tma(pano_ctx* ctx, int grid, const MbPlane* planes, const int2* span, int n_planes,
                                       int n_tiles, const TmaDesc* maps, float* dst, const BlurTaps& bt) {
-  constexpr int RX = (C + 3) & ~3, GW = BT_W + 2 * RX, GH = BT_H + 2 * C, GSZ = (GH * GW + 31) & ~31, CS = GW | 1;
-  const size_t smem = (size_t)(2 * GSZ + BT_H * CS + BT_H * (BT_W + 1)) * sizeof(float);
+  constexpr int RX = (C + 3) & ~3, GW = BT_W + 2 * RX, GH = BT_H + 2 * C, GSZ = (GH * GW + 31) & ~31;
+  const size_t smem = (size_t)(2 * GSZ + BLUR_COLBUF_FLOATS(C) + BT_H * (BT_W + 1)) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(k_mb_blur_tma<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k_mb_blur_tma<C><<<grid, BT_THREADS, smem, ctx->stream>>>(planes, span, n_planes, n_tiles, maps, dst, bt);

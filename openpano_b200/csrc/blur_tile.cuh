@@ -27,52 +27,83 @@ __device__ __forceinline__ BlurTile find_blur_tile(const int2* __restrict__ span
   return t;
 }
 
-// Fast path for the window half-widths the reference's defaults produce (kw = 7
-// and 13): both passes keep a sliding window in registers so one
-// shared-memory load feeds up to 2C+1 taps, 8 outputs per thread per pass.
-//   column pass: lane <-> column, thread = 8 consecutive rows
-//   row pass   : lane <-> row (odd row stride => conflict-free), thread = 8
-//                consecutive columns, results staged transposed-safe in `outT`
-//   store      : lane <-> column, coalesced level + |DoG| writes
-// The arithmetic per output is unchanged: tmp = 0; tmp += v[k] * tap[k], k ascending.
+// Register-blocked passes for compile-time half-widths C (the reference's defaults give kw = 7,
+// 13 and, in the blender's last level, 19): both passes keep a sliding window in registers so one
+// shared-memory load feeds up to 2C+1 taps, 8 outputs per thread per pass, and work on PAIRS of
+// independent outputs so that the multiplies run packed (Blackwell FMUL2, two products per
+// instruction; the adds stay scalar FADDs — ptxas would fuse a packed add into FFMA2 and change
+// the rounding).  The arithmetic per output is unchanged: tmp = 0; tmp += v[k] * tap[k], k ascending.
+//   column pass: thread = (2 adjacent columns) x (8 rows); the staged tile delivers column pairs
+//                as one 8-byte load; results go to `colbuf2` as ROW pairs: colbuf2[p][x] =
+//                (row 2p, row 2p+1) of column x, row-pair stride `csp` float2 (odd: conflict-free)
+//   row pass   : thread = (row pair) x (8 columns), 128 threads; results to `outT` [32][65]
+//   store      : lane <-> column, coalesced writes by the caller
+// `grey` is the staged tile with a halo of R rows / RX columns (RX a multiple of 4, GW floats per
+// row); the column pass covers staged columns [start, start + 2*npair), start = (RX - C) & ~1.
+__device__ __forceinline__ float2 fmul2(float2 a, float t) {
+  unsigned long long ra, rb, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(rb) : "f"(t));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
+#define BLUR_COLBUF_FLOATS(C) (16 * ((((BT_W + 2 * (C) + 2) / 2) * 2) | 1) * 2)   // upper bound for any column parity
+
 template <int C>
 __device__ __forceinline__ void blur_level(const float* __restrict__ grey, float* __restrict__ colbuf,
                                            float* __restrict__ outT, const float* __restrict__ taps_g,
-                                           int R, int RX, int GW, int CS, int tid) {
+                                           int R, int RX, int GW, int tid) {
   constexpr int KW = 2 * C + 1;
   float tap[KW];
 #pragma unroll
   for (int k = 0; k < KW; ++k) tap[k] = taps_g[k];
-  const int cw = BT_W + 2 * C;
-  // column pass: items = (BT_H/8 row strips) x cw columns
-  for (int item = tid; item < (BT_H / 8) * cw; item += BT_THREADS) {
-    const int strip = item / cw, xx = item - strip * cw;
-    const float* col = grey + (strip * 8 + R - C) * GW + (xx + RX - C);
-    float win[8 + 2 * C];
+  const int start = (RX - C) & ~1, off = (RX - C) - start;
+  const int npair = (BT_W + 2 * C + off + 1) >> 1;
+  const int csp = (2 * npair) | 1;
+  float2* colbuf2 = reinterpret_cast<float2*>(colbuf);
+  // column pass: items = (BT_H/8 row strips) x npair column pairs (<= 256: one round)
+  for (int item = tid; item < (BT_H / 8) * npair; item += BT_THREADS) {
+    const int strip = item / npair, pr = item - strip * npair;
+    const float2* col = reinterpret_cast<const float2*>(grey + (strip * 8 + R - C) * GW + start) + pr;
+    const int gw2 = GW >> 1;
+    float2 win[8 + 2 * C];
 #pragma unroll
-    for (int j = 0; j < 8 + 2 * C; ++j) win[j] = col[j * GW];
+    for (int j = 0; j < 8 + 2 * C; ++j) win[j] = col[j * gw2];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      float tmp = 0.f;
+    for (int r = 0; r < 8; r += 2) {
+      float a0x = 0.f, a0y = 0.f, a1x = 0.f, a1y = 0.f;     // rows r and r+1, columns x and x+1
 #pragma unroll
-      for (int k = 0; k < KW; ++k) tmp += win[r + k] * tap[k];
-      colbuf[(strip * 8 + r) * CS + xx] = tmp;
+      for (int k = 0; k < KW; ++k) {
+        const float2 p0 = fmul2(win[r + k], tap[k]);
+        const float2 p1 = fmul2(win[r + 1 + k], tap[k]);
+        a0x += p0.x; a0y += p0.y; a1x += p1.x; a1y += p1.y;
+      }
+      float2* dst = colbuf2 + (strip * 4 + (r >> 1)) * csp + 2 * pr;
+      dst[0] = make_float2(a0x, a1x);
+      dst[1] = make_float2(a0y, a1y);
     }
   }
   __syncthreads();
-  // row pass: warp <-> 8-column strip, lane <-> row
-  {
-    const int lane = tid & 31, xs = (tid >> 5) * 8;
-    const float* row = colbuf + lane * CS + xs;
-    float win[8 + 2 * C];
+  // row pass: lane & 15 <-> row pair, (warp, lane >> 4) <-> 8-column strip
+  if (tid < 128) {
+    const int lane = tid & 31, p = lane & 15, xs = ((tid >> 5) * 2 + (lane >> 4)) * 8;
+    const float2* row = colbuf2 + p * csp + off + xs;
+    float2 win[8 + 2 * C];
 #pragma unroll
     for (int j = 0; j < 8 + 2 * C; ++j) win[j] = row[j];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      float tmp = 0.f;
+    for (int c = 0; c < 8; ++c) {
+      float ax = 0.f, ay = 0.f;
 #pragma unroll
-      for (int k = 0; k < KW; ++k) tmp += win[r + k] * tap[k];
-      outT[lane * (BT_W + 1) + xs + r] = tmp;
+      for (int k = 0; k < KW; ++k) {
+        const float2 pp = fmul2(win[c + k], tap[k]);
+        ax += pp.x; ay += pp.y;
+      }
+      outT[(2 * p) * (BT_W + 1) + xs + c] = ax;
+      outT[(2 * p + 1) * (BT_W + 1) + xs + c] = ay;
     }
   }
   __syncthreads();

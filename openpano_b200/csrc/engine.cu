@@ -657,6 +657,14 @@ static int featureset_build(pano_ctx* ctx, int n_images, const int* n_kp, const 
   return PANO_OK;
 }
 
+}  // extern "C"
+// the same import for the communicator code (comm.cu)
+int featureset_build_dev(pano_ctx* ctx, int n_images, const int* n_kp, const float* const* d_desc,
+                         const double* const* d_coor, pano_featureset** out) {
+  return featureset_build(ctx, n_images, n_kp, d_desc, d_coor, out, true);
+}
+extern "C" {
+
 int pano_featureset_upload(pano_ctx* ctx, int n_images, const int* n_kp, const float* const* desc,
                            const double* const* coor, pano_featureset** out) {
   ctx_enter(ctx);

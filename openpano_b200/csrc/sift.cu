@@ -159,10 +159,9 @@ k_blur_dog_fast(const OctMeta* __restrict__ octs, const int2* __restrict__ span,
   const int RX = (R + 3) & ~3;
   const int GW = BT_W + 2 * RX, GH = BT_H + 2 * R;
   const int GSZ = (GH * GW + 31) & ~31;  // floats per grey buffer, 128-byte multiple
-  const int CS = GW | 1;                 // odd stride: row-pass lanes (rows) hit distinct banks
   float* grey0 = smem;                   // [2][GH][GW]
-  float* colbuf = smem + 2 * GSZ;        // [BT_H][CS]
-  float* outT = colbuf + BT_H * CS;      // [BT_H][BT_W+1]
+  float* colbuf = smem + 2 * GSZ;        // column-pass results as row pairs (blur_tile.cuh)
+  float* outT = colbuf + BLUR_COLBUF_FLOATS(6);   // [BT_H][BT_W+1]
   const int tid = threadIdx.x;
   const uint32_t tile_bytes = (uint32_t)(GH * GW * sizeof(float));
   int t = blockIdx.x;
@@ -209,8 +208,8 @@ k_blur_dog_fast(const OctMeta* __restrict__ octs, const int2* __restrict__ span,
 #pragma unroll
     for (int i = 0; i < BT_H / 4; ++i) prev[i] = grey[(ty + 4 * i + R) * GW + tx + RX];
     for (int s = 0; s < gt.nlev; ++s) {
-      if (gt.center[s] == 3) blur_level<3>(grey, colbuf, outT, gt.taps[s], R, RX, GW, CS, tid);
-      else blur_level<6>(grey, colbuf, outT, gt.taps[s], R, RX, GW, CS, tid);
+      if (gt.center[s] == 3) blur_level<3>(grey, colbuf, outT, gt.taps[s], R, RX, GW, tid);
+      else blur_level<6>(grey, colbuf, outT, gt.taps[s], R, RX, GW, tid);
       float* lvl = arena + om.gauss_off + (size_t)(s + 1) * om.plane;
       float* dog = arena + om.dog_off + (size_t)s * om.plane;
 #pragma unroll
@@ -1144,9 +1143,9 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     size_t smem = ((size_t)(BT_H + 2 * R) * (BT_W + 2 * R) + (size_t)BT_H * (BT_W + 2 * R)) * sizeof(float);
     if (smem > 200 * 1024) { sift_work_free(ctx, wk); return ctx_fail(ctx, PANO_ERR_INVALID, "sift: blur halo too large"); }
     if (fast) {
-      const int GW = BT_W + 2 * ((R + 3) & ~3), GH = BT_H + 2 * R, CS = GW | 1;
+      const int GW = BT_W + 2 * ((R + 3) & ~3), GH = BT_H + 2 * R;
       const size_t gsz = ((size_t)GH * GW + 31) & ~(size_t)31;
-      size_t smf = (2 * gsz + (size_t)BT_H * CS + (size_t)BT_H * (BT_W + 1)) * sizeof(float);
+      size_t smf = (2 * gsz + (size_t)BLUR_COLBUF_FLOATS(6) + (size_t)BT_H * (BT_W + 1)) * sizeof(float);
       SIFT_CUDA(cudaFuncSetAttribute(k_blur_dog_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smf));
       const int grid = std::min(wk->n_tiles, ctx->num_sms * 3);
       SIFT_LAUNCH("k_blur_dog", k_blur_dog_fast, grid, BT_THREADS, smf, wk->d_oct, wk->d_tilespan, n_om, wk->n_tiles, wk->d_maps,

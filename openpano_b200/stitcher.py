@@ -24,9 +24,16 @@ from .synth import all_pairs, ordered_pairs  # noqa: F401  (task lists live with
 
 
 class Stitcher:
-    def __init__(self, engine: Engine, params=None):
+    def __init__(self, engine: Engine, params=None, overlap_blend: bool = True):
+        """overlap_blend: the composite depends on the images and the caller's geometry only, not
+        on the features (the geometry in between is host code), so it runs on a second context /
+        stream of the same device next to SIFT + matching: its bandwidth-bound kernels fill the
+        gaps of the issue-bound descriptor kernel.  Ordered with events; results are unchanged."""
         self.eng = engine
         self.params = params or default_params()
+        self._aux = None
+        self._overlap = overlap_blend
+        self._ev_in = self._ev_blend = None
         self._d_imgs = None      # device block holding all input images
         self._d_out = None
         self._shapes = None
@@ -61,6 +68,19 @@ class Stitcher:
             self.eng.dev_free(self._d_out)
             self._d_out = None
             self._out_shape = None
+        if self._aux is not None:
+            self._aux.sync()
+            Engine.event_destroy(self._ev_in)
+            Engine.event_destroy(self._ev_blend)
+            self._aux.close()
+            self._aux = None
+
+    def _aux_engine(self):
+        if self._aux is None:
+            self._aux = Engine(self.eng.device)
+            self._ev_in = self.eng.event_create()
+            self._ev_blend = self._aux.event_create()
+        return self._aux
 
     def image_ptrs(self):
         return [self._d_imgs + o for o in self._offs]
@@ -77,14 +97,23 @@ class Stitcher:
         (featureset, matches-or-total)."""
         shapes = self._shapes
         ptrs = self.image_ptrs()
+        if self._overlap:
+            aux = self._aux_engine()
+            self.eng.event_record(self._ev_in)          # images (and the previous reader of d_out) are done on the main stream
+            aux.event_wait(self._ev_in)
+            aux.blend_dev(ptrs, shapes, items, geom, self._d_out, self._out_shape[0], self._out_shape[1], bands, self.params)
+            aux.event_record(self._ev_blend)
         fs = self.eng.sift_detect_batch_ptr(ptrs, [s[1] for s in shapes], [s[0] for s in shapes], self.params,
                                             device=True)
         if want_matches:
             m = self.eng.match_pairs(fs, pairs, self.params)
         else:
             m = self.eng.match_pairs_dev(fs, pairs, self.params)
-        self.eng.blend_dev(ptrs, shapes, items, geom, self._d_out, self._out_shape[0], self._out_shape[1], bands,
-                           self.params)
+        if self._overlap:
+            self.eng.event_wait(self._ev_blend)         # the mosaic is complete in main-stream order
+        else:
+            self.eng.blend_dev(ptrs, shapes, items, geom, self._d_out, self._out_shape[0], self._out_shape[1], bands,
+                               self.params)
         return fs, m
 
     # -- the end-to-end call a user makes: host images in, host mosaic + matches out
@@ -292,6 +321,7 @@ class StitchLanes:
 
     def __init__(self, device: int, params=None, lanes: int = 2, depth: int = 2, rgb8: bool = False, crop: bool = True):
         self.lanes = [PipelinedStitcher(device, params, depth=depth, rgb8=rgb8, crop=crop) for _ in range(lanes)]
+        self.done_times = []       # perf_counter() at which each job of the last map() came back (diagnostics)
 
     def out_bytes(self, out_wh):
         return self.lanes[0].out_bytes(out_wh)
@@ -300,7 +330,8 @@ class StitchLanes:
         return self.lanes[0].in_bytes(shapes)
 
     @staticmethod
-    def _run_lane(ps, jobs, results, errors):
+    def _run_lane(ps, jobs, results, errors, done=None):
+        import time
         try:
             if not jobs:
                 return
@@ -314,11 +345,15 @@ class StitchLanes:
                 handle = ps.run(slot, job[3], job[4], job[5], job[6], job[7])
                 if pending is not None:
                     results[pending[0]] = ps.wait(pending[1])
+                    if done is not None:
+                        done[pending[0]] = time.perf_counter()
                 pending = (idx, handle)
                 if nxt is None:
                     break
                 (idx, job), slot = nxt, nslot
             results[pending[0]] = ps.wait(pending[1])
+            if done is not None:
+                done[pending[0]] = time.perf_counter()
         except Exception as ex:  # surfaced by map()
             errors.append(ex)
 
@@ -328,15 +363,17 @@ class StitchLanes:
         jobs = list(jobs)
         results = [None] * len(jobs)
         errors = []
+        done = [0.0] * len(jobs)
         L = len(self.lanes)
         threads = [threading.Thread(target=self._run_lane, args=(self.lanes[q], [(i, j) for i, j in enumerate(jobs) if i % L == q],
-                                                                 results, errors)) for q in range(L)]
+                                                                 results, errors, done)) for q in range(L)]
         for t in threads:
             t.start()
         for t in threads:
             t.join()
         if errors:
             raise errors[0]
+        self.done_times = done
         return results
 
     def close(self):
