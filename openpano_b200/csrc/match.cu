@@ -171,7 +171,7 @@ __device__ __forceinline__ float tc_eps(float nq, float nmax) {
 
 __global__ void k_refine(const float* __restrict__ desc, const float* __restrict__ norms,
                          const unsigned* __restrict__ maxnorm_bits, const SideMeta* __restrict__ sides,
-                         const TcTop2* __restrict__ approx, RowInfo* __restrict__ info) {
+                         const TcTop2* __restrict__ approx, float ratio_sqr, RowInfo* __restrict__ info) {
   const int side = blockIdx.y;
   const SideMeta sm = sides[side];
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,6 +186,17 @@ __global__ void k_refine(const float* __restrict__ desc, const float* __restrict
   const bool single = ap.m2 == FLT_MAX;                 // only one real target
   const bool certain = idx_ok && (single || (ap.m2 - ap.m1 > 2.f * eps));
   if (sm.t_n <= 0) { o.mn = FLT_MAX; o.mn_hi = FLT_MAX; o.sec_lo = FLT_MAX; o.sec_hi = FLT_MAX; o.state = 3; }
+  else if (certain && !single && (ap.m1 - eps) > ratio_sqr * (ap.m2 + eps)) {
+    // The argmin is certain and so is the outcome of the row's ratio test (min > R * next_min for every
+    // distance inside the error band): the row is rejected whatever its exact distance is, so the 1 KB
+    // exact re-computation is skipped and the row keeps certified BOUNDS.  k_match_decide rejects it
+    // at its first test (mn_lo > R * min(sec_hi, .)); as a column of another row it still offers
+    // valid bounds [mn, mn_hi] / [sec_lo, sec_hi] — in an all-pairs run nearly every row of a
+    // non-overlapping image pair ends here.
+    o.mn = ap.m1 - eps; o.mn_hi = ap.m1 + eps;
+    o.sec_lo = fmaxf(ap.m2 - eps, o.mn); o.sec_hi = ap.m2 + eps;
+    o.state = 2;
+  }
   else if (certain) {
     // the argmin is certain: its exact fp32 distance is the row minimum
     o.mn = exact_dist(desc + (size_t)(sm.q_base + r) * 128, desc + (size_t)(sm.t_base + o.idx) * 128);
@@ -512,7 +523,7 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
   if (rc) return rc;
   if (pl.max_side_n > 0) {
     dim3 gr(ceil_div(pl.max_side_n, 128), (unsigned)pl.sides.size());
-    PANO_LAUNCH(ctx, "k_refine", k_refine, gr, 128, 0, fs->d_desc, ops->d_norms, ops->d_maxnorm, b.sides, b.approx,
+    PANO_LAUNCH(ctx, "k_refine", k_refine, gr, 128, 0, fs->d_desc, ops->d_norms, ops->d_maxnorm, b.sides, b.approx, rs,
                 b.info);
   }
   if (pl.max_small > 0) {

@@ -179,7 +179,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ------------------------------------------------------------------ the GEMM + top-2 kernel
 
 struct __align__(8) TcBarriers {
-  uint64_t full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2], a_full;
+  uint64_t full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2], a_full[2], a_empty[2];
   uint32_t tmem_base;
 };
 
@@ -187,53 +187,64 @@ struct __align__(8) TcBarriers {
 // FILTER = true : second pass over GATHERED rows only; every column whose score is
 //                 within the row's threshold key is appended to that row's candidate
 //                 slots (the exact kernel then decides among a handful of columns).
+//
+// PERSISTENT: a CTA walks tasks blockIdx.x, blockIdx.x + gridDim.x, ...; the three roles run the
+// same task sequence on their own, coupled only through mbarriers whose phases follow two running
+// counters (target tiles and tasks).  Nothing is re-initialised between tasks, so the producer is
+// already fetching the next task's query block (two A buffers) and target tiles while the MMA and
+// the epilogue finish the current one: an image pair of ~2 k descriptors is only ~10 tiles per
+// task, and the per-task prologue used to cost as much as the tiles themselves.
 template <bool FILTER>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restrict__ tbuf,
-          const TcTask* __restrict__ tasks, const int* __restrict__ n_tasks_dev,
+          const TcTask* __restrict__ tasks, const int* __restrict__ n_tasks_dev, int n_tasks_host,
           const unsigned* __restrict__ maxnorm_bits, TcTop2* __restrict__ res,
           const int* __restrict__ g_thr, int* __restrict__ cand_cnt, int* __restrict__ cand) {
   extern __shared__ __align__(1024) unsigned char tc_smem[];
-  if (n_tasks_dev && (int)blockIdx.x >= *n_tasks_dev) return;   // uniform per CTA, before any barrier / TMEM use
-  unsigned char* sA = tc_smem;                                        // 1 block
-  unsigned char* sB = tc_smem + TC_BLOCK_BYTES;                       // TC_STAGES x 2 blocks
+  const int task_end = n_tasks_dev ? *n_tasks_dev : n_tasks_host;
+  if ((int)blockIdx.x >= task_end) return;   // uniform per CTA, before any barrier / TMEM use
+  unsigned char* sA = tc_smem;                                        // 2 query blocks
+  unsigned char* sB = tc_smem + 2 * TC_BLOCK_BYTES;                   // TC_STAGES x 2 blocks
   TcBarriers* bars = (TcBarriers*)(sB + (size_t)TC_STAGES * TC_TILE_BLOCKS * TC_BLOCK_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // The filter pass is launched with a small persistent grid (its task count lives on
-  // the device); each CTA loops over tasks and re-arms its barriers per task.
-  const int task_end = n_tasks_dev ? *n_tasks_dev : (int)blockIdx.x + 1;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  uint32_t tmem = 0;
-  for (int task = blockIdx.x; task < task_end; task += gridDim.x) {
-  const TcTask tk = tasks[task];
-  const int ntile = tk.t_blocks / TC_TILE_BLOCKS;
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bars->acc_full[s]), 1); mbar_init(smem_u32(&bars->acc_empty[s]), 128); }
-    mbar_init(smem_u32(&bars->a_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bars->acc_full[s]), 1); mbar_init(smem_u32(&bars->acc_empty[s]), 128);
+      mbar_init(smem_u32(&bars->a_full[s]), 1); mbar_init(smem_u32(&bars->a_empty[s]), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  tmem = bars->tmem_base;
+  const uint32_t tmem = bars->tmem_base;
 
   if (warp == 0) {
     // ===== producer
     if (lane == 0) {
-      mbar_expect_tx(smem_u32(&bars->a_full), TC_BLOCK_BYTES);
-      bulk_g2s(smem_u32(sA), qbuf + (size_t)tk.q_blk * TC_BLOCK_BYTES, TC_BLOCK_BYTES, smem_u32(&bars->a_full));
-      for (int t = 0; t < ntile; ++t) {
-        const int s = t % TC_STAGES;
-        const uint32_t ph = (uint32_t)(t / TC_STAGES) & 1u;
-        mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
-        const uint32_t bytes = TC_TILE_BLOCKS * TC_BLOCK_BYTES;
-        mbar_expect_tx(smem_u32(&bars->full[s]), bytes);
-        bulk_g2s(smem_u32(sB + (size_t)s * bytes), tbuf + (size_t)(tk.t_blk0 + t * TC_TILE_BLOCKS) * TC_BLOCK_BYTES, bytes,
-                 smem_u32(&bars->full[s]));
+      uint32_t gt = 0;                       // target tiles issued so far (all tasks)
+      uint32_t ti = 0;                       // tasks started so far
+      for (int task = blockIdx.x; task < task_end; task += gridDim.x, ++ti) {
+        const TcTask tk = tasks[task];
+        const int ntile = tk.t_blocks / TC_TILE_BLOCKS;
+        const uint32_t as = ti & 1u;
+        mbar_wait(smem_u32(&bars->a_empty[as]), ((ti >> 1) & 1u) ^ 1u);
+        mbar_expect_tx(smem_u32(&bars->a_full[as]), TC_BLOCK_BYTES);
+        bulk_g2s(smem_u32(sA + (size_t)as * TC_BLOCK_BYTES), qbuf + (size_t)tk.q_blk * TC_BLOCK_BYTES, TC_BLOCK_BYTES,
+                 smem_u32(&bars->a_full[as]));
+        for (int t = 0; t < ntile; ++t, ++gt) {
+          const uint32_t s = gt % TC_STAGES, ph = (gt / TC_STAGES) & 1u;
+          mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
+          const uint32_t bytes = TC_TILE_BLOCKS * TC_BLOCK_BYTES;
+          mbar_expect_tx(smem_u32(&bars->full[s]), bytes);
+          bulk_g2s(smem_u32(sB + (size_t)s * bytes), tbuf + (size_t)(tk.t_blk0 + t * TC_TILE_BLOCKS) * TC_BLOCK_BYTES, bytes,
+                   smem_u32(&bars->full[s]));
+        }
       }
     }
   } else if (warp == 1) {
@@ -241,110 +252,108 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
     if (lane == 0) {
       // UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b F16 = 0, K-major both, N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-      mbar_wait(smem_u32(&bars->a_full), 0);
-      for (int t = 0; t < ntile; ++t) {
-        const int s = t % TC_STAGES, as = t & 1;
-        mbar_wait(smem_u32(&bars->full[s]), (uint32_t)(t / TC_STAGES) & 1u);
-        mbar_wait(smem_u32(&bars->acc_empty[as]), ((uint32_t)(t >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(sA);
-        const uint32_t b0 = smem_u32(sB + (size_t)s * TC_TILE_BLOCKS * TC_BLOCK_BYTES);
+      uint32_t gt = 0, ti = 0;
+      for (int task = blockIdx.x; task < task_end; task += gridDim.x, ++ti) {
+        const TcTask tk = tasks[task];
+        const int ntile = tk.t_blocks / TC_TILE_BLOCKS;
+        const uint32_t asl = ti & 1u;
+        mbar_wait(smem_u32(&bars->a_full[asl]), (ti >> 1) & 1u);
+        const uint32_t a0 = smem_u32(sA + (size_t)asl * TC_BLOCK_BYTES);
+        for (int t = 0; t < ntile; ++t, ++gt) {
+          const uint32_t s = gt % TC_STAGES, as = gt & 1u;
+          mbar_wait(smem_u32(&bars->full[s]), (gt / TC_STAGES) & 1u);
+          mbar_wait(smem_u32(&bars->acc_empty[as]), ((gt >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          const uint32_t b0 = smem_u32(sB + (size_t)s * TC_TILE_BLOCKS * TC_BLOCK_BYTES);
 #pragma unroll
-        for (int half = 0; half < TC_TILE_BLOCKS; ++half) {
-          const uint32_t d = tmem + (uint32_t)(as * 256 + half * 128);
+          for (int half = 0; half < TC_TILE_BLOCKS; ++half) {
+            const uint32_t d = tmem + (uint32_t)(as * 256 + half * 128);
 #pragma unroll
-          for (int k = 0; k < TC_KC / 2; ++k) {
-            const uint64_t ad = make_smem_desc(a0 + k * 2 * TC_LBO);
-            const uint64_t bd = make_smem_desc(b0 + half * TC_BLOCK_BYTES + k * 2 * TC_LBO);
-            umma_f16(d, ad, bd, idesc, k > 0 ? 1u : 0u);
+            for (int k = 0; k < TC_KC / 2; ++k) {
+              const uint64_t ad = make_smem_desc(a0 + k * 2 * TC_LBO);
+              const uint64_t bd = make_smem_desc(b0 + half * TC_BLOCK_BYTES + k * 2 * TC_LBO);
+              umma_f16(d, ad, bd, idesc, k > 0 ? 1u : 0u);
+            }
           }
+          umma_commit(smem_u32(&bars->empty[s]));      // smem slot reusable once these MMAs retire
+          umma_commit(smem_u32(&bars->acc_full[as]));  // accumulators ready for the epilogue
         }
-        umma_commit(smem_u32(&bars->empty[s]));      // smem slot reusable once these MMAs retire
-        umma_commit(smem_u32(&bars->acc_full[as]));  // accumulators ready for the epilogue
+        umma_commit(smem_u32(&bars->a_empty[asl]));    // every MMA that reads this query block has retired
       }
     }
   } else if (warp >= 4) {
     // ===== epilogue: thread <-> query row (TMEM lane)
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    int g1 = 0x7f7fff00, g2 = 0x7f7fff00;   // running best / second (value bits, low 8 cleared)
-    int gi = 0x7fffffff;
-    const int grow = tk.q_row0 + row;        // FILTER: index of this gathered row
-    const int thr = FILTER ? g_thr[grow] : 0;
-    for (int t = 0; t < ntile; ++t) {
-      const int as = t & 1;
-      mbar_wait(smem_u32(&bars->acc_full[as]), (uint32_t)(t >> 1) & 1u);
-      tc_fence_after();
-      int k1 = 0x7fffffff, k2 = 0x7fffffff;
+    uint32_t gt = 0;
+    for (int task = blockIdx.x; task < task_end; task += gridDim.x) {
+      const TcTask tk = tasks[task];
+      const int ntile = tk.t_blocks / TC_TILE_BLOCKS;
+      int g1 = 0x7f7fff00, g2 = 0x7f7fff00;   // running best / second (value bits, low 8 cleared)
+      int gi = 0x7fffffff;
+      const int grow = tk.q_row0 + row;        // FILTER: index of this gathered row
+      const int thr = FILTER ? g_thr[grow] : 0;
+      for (int t = 0; t < ntile; ++t, ++gt) {
+        const uint32_t as = gt & 1u;
+        mbar_wait(smem_u32(&bars->acc_full[as]), (gt >> 1) & 1u);
+        tc_fence_after();
+        int k1 = 0x7fffffff, k2 = 0x7fffffff;
 #pragma unroll
-      for (int c0 = 0; c0 < 256; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + (uint32_t)(as * 256 + c0), v);
-        tmem_ld_wait();
-        if (FILTER) {
-          // branch-free hit mask first: a conditional body inside the 256-way unrolled compare
-          // blows the loop up past the instruction cache (measured 3x slower per tile)
-          unsigned hit = 0;
+        for (int c0 = 0; c0 < 256; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(lane_addr + (uint32_t)(as * 256 + c0), v);
+          tmem_ld_wait();
+          if (FILTER) {
+            // branch-free hit mask first: a conditional body inside the 256-way unrolled compare
+            // blows the loop up past the instruction cache (measured 3x slower per tile)
+            unsigned hit = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) hit |= ((int)(v[j] & 0xffffff00u) <= thr) ? (1u << j) : 0u;
-          while (hit) {
-            const int j = __ffs(hit) - 1;
-            hit &= hit - 1;
-            const int col = t * 256 + c0 + j;
-            if (col < tk.t_n) {
-              const int slot = atomicAdd(&cand_cnt[grow], 1);
-              if (slot < TC_CAND_CAP) cand[(size_t)grow * TC_CAND_CAP + slot] = col;
+            for (int j = 0; j < 32; ++j) hit |= ((int)(v[j] & 0xffffff00u) <= thr) ? (1u << j) : 0u;
+            while (hit) {
+              const int j = __ffs(hit) - 1;
+              hit &= hit - 1;
+              const int col = t * 256 + c0 + j;
+              if (col < tk.t_n) {
+                const int slot = atomicAdd(&cand_cnt[grow], 1);
+                if (slot < TC_CAND_CAP) cand[(size_t)grow * TC_CAND_CAP + slot] = col;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int key = (int)((v[j] & 0xffffff00u) | (uint32_t)(c0 + j));
+              k2 = min(k2, max(k1, key));
+              k1 = min(k1, key);
             }
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int key = (int)((v[j] & 0xffffff00u) | (uint32_t)(c0 + j));
-            k2 = min(k2, max(k1, key));
-            k1 = min(k1, key);
-          }
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->acc_empty[as]));
+        if (!FILTER) {
+          // merge the tile's top-2 into the running top-2
+          const int v1 = k1 & (int)0xffffff00, v2 = k2 & (int)0xffffff00;
+          if (v1 < g1) { g2 = min(g1, v2); g1 = v1; gi = t * 256 + (k1 & 0xff); }
+          else g2 = min(g2, v1);
         }
       }
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bars->acc_empty[as]));
-      if (!FILTER) {
-        // merge the tile's top-2 into the running top-2
-        const int v1 = k1 & (int)0xffffff00, v2 = k2 & (int)0xffffff00;
-        if (v1 < g1) { g2 = min(g1, v2); g1 = v1; gi = t * 256 + (k1 & 0xff); }
-        else g2 = min(g2, v1);
+      const int qrow = tk.q_row0 + row;
+      if (!FILTER && qrow < tk.q_n) {
+        const float s = tc_scale_from_maxnorm(__uint_as_float(*maxnorm_bits));
+        const float inv = 1.f / (s * s);
+        TcTop2 o;
+        o.m1 = (__int_as_float(g1) - 1.f) * inv;
+        o.m2 = g2 == 0x7f7fff00 ? FLT_MAX : (__int_as_float(g2) - 1.f) * inv;
+        o.idx = gi;
+        o.pad = 0;
+        res[tk.res_off + qrow] = o;
       }
-    }
-    const int qrow = tk.q_row0 + row;
-    if (!FILTER && qrow < tk.q_n) {
-      const float s = tc_scale_from_maxnorm(__uint_as_float(*maxnorm_bits));
-      const float inv = 1.f / (s * s);
-      TcTop2 o;
-      o.m1 = (__int_as_float(g1) - 1.f) * inv;
-      o.m2 = g2 == 0x7f7fff00 ? FLT_MAX : (__int_as_float(g2) - 1.f) * inv;
-      o.idx = gi;
-      o.pad = 0;
-      res[tk.res_off + qrow] = o;
     }
   }
   tc_fence_before();
-  __syncthreads();                 // every role is done with this task's barriers, smem and TMEM
-  if (threadIdx.x == 0 && task + (int)gridDim.x < task_end) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->full[s])) : "memory");
-      asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->empty[s])) : "memory");
-    }
-    for (int s = 0; s < 2; ++s) {
-      asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->acc_full[s])) : "memory");
-      asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->acc_empty[s])) : "memory");
-    }
-    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars->a_full)) : "memory");
-  }
-  }  // task loop
+  __syncthreads();                 // every role is done with the barriers, smem and TMEM
   if (warp == 2) {
-    // a CTA without any task still allocated TMEM above: read the address back directly
     tc_fence_after();
-    const uint32_t base = *(volatile uint32_t*)&bars->tmem_base;
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
 
@@ -353,7 +362,7 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
 size_t tc_block_bytes() { return TC_BLOCK_BYTES; }
 
 size_t tc_smem_bytes() {
-  return (size_t)TC_BLOCK_BYTES * (1 + TC_STAGES * TC_TILE_BLOCKS) + sizeof(TcBarriers) + 1024;
+  return (size_t)TC_BLOCK_BYTES * (2 + TC_STAGES * TC_TILE_BLOCKS) + sizeof(TcBarriers) + 1024;
 }
 
 int tc_prepare(pano_ctx* ctx, const float* d_desc, const std::vector<TcImage>& imgs, TcOperands* ops) {
@@ -392,8 +401,8 @@ int tc_run_top2(pano_ctx* ctx, const TcOperands* ops, const TcTask* d_tasks, int
     PANO_CUDA(ctx, cudaFuncSetAttribute(k_tc_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ctx->attr_tc = true;
   }
-  PANO_LAUNCH(ctx, "k_tc_top2", k_tc_pass<false>, n_tasks, TC_THREADS, smem, ops->qbuf, ops->tbuf, d_tasks,
-              (const int*)nullptr, ops->d_maxnorm, d_res, (const int*)nullptr, (int*)nullptr, (int*)nullptr);
+  PANO_LAUNCH(ctx, "k_tc_top2", k_tc_pass<false>, std::min(n_tasks, ctx->num_sms), TC_THREADS, smem, ops->qbuf, ops->tbuf, d_tasks,
+              (const int*)nullptr, n_tasks, ops->d_maxnorm, d_res, (const int*)nullptr, (int*)nullptr, (int*)nullptr);
   return PANO_OK;
 }
 
@@ -444,6 +453,6 @@ int tc_run_filter(pano_ctx* ctx, const TcOperands* ops, const TcFilter* f, int m
   PANO_LAUNCH(ctx, "k_tc_gather_rows", k_tc_gather_rows, max_blocks, 128, 0, ops->qbuf, f->gq, f->tasks, f->n_tasks,
               f->gsides, f->list_rows, f->approx, ops->d_norms, ops->d_maxnorm, f->g_meta, f->g_thr, f->cand_cnt);
   PANO_LAUNCH(ctx, "k_tc_filter", k_tc_pass<true>, std::min(max_blocks, ctx->num_sms), TC_THREADS, smem, f->gq, ops->tbuf, f->tasks, f->n_tasks,
-              ops->d_maxnorm, (TcTop2*)nullptr, f->g_thr, f->cand_cnt, f->cand);
+              0, ops->d_maxnorm, (TcTop2*)nullptr, f->g_thr, f->cand_cnt, f->cand);
   return PANO_OK;
 }

@@ -24,7 +24,8 @@ __device__ __forceinline__ void bilinear_coef(int d, float inv, int src_n, int* 
   *s = si; *frac = r;
 }
 
-__global__ void k_working_resize(const ImgMeta* __restrict__ imgs, float* __restrict__ arena) {
+__global__ void k_working_resize(const ImgMeta* __restrict__ imgs, const OctMeta* __restrict__ octs, int n_oct,
+                                 float* __restrict__ arena) {
   const ImgMeta im = imgs[blockIdx.z];
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   int r = blockIdx.y * blockDim.y + threadIdx.y;
@@ -36,39 +37,74 @@ __global__ void k_working_resize(const ImgMeta* __restrict__ imgs, float* __rest
   const float* p0 = im.src + ((size_t)sx * im.in_w + sy) * 3;
   const float* p1 = p0 + (size_t)im.in_w * 3;
   float* dst = arena + im.work_off + ((size_t)r * im.w0 + c) * 3;
+  float v[3];
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     float p00 = __ldg(p0 + ch), p01 = __ldg(p0 + 3 + ch), p10 = __ldg(p1 + ch), p11 = __ldg(p1 + 3 + ch);
-    dst[ch] = rx * (p11 * ry + p10 * iry) + irx * (p01 * ry + p00 * iry);
+    v[ch] = rx * (p11 * ry + p10 * iry) + irx * (p01 * ry + p00 * iry);
+    dst[ch] = v[ch];
   }
+  // octave 0 is the working image itself (dog.cc:100-103): its grey plane (imgproc.cc:237-249) falls
+  // out of the same thread, so the working RGB is not read back for it
+  const OctMeta om = octs[blockIdx.z * n_oct];
+  arena[om.gauss_off + (size_t)r * om.pitch + c] = (v[0] + v[1] + v[2]) / 3.f;
 }
 
 // ============================================================ K1b octave grey
-// feature/dog.cc:96-114 (octave o>0 resized from the WORKING image) +
-// lib/imgproc.cc:237-249 rgb2grey.
-__global__ void k_octave_grey(const ImgMeta* __restrict__ imgs, const OctMeta* __restrict__ octs,
-                              float* __restrict__ arena) {
-  const OctMeta om = octs[blockIdx.z];
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  int r = blockIdx.y * blockDim.y + threadIdx.y;
-  if (c >= om.w || r >= om.h) return;
-  const ImgMeta im = imgs[om.img];
+// feature/dog.cc:96-114 (octave o>0 resized from the WORKING image) + lib/imgproc.cc:237-249
+// rgb2grey.  A CTA produces a 32x8 tile of one octave; the source rows it taps (a strip of the
+// interleaved working RGB) are staged through shared memory with coalesced loads, the 12
+// strided taps per pixel then hit shared memory instead of L1.
+#define OG_W 32
+#define OG_H 8
+__global__ void __launch_bounds__(OG_W * OG_H)
+k_octave_grey(const ImgMeta* __restrict__ imgs, const OctMeta* __restrict__ octs, int n_oct,
+              float* __restrict__ arena, int smem_floats) {
+  extern __shared__ float og_smem[];
+  // blockIdx.z enumerates (image, octave >= 1)
+  const int img = blockIdx.z / (n_oct - 1), oct = 1 + blockIdx.z % (n_oct - 1);
+  const OctMeta om = octs[img * n_oct + oct];
+  const int c0 = blockIdx.x * OG_W, r0 = blockIdx.y * OG_H;
+  if (c0 >= om.w || r0 >= om.h) return;
+  const ImgMeta im = imgs[img];
   const float* work = arena + im.work_off;
-  float v0, v1, v2;
-  if (om.oct == 0) {
-    const float* p = work + ((size_t)r * im.w0 + c) * 3;
-    v0 = p[0]; v1 = p[1]; v2 = p[2];
+  const int tid = threadIdx.y * OG_W + threadIdx.x;
+  // source rectangle of the tile (both taps of the first and the last output row / column)
+  int s_lo, s_hi, t_lo, t_hi; float fr;
+  bilinear_coef(r0, om.ifx, im.h0, &s_lo, &fr);
+  bilinear_coef(min(r0 + OG_H, om.h) - 1, om.ifx, im.h0, &s_hi, &fr);
+  bilinear_coef(c0, om.ify, im.w0, &t_lo, &fr);
+  bilinear_coef(min(c0 + OG_W, om.w) - 1, om.ify, im.w0, &t_hi, &fr);
+  const int nrow = s_hi + 2 - s_lo, ncol3 = (t_hi + 2 - t_lo) * 3;
+  const bool staged = nrow * ncol3 <= smem_floats;     // always true for the sizes the host computed
+  if (staged) {
+    for (int i = tid; i < nrow * ncol3; i += OG_W * OG_H) {
+      const int rr = i / ncol3, cc = i - rr * ncol3;
+      og_smem[i] = __ldg(work + ((size_t)(s_lo + rr) * im.w0 + t_lo) * 3 + cc);
+    }
+  }
+  __syncthreads();
+  const int c = c0 + threadIdx.x, r = r0 + threadIdx.y;
+  if (c >= om.w || r >= om.h) return;
+  int sx, sy; float rx, ry;
+  bilinear_coef(r, om.ifx, im.h0, &sx, &rx);
+  bilinear_coef(c, om.ify, im.w0, &sy, &ry);
+  float irx = 1.0f - rx, iry = 1.0f - ry;
+  float a[6], b[6];
+  if (staged) {
+    const float* p0 = og_smem + (sx - s_lo) * ncol3 + (sy - t_lo) * 3;
+    const float* p1 = p0 + ncol3;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { a[q] = p0[q]; b[q] = p1[q]; }
   } else {
-    int sx, sy; float rx, ry;
-    bilinear_coef(r, om.ifx, im.h0, &sx, &rx);
-    bilinear_coef(c, om.ify, im.w0, &sy, &ry);
-    float irx = 1.0f - rx, iry = 1.0f - ry;
     const float* p0 = work + ((size_t)sx * im.w0 + sy) * 3;
     const float* p1 = p0 + (size_t)im.w0 * 3;
-    v0 = rx * (p1[3] * ry + p1[0] * iry) + irx * (p0[3] * ry + p0[0] * iry);
-    v1 = rx * (p1[4] * ry + p1[1] * iry) + irx * (p0[4] * ry + p0[1] * iry);
-    v2 = rx * (p1[5] * ry + p1[2] * iry) + irx * (p0[5] * ry + p0[2] * iry);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { a[q] = __ldg(p0 + q); b[q] = __ldg(p1 + q); }
   }
+  const float v0 = rx * (b[3] * ry + b[0] * iry) + irx * (a[3] * ry + a[0] * iry);
+  const float v1 = rx * (b[4] * ry + b[1] * iry) + irx * (a[4] * ry + a[1] * iry);
+  const float v2 = rx * (b[5] * ry + b[2] * iry) + irx * (a[5] * ry + a[2] * iry);
   arena[om.gauss_off + (size_t)r * om.pitch + c] = (v0 + v1 + v2) / 3.f;
 }
 
@@ -1134,9 +1170,23 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
 
   {
     dim3 b(32, 8), g(ceil_div(max_w0, 32), ceil_div(max_h0, 8), n);
-    SIFT_LAUNCH("k_working_resize", k_working_resize, g, b, 0, wk->d_img, wk->arena);
-    dim3 g2(ceil_div(max_w0, 32), ceil_div(max_h0, 8), n * n_oct);
-    SIFT_LAUNCH("k_octave_grey", k_octave_grey, g2, b, 0, wk->d_img, wk->d_oct, wk->arena);
+    SIFT_LAUNCH("k_working_resize", k_working_resize, g, b, 0, wk->d_img, wk->d_oct, n_oct, wk->arena);
+    if (n_oct > 1) {
+      // staging buffer for the widest source rectangle of a 32x8 tile (octave 1 has the largest
+      // octave, the last octave the largest source footprint per tile)
+      int max_w1 = 0, max_h1 = 0;
+      size_t need = 0;
+      for (int i = 0; i < n; ++i)
+        for (int o = 1; o < n_oct; ++o) {
+          const OctMeta& om = wk->h_oct[(size_t)i * n_oct + o];
+          max_w1 = std::max(max_w1, om.w); max_h1 = std::max(max_h1, om.h);
+          const size_t rows = (size_t)(OG_H * om.ifx) + 4, cols = (size_t)(OG_W * om.ify) + 4;
+          need = std::max(need, rows * cols * 3);
+        }
+      need = std::min(need, (size_t)48 * 1024 / sizeof(float));
+      dim3 g2(ceil_div(max_w1, OG_W), ceil_div(max_h1, OG_H), n * (n_oct - 1));
+      SIFT_LAUNCH("k_octave_grey", k_octave_grey, g2, b, need * sizeof(float), wk->d_img, wk->d_oct, n_oct, wk->arena, (int)need);
+    }
   }
   {
     const int R = gt.rmax;
