@@ -24,8 +24,7 @@ __device__ __forceinline__ void bilinear_coef(int d, float inv, int src_n, int* 
   *s = si; *frac = r;
 }
 
-__global__ void k_working_resize(const ImgMeta* __restrict__ imgs, const OctMeta* __restrict__ octs, int n_oct,
-                                 float* __restrict__ arena) {
+__global__ void k_working_resize(const ImgMeta* __restrict__ imgs, float* __restrict__ arena) {
   const ImgMeta im = imgs[blockIdx.z];
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   int r = blockIdx.y * blockDim.y + threadIdx.y;
@@ -37,74 +36,39 @@ __global__ void k_working_resize(const ImgMeta* __restrict__ imgs, const OctMeta
   const float* p0 = im.src + ((size_t)sx * im.in_w + sy) * 3;
   const float* p1 = p0 + (size_t)im.in_w * 3;
   float* dst = arena + im.work_off + ((size_t)r * im.w0 + c) * 3;
-  float v[3];
 #pragma unroll
   for (int ch = 0; ch < 3; ++ch) {
     float p00 = __ldg(p0 + ch), p01 = __ldg(p0 + 3 + ch), p10 = __ldg(p1 + ch), p11 = __ldg(p1 + 3 + ch);
-    v[ch] = rx * (p11 * ry + p10 * iry) + irx * (p01 * ry + p00 * iry);
-    dst[ch] = v[ch];
+    dst[ch] = rx * (p11 * ry + p10 * iry) + irx * (p01 * ry + p00 * iry);
   }
-  // octave 0 is the working image itself (dog.cc:100-103): its grey plane (imgproc.cc:237-249) falls
-  // out of the same thread, so the working RGB is not read back for it
-  const OctMeta om = octs[blockIdx.z * n_oct];
-  arena[om.gauss_off + (size_t)r * om.pitch + c] = (v[0] + v[1] + v[2]) / 3.f;
 }
 
 // ============================================================ K1b octave grey
-// feature/dog.cc:96-114 (octave o>0 resized from the WORKING image) + lib/imgproc.cc:237-249
-// rgb2grey.  A CTA produces a 32x8 tile of one octave; the source rows it taps (a strip of the
-// interleaved working RGB) are staged through shared memory with coalesced loads, the 12
-// strided taps per pixel then hit shared memory instead of L1.
-#define OG_W 32
-#define OG_H 8
-__global__ void __launch_bounds__(OG_W * OG_H)
-k_octave_grey(const ImgMeta* __restrict__ imgs, const OctMeta* __restrict__ octs, int n_oct,
-              float* __restrict__ arena, int smem_floats) {
-  extern __shared__ float og_smem[];
-  // blockIdx.z enumerates (image, octave >= 1)
-  const int img = blockIdx.z / (n_oct - 1), oct = 1 + blockIdx.z % (n_oct - 1);
-  const OctMeta om = octs[img * n_oct + oct];
-  const int c0 = blockIdx.x * OG_W, r0 = blockIdx.y * OG_H;
-  if (c0 >= om.w || r0 >= om.h) return;
-  const ImgMeta im = imgs[img];
-  const float* work = arena + im.work_off;
-  const int tid = threadIdx.y * OG_W + threadIdx.x;
-  // source rectangle of the tile (both taps of the first and the last output row / column)
-  int s_lo, s_hi, t_lo, t_hi; float fr;
-  bilinear_coef(r0, om.ifx, im.h0, &s_lo, &fr);
-  bilinear_coef(min(r0 + OG_H, om.h) - 1, om.ifx, im.h0, &s_hi, &fr);
-  bilinear_coef(c0, om.ify, im.w0, &t_lo, &fr);
-  bilinear_coef(min(c0 + OG_W, om.w) - 1, om.ify, im.w0, &t_hi, &fr);
-  const int nrow = s_hi + 2 - s_lo, ncol3 = (t_hi + 2 - t_lo) * 3;
-  const bool staged = nrow * ncol3 <= smem_floats;     // always true for the sizes the host computed
-  if (staged) {
-    for (int i = tid; i < nrow * ncol3; i += OG_W * OG_H) {
-      const int rr = i / ncol3, cc = i - rr * ncol3;
-      og_smem[i] = __ldg(work + ((size_t)(s_lo + rr) * im.w0 + t_lo) * 3 + cc);
-    }
-  }
-  __syncthreads();
-  const int c = c0 + threadIdx.x, r = r0 + threadIdx.y;
+// feature/dog.cc:96-114 (octave o>0 resized from the WORKING image) +
+// lib/imgproc.cc:237-249 rgb2grey.
+__global__ void k_octave_grey(const ImgMeta* __restrict__ imgs, const OctMeta* __restrict__ octs,
+                              float* __restrict__ arena) {
+  const OctMeta om = octs[blockIdx.z];
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  int r = blockIdx.y * blockDim.y + threadIdx.y;
   if (c >= om.w || r >= om.h) return;
-  int sx, sy; float rx, ry;
-  bilinear_coef(r, om.ifx, im.h0, &sx, &rx);
-  bilinear_coef(c, om.ify, im.w0, &sy, &ry);
-  float irx = 1.0f - rx, iry = 1.0f - ry;
-  float a[6], b[6];
-  if (staged) {
-    const float* p0 = og_smem + (sx - s_lo) * ncol3 + (sy - t_lo) * 3;
-    const float* p1 = p0 + ncol3;
-#pragma unroll
-    for (int q = 0; q < 6; ++q) { a[q] = p0[q]; b[q] = p1[q]; }
+  const ImgMeta im = imgs[om.img];
+  const float* work = arena + im.work_off;
+  float v0, v1, v2;
+  if (om.oct == 0) {
+    const float* p = work + ((size_t)r * im.w0 + c) * 3;
+    v0 = p[0]; v1 = p[1]; v2 = p[2];
   } else {
+    int sx, sy; float rx, ry;
+    bilinear_coef(r, om.ifx, im.h0, &sx, &rx);
+    bilinear_coef(c, om.ify, im.w0, &sy, &ry);
+    float irx = 1.0f - rx, iry = 1.0f - ry;
     const float* p0 = work + ((size_t)sx * im.w0 + sy) * 3;
     const float* p1 = p0 + (size_t)im.w0 * 3;
-#pragma unroll
-    for (int q = 0; q < 6; ++q) { a[q] = __ldg(p0 + q); b[q] = __ldg(p1 + q); }
+    v0 = rx * (p1[3] * ry + p1[0] * iry) + irx * (p0[3] * ry + p0[0] * iry);
+    v1 = rx * (p1[4] * ry + p1[1] * iry) + irx * (p0[4] * ry + p0[1] * iry);
+    v2 = rx * (p1[5] * ry + p1[2] * iry) + irx * (p0[5] * ry + p0[2] * iry);
   }
-  const float v0 = rx * (b[3] * ry + b[0] * iry) + irx * (a[3] * ry + a[0] * iry);
-  const float v1 = rx * (b[4] * ry + b[1] * iry) + irx * (a[4] * ry + a[1] * iry);
-  const float v2 = rx * (b[5] * ry + b[2] * iry) + irx * (a[5] * ry + a[2] * iry);
   arena[om.gauss_off + (size_t)r * om.pitch + c] = (v0 + v1 + v2) / 3.f;
 }
 
@@ -746,7 +710,7 @@ k_expand_scan(const int* __restrict__ cand_count, const unsigned char* __restric
 #define DESC_WARPS 4
 #define DESC_THREADS (DESC_WARPS * 32)
 #ifndef DESC_REC_CAP
-#define DESC_REC_CAP 384                 // records per flush (more records simply flush again)
+#define DESC_REC_CAP 256                 // records per flush (more records simply flush again)
 #endif
 #define DESC_CHUNKS (DESC_REC_CAP / 32)
 #define DESC_SKIP 0xffffffffu
@@ -758,7 +722,11 @@ k_expand_scan(const int* __restrict__ cand_count, const unsigned char* __restric
 struct DescParams { int hist_scale_factor; int int_factor; };
 
 struct __align__(16) DescWarpSmem {
-  float r_w[DESC_REC_CAP], r_yd[DESC_REC_CAP], r_xd[DESC_REC_CAP], r_hd[DESC_REC_CAP];
+  // one record per surviving sample, written by phase B with everything phase D needs already
+  // multiplied out in the reference's order (sift.cc:57-66): wyx[dy*2+dx] = (weight * fy) * fx,
+  // h = (1 - hbind, hbind); pk = (ybinf+2) | (xbinf+2)<<8 | hbinf<<16
+  float4 r_wyx[DESC_REC_CAP];
+  float2 r_h[DESC_REC_CAP];
   uint32_t r_pk[DESC_REC_CAP];
   uint32_t mask[16][DESC_CHUNKS];
   uint32_t stage[64];                    // packed (xx+128)<<8 | (yy+128), in scan order
@@ -790,6 +758,7 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
   // has its parity.  A record adds to bins hbinf and hbinf+1 — one even, one odd — so
   // each bin has exactly one owner lane and the accumulators can live in registers.
   const int cell = lane >> 1, parity = lane & 1, by = cell >> 2, bx = cell & 3;
+  const int by2 = by + 2, bx2 = bx + 2;
   // Work is handed out one descriptor at a time from a global counter: window sizes vary
   // by an order of magnitude with the keypoint scale, and a static assignment left most
   // warps idle while the unlucky ones worked through their heavy keypoints.
@@ -844,14 +813,11 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
           const int t = ci * 32 + b;
           const uint32_t pk = S.r_pk[t];
           const int hbinf = (int)(pk >> 16);
-          const int dy = by - ((int)(pk & 0xff) - 2);
-          const int dx = bx - ((int)((pk >> 8) & 0xff) - 2);
-          const float yd = S.r_yd[t], xd = S.r_xd[t], hd = S.r_hd[t];
-          const float w_y = S.r_w[t] * (dy ? yd : 1 - yd);
-          const float w_x = w_y * (dx ? xd : 1 - xd);
-          // my parity's bin: hbinf itself (factor 1-hd) or hbinf+1 (factor hd)
+          const int dy = by2 - (int)(pk & 0xff);            // 0 or 1: the record touches this cell
+          const int dx = bx2 - (int)((pk >> 8) & 0xff);
+          // my parity's bin: hbinf itself (factor 1-hbind) or hbinf+1 (factor hbind)
           const int up = (hbinf ^ parity) & 1;
-          const float v = w_x * (up ? hd : 1 - hd);
+          const float v = reinterpret_cast<const float*>(&S.r_wyx[t])[dy * 2 + dx] * reinterpret_cast<const float*>(&S.r_h[t])[up];
           const int q = ((hbinf + up) & 7) >> 1;
           if (q == 0) a0 += v; else if (q == 1) a1 += v; else if (q == 2) a2 += v; else a3 += v;
         }
@@ -892,7 +858,14 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
           }
         }
         const int t = nrec + lane;
-        S.r_pk[t] = pk; S.r_w[t] = wgt; S.r_yd[t] = ybind; S.r_xd[t] = xbind; S.r_hd[t] = hbind;
+        {
+          // sift.cc:57-66 in its own order: w_y = weight * (dy ? ybind : 1 - ybind); w_x = w_y * (dx ? ...)
+          const float wy0 = wgt * (1 - ybind), wy1 = wgt * ybind;
+          const float ix = 1 - xbind;
+          S.r_wyx[t] = make_float4(wy0 * ix, wy0 * xbind, wy1 * ix, wy1 * xbind);
+          S.r_h[t] = make_float2(1 - hbind, hbind);
+          S.r_pk[t] = pk;
+        }
         const int ci = nrec >> 5;
         uint32_t mine = 0;
 #pragma unroll
@@ -1170,23 +1143,9 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
 
   {
     dim3 b(32, 8), g(ceil_div(max_w0, 32), ceil_div(max_h0, 8), n);
-    SIFT_LAUNCH("k_working_resize", k_working_resize, g, b, 0, wk->d_img, wk->d_oct, n_oct, wk->arena);
-    if (n_oct > 1) {
-      // staging buffer for the widest source rectangle of a 32x8 tile (octave 1 has the largest
-      // octave, the last octave the largest source footprint per tile)
-      int max_w1 = 0, max_h1 = 0;
-      size_t need = 0;
-      for (int i = 0; i < n; ++i)
-        for (int o = 1; o < n_oct; ++o) {
-          const OctMeta& om = wk->h_oct[(size_t)i * n_oct + o];
-          max_w1 = std::max(max_w1, om.w); max_h1 = std::max(max_h1, om.h);
-          const size_t rows = (size_t)(OG_H * om.ifx) + 4, cols = (size_t)(OG_W * om.ify) + 4;
-          need = std::max(need, rows * cols * 3);
-        }
-      need = std::min(need, (size_t)48 * 1024 / sizeof(float));
-      dim3 g2(ceil_div(max_w1, OG_W), ceil_div(max_h1, OG_H), n * (n_oct - 1));
-      SIFT_LAUNCH("k_octave_grey", k_octave_grey, g2, b, need * sizeof(float), wk->d_img, wk->d_oct, n_oct, wk->arena, (int)need);
-    }
+    SIFT_LAUNCH("k_working_resize", k_working_resize, g, b, 0, wk->d_img, wk->arena);
+    dim3 g2(ceil_div(max_w0, 32), ceil_div(max_h0, 8), n * n_oct);
+    SIFT_LAUNCH("k_octave_grey", k_octave_grey, g2, b, 0, wk->d_img, wk->d_oct, wk->arena);
   }
   {
     const int R = gt.rmax;
