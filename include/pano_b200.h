@@ -161,6 +161,9 @@ int pano_featureset_import_dev(pano_ctx* ctx, int n_images, const int* n_kp,
                                pano_featureset** out);
 /* Copies image i's rows device-to-device (the sending side); either may be NULL. */
 int pano_featureset_export_dev(pano_featureset* fs, int image, double* d_coor_xy, float* d_desc);
+/* All images at once: image 0's rows, then image 1's, ... packed back to back (one launch instead
+ * of two copies per image); destinations must be 16-byte aligned. */
+int pano_featureset_export_all_dev(pano_featureset* fs, double* d_coor_xy, float* d_desc);
 int pano_featureset_num_images(const pano_featureset* fs);
 /* Number of descriptors of image i (synchronizes on first use). */
 int pano_featureset_count(pano_featureset* fs, int image);

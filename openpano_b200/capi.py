@@ -86,6 +86,7 @@ def _load():
                                           C.c_int, P, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
         "pano_featureset_import_dev": (C.c_int, [C.c_void_p, C.c_int, _ip, _vpp, _vpp, _vpp]),
         "pano_featureset_export_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+        "pano_featureset_export_all_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
         "pano_rgb8_to_mat32f_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
         "pano_rgb8_to_mat32f_batch_dev": (C.c_int, [C.c_void_p, C.c_int, _vpp, _ip, _ip, _ip, _vpp]),
         "pano_crop_rect_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
@@ -155,6 +156,10 @@ class FeatureSet:
         desc = np.zeros((n, 128), np.float32)
         self.eng._check(LIB.pano_featureset_download(self._h, i, _d(coor), _f(desc)))
         return coor, desc
+
+    def export_all_dev(self, d_coor, d_desc):
+        """Every image's rows packed back to back into device buffers (one launch)."""
+        self.eng._check(LIB.pano_featureset_export_all_dev(self._h, C.c_void_p(d_coor or 0), C.c_void_p(d_desc or 0)))
 
     def export_dev(self, i, d_coor, d_desc):
         """Device-to-device copy of image i's rows (coordinates n×2 f64, descriptors n×128 f32)."""

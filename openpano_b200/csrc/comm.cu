@@ -159,11 +159,18 @@ int pano_comm_allgather_features(pano_comm* c, pano_featureset* local, int n_ima
       (rc = ctx_alloc(ctx, (void**)&c_send, pad * 2 * sizeof(double))) || (rc = ctx_alloc(ctx, (void**)&c_all, pad * W * 2 * sizeof(double))))
     goto done;
   {
+    // this rank's rows into the send buffers: one launch for all images
+    std::vector<void*> dsts; std::vector<const void*> srcs; std::vector<size_t> sizes;
     size_t off = 0;
     for (int q = 0; q < mine; ++q) {
-      if ((rc = pano_featureset_export_dev(local, q, local->d_coor ? c_send + off * 2 : nullptr, d_send + off * 128))) goto done;
-      off += local->h_count[q];
+      const size_t nq = (size_t)local->h_count[q];
+      if (nq) {
+        dsts.push_back(d_send + off * 128); srcs.push_back(local->d_desc + local->base[q] * 128); sizes.push_back(nq * 128 * sizeof(float));
+        if (local->d_coor) { dsts.push_back(c_send + off * 2); srcs.push_back(local->d_coor + local->base[q] * 2); sizes.push_back(nq * 2 * sizeof(double)); }
+      }
+      off += nq;
     }
+    if ((rc = ctx_copy_blocks(ctx, (int)dsts.size(), dsts.data(), srcs.data(), sizes.data()))) goto done;
   }
   {
     ncclResult_t r1 = g_nccl.GroupStart();

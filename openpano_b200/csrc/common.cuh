@@ -108,6 +108,7 @@ int  ctx_zero(pano_ctx* ctx, void* d_dst, size_t bytes);
 #define CTX_MAX_SEGS 8
 int  ctx_put_many(pano_ctx* ctx, int n, void* const* d_dst, const void* const* h_src, const size_t* bytes);
 int  ctx_store_many(pano_ctx* ctx, int n, void* const* h_pinned_dst, const void* const* d_src, const size_t* bytes);
+int  ctx_copy_blocks(pano_ctx* ctx, int n, void* const* dst, const void* const* src, const size_t* bytes);
 void ctx_prof_begin(pano_ctx* ctx, const char* name);
 void ctx_prof_end(pano_ctx* ctx);
 

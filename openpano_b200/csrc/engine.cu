@@ -300,6 +300,41 @@ int ctx_store_many(pano_ctx* ctx, int n, void* const* h_pinned_dst, const void* 
   return launch_segs(ctx, segs, m, max_words);
 }
 
+// Many device-to-device block moves in ONE launch (the descriptor exchange moves two blocks per
+// image: dozens of cudaMemcpyAsync calls cost more host time than the copies take on the GPU).
+struct CopySeg { void* dst; const void* src; unsigned long long bytes; };
+__global__ void k_copy_blocks(const CopySeg* __restrict__ segs) {
+  const CopySeg sg = segs[blockIdx.y];
+  const size_t n16 = sg.bytes >> 4;
+  const uint4* s4 = (const uint4*)sg.src;
+  uint4* d4 = (uint4*)sg.dst;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) d4[i] = s4[i];
+  const size_t tail0 = n16 << 4;
+  for (size_t i = tail0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < sg.bytes; i += (size_t)gridDim.x * blockDim.x)
+    ((unsigned char*)sg.dst)[i] = ((const unsigned char*)sg.src)[i];
+}
+
+// dst / src must be 16-byte aligned device pointers (or bytes[i] < 16)
+int ctx_copy_blocks(pano_ctx* ctx, int n, void* const* dst, const void* const* src, const size_t* bytes) {
+  std::vector<CopySeg> segs;
+  size_t mx = 0;
+  for (int i = 0; i < n; ++i)
+    if (bytes[i]) { segs.push_back(CopySeg{dst[i], src[i], (unsigned long long)bytes[i]}); mx = std::max(mx, bytes[i]); }
+  if (segs.empty()) return PANO_OK;
+  CopySeg* d_segs = nullptr;
+  int rc = ctx_alloc(ctx, (void**)&d_segs, segs.size() * sizeof(CopySeg));
+  if (rc) return rc;
+  if ((rc = ctx_put(ctx, d_segs, segs.data(), segs.size() * sizeof(CopySeg)))) { ctx_free(ctx, d_segs); return rc; }
+  dim3 grid((unsigned)std::min<size_t>(std::max<size_t>(mx / (16 * 256 * 4), 1), 64), (unsigned)segs.size());
+  ctx->launches++;
+  if (ctx->profiling) ctx_prof_begin(ctx, "k_copy_blocks");
+  k_copy_blocks<<<grid, 256, 0, ctx->stream>>>(d_segs);
+  if (ctx->profiling) ctx_prof_end(ctx);
+  cudaError_t e = cudaGetLastError();
+  ctx_free(ctx, d_segs);
+  return e == cudaSuccess ? PANO_OK : ctx_cuda(ctx, e, "k_copy_blocks");
+}
+
 static cudaEvent_t get_event(pano_ctx* ctx) {
   if (!ctx->event_pool.empty()) { cudaEvent_t e = ctx->event_pool.back(); ctx->event_pool.pop_back(); return e; }
   cudaEvent_t e;
@@ -636,12 +671,22 @@ static int featureset_build(pano_ctx* ctx, int n_images, const int* n_kp, const 
   if (!rc && coor) rc = ctx_alloc(ctx, (void**)&fs->d_coor, (size_t)std::max(total, 1LL) * 2 * sizeof(double));
   if (rc) { featureset_release(fs); return rc; }
   cudaError_t e = cudaSuccess;
-  for (int i = 0; i < n_images && e == cudaSuccess; ++i) {
-    if (!n_kp[i]) continue;
-    const cudaMemcpyKind kind = from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    e = cudaMemcpyAsync(fs->d_desc + fs->base[i] * 128, desc[i], (size_t)n_kp[i] * 128 * sizeof(float), kind, ctx->stream);
-    if (e == cudaSuccess && coor && coor[i])
-      e = cudaMemcpyAsync(fs->d_coor + fs->base[i] * 2, coor[i], (size_t)n_kp[i] * 2 * sizeof(double), kind, ctx->stream);
+  if (from_device) {
+    // every image's rows in one launch (sources are device blocks of the exchange buffers)
+    std::vector<void*> dsts; std::vector<const void*> srcs; std::vector<size_t> sizes;
+    for (int i = 0; i < n_images; ++i) {
+      if (!n_kp[i]) continue;
+      dsts.push_back(fs->d_desc + fs->base[i] * 128); srcs.push_back(desc[i]); sizes.push_back((size_t)n_kp[i] * 128 * sizeof(float));
+      if (coor && coor[i]) { dsts.push_back(fs->d_coor + fs->base[i] * 2); srcs.push_back(coor[i]); sizes.push_back((size_t)n_kp[i] * 2 * sizeof(double)); }
+    }
+    if (ctx_copy_blocks(ctx, (int)dsts.size(), dsts.data(), srcs.data(), sizes.data())) e = cudaErrorUnknown;
+  } else {
+    for (int i = 0; i < n_images && e == cudaSuccess; ++i) {
+      if (!n_kp[i]) continue;
+      e = cudaMemcpyAsync(fs->d_desc + fs->base[i] * 128, desc[i], (size_t)n_kp[i] * 128 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess && coor && coor[i])
+        e = cudaMemcpyAsync(fs->d_coor + fs->base[i] * 2, coor[i], (size_t)n_kp[i] * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    }
   }
   if (e == cudaSuccess) {
     if (from_device) {
@@ -693,6 +738,24 @@ int pano_featureset_export_dev(pano_featureset* fs, int image, double* d_coor_xy
                                    cudaMemcpyDeviceToDevice, ctx->stream));
   }
   return PANO_OK;
+}
+
+int pano_featureset_export_all_dev(pano_featureset* fs, double* d_coor_xy, float* d_desc) {
+  if (fs) ctx_enter(fs->ctx);
+  if (!fs) return PANO_ERR_INVALID;
+  int rc = featureset_sync_counts(fs);
+  if (rc) return rc;
+  pano_ctx* ctx = fs->ctx;
+  if (d_coor_xy && !fs->d_coor) return ctx_fail(ctx, PANO_ERR_INVALID, "featureset has no coordinates");
+  std::vector<void*> dsts; std::vector<const void*> srcs; std::vector<size_t> sizes;
+  size_t off = 0;
+  for (int i = 0; i < fs->n_images; ++i) {
+    const size_t n = (size_t)fs->h_count[i];
+    if (n && d_desc) { dsts.push_back(d_desc + off * 128); srcs.push_back(fs->d_desc + fs->base[i] * 128); sizes.push_back(n * 128 * sizeof(float)); }
+    if (n && d_coor_xy) { dsts.push_back(d_coor_xy + off * 2); srcs.push_back(fs->d_coor + fs->base[i] * 2); sizes.push_back(n * 2 * sizeof(double)); }
+    off += n;
+  }
+  return ctx_copy_blocks(ctx, (int)dsts.size(), dsts.data(), srcs.data(), sizes.data());
 }
 
 int pano_featureset_num_images(const pano_featureset* fs) {

@@ -270,6 +270,7 @@ struct PairMeta {
   int side_small, side_large;    // indices into the side table (small set queries / large set queries)
   int n_small, n_large;
   long long out_off;             // per-row decision of the smaller set
+  int rev, pad;                  // the pair was swapped (its first image is the larger set): MatchData::reverse
 };
 
 #define OUT_PENDING (-2)
@@ -398,6 +399,96 @@ k_exact_cands(const float* __restrict__ desc, const SideMeta* __restrict__ sides
   }
 }
 
+// ------------------------------------------------------------------ result lists on the device
+// The decisions are one int per row of the smaller set; what the caller wants is MatchData
+// (matcher.hh:14-25): per pair the (i-index, j-index) list in ascending row order.  Counting,
+// the prefix over pairs and the ordered compaction run here, so that only the matches themselves
+// (8 bytes each) cross PCIe and the host never walks the rows.
+// hdr layout (ints): [0] total, [1] undecided rows, [2 .. 2+n) count, [2+n .. 3+2n) offset
+__global__ void __launch_bounds__(256)
+k_match_count(const PairMeta* __restrict__ pairs, const int* __restrict__ out, int n_pairs, int* __restrict__ hdr) {
+  __shared__ int s_c[8], s_p[8];
+  const PairMeta pm = pairs[blockIdx.x];
+  int c = 0, pend = 0;
+  for (int r = threadIdx.x; r < pm.n_small; r += 256) {
+    const int v = out[pm.out_off + r];
+    c += v >= 0; pend += v == OUT_PENDING;
+  }
+  for (int off = 16; off; off >>= 1) { c += __shfl_xor_sync(0xffffffffu, c, off); pend += __shfl_xor_sync(0xffffffffu, pend, off); }
+  if ((threadIdx.x & 31) == 0) { s_c[threadIdx.x >> 5] = c; s_p[threadIdx.x >> 5] = pend; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; ++q) { c += s_c[q]; pend += s_p[q]; }
+    hdr[2 + blockIdx.x] = c;
+    if (pend) atomicAdd(&hdr[1], pend);
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+k_match_offsets(int n_pairs, int* __restrict__ hdr) {
+  __shared__ int s_w[32];
+  __shared__ int s_carry;
+  const int* cnt = hdr + 2;
+  int* off = hdr + 2 + n_pairs;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_pairs; base += 1024) {
+    const int k = base + tid;
+    const int v = k < n_pairs ? cnt[k] : 0;
+    int incl = v;
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) s_w[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int w = s_w[lane], a = w;
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, a, d); if (lane >= d) a += t; }
+      s_w[lane] = a - w;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    if (k < n_pairs) off[k] = carry + s_w[wid] + incl - v;
+    __syncthreads();
+    if (tid == 1023) s_carry = carry + s_w[31] + incl;
+    __syncthreads();
+  }
+  if (tid == 0) { off[n_pairs] = s_carry; hdr[0] = s_carry; }
+}
+
+__global__ void __launch_bounds__(256)
+k_match_write(const PairMeta* __restrict__ pairs, const int* __restrict__ out, int n_pairs, const int* __restrict__ hdr,
+              int* __restrict__ dense) {
+  __shared__ int s_w[8];
+  __shared__ int s_base;
+  const PairMeta pm = pairs[blockIdx.x];
+  int* dst = dense + 2 * (size_t)hdr[2 + n_pairs + blockIdx.x];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int r0 = 0; r0 < pm.n_small; r0 += 256) {
+    const int r = r0 + tid;
+    const int j = r < pm.n_small ? out[pm.out_off + r] : -1;
+    const unsigned bal = __ballot_sync(0xffffffffu, j >= 0);
+    if (lane == 0) s_w[wid] = __popc(bal);
+    __syncthreads();
+    int before = s_base;
+    for (int q = 0; q < wid; ++q) before += s_w[q];
+    if (j >= 0) {
+      int* d = dst + 2 * (before + __popc(bal & ((1u << lane) - 1)));
+      if (pm.rev) { d[0] = j; d[1] = r; } else { d[0] = r; d[1] = j; }        // MatchData::reverse (matcher.cc:127-128)
+    }
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int q = 0; q < 8; ++q) t += s_w[q]; s_base += t; }
+    __syncthreads();
+  }
+}
+
+// copies hdr[0] * 2 ints of the dense list (the count lives on the device) into pinned host memory
+__global__ void k_match_download(int* __restrict__ h_dst, const int* __restrict__ dense, const int* __restrict__ hdr) {
+  const size_t n = (size_t)hdr[0] * 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) h_dst[i] = dense[i];
+}
+
 // ------------------------------------------------------------------ host driver
 
 struct MatchPlan {
@@ -428,7 +519,7 @@ static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int
     const int ns = fs->h_count[is], nl = fs->h_count[il];
     SideMeta a{fs->base[is], fs->base[il], ns, nl, pl.res_total}; pl.res_total += ns;
     SideMeta b{fs->base[il], fs->base[is], nl, ns, pl.res_total}; pl.res_total += nl;
-    PairMeta pm{(int)pl.sides.size(), (int)pl.sides.size() + 1, ns, nl, pl.out_total};
+    PairMeta pm{(int)pl.sides.size(), (int)pl.sides.size() + 1, ns, nl, pl.out_total, rev ? 1 : 0, 0};
     pl.out_total += ns;
     pl.sides.push_back(a); pl.sides.push_back(b);
     pl.pairs.push_back(pm);
@@ -608,42 +699,41 @@ int pano_match_pairs(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int*
   MatchBuffers b;
   int rc = match_common(ctx, fs, n_pairs, ij, p, pl, b);
   if (rc) { free_buffers(ctx, b, false); return rc; }
-  std::vector<int> h_out(std::max<long long>(pl.out_total, 1));
-  int* h_stage = (int*)ctx_ring(ctx, (size_t)std::max<long long>(pl.out_total, 1) * sizeof(int));
-  if (!h_stage) { free_buffers(ctx, b, false); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned ring allocation failed"); }
-  rc = ctx_store(ctx, h_stage, b.out, pl.out_total * sizeof(int));
+  // count -> offsets -> ordered compaction on the device; one read-back of header + matches
+  const size_t n_hdr = 3 + 2 * (size_t)n_pairs;
+  const size_t cap = (size_t)std::max<long long>(pl.out_total, 1) * 2;
+  int *d_hdr = nullptr, *d_dense = nullptr;
+  if ((rc = ctx_alloc(ctx, (void**)&d_hdr, n_hdr * sizeof(int))) || (rc = ctx_alloc(ctx, (void**)&d_dense, cap * sizeof(int)))) {
+    ctx_free(ctx, d_hdr); ctx_free(ctx, d_dense); free_buffers(ctx, b, false); return rc;
+  }
+  int* h_stage = (int*)ctx_ring(ctx, (n_hdr + cap) * sizeof(int));
+  if (!h_stage) { ctx_free(ctx, d_hdr); ctx_free(ctx, d_dense); free_buffers(ctx, b, false); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned ring allocation failed"); }
+  auto finish = [&](int code) { ctx_free(ctx, d_hdr); ctx_free(ctx, d_dense); free_buffers(ctx, b, false); return code; };
+  if ((rc = ctx_zero(ctx, d_hdr, 2 * sizeof(int)))) return finish(rc);
+  if (n_pairs > 0) {
+    ctx->launches += 4;
+    k_match_count<<<n_pairs, 256, 0, ctx->stream>>>(b.pairs, b.out, n_pairs, d_hdr);
+    k_match_offsets<<<1, 1024, 0, ctx->stream>>>(n_pairs, d_hdr);
+    k_match_write<<<n_pairs, 256, 0, ctx->stream>>>(b.pairs, b.out, n_pairs, d_hdr, d_dense);
+    k_match_download<<<std::max(1, std::min(ctx->num_sms, (int)(cap / 4096) + 1)), 256, 0, ctx->stream>>>(h_stage + n_hdr, d_dense, d_hdr);
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return finish(ctx_cuda(ctx, le, "match result compaction"));
+  }
+  rc = ctx_store(ctx, h_stage, d_hdr, n_hdr * sizeof(int));
   cudaError_t e = ctx_spin_stream(ctx);
-  free_buffers(ctx, b, false);
-  if (rc) return rc;
-  if (e != cudaSuccess) return ctx_cuda(ctx, e, "match download");
-  if (pl.out_total) memcpy(h_out.data(), h_stage, pl.out_total * sizeof(int));
+  if (rc) return finish(rc);
+  if (e != cudaSuccess) return finish(ctx_cuda(ctx, e, "match download"));
+  finish(0);
+  if (n_pairs > 0 && h_stage[1] != 0) return ctx_fail(ctx, PANO_ERR_CUDA, "match: %d undecided rows (internal error)", h_stage[1]);
+  const int total = n_pairs > 0 ? h_stage[0] : 0;
   out->n_pairs = n_pairs;
   out->count = (int*)calloc(std::max(n_pairs, 1), sizeof(int));
   out->offset = (int*)calloc(n_pairs + 1, sizeof(int));
-  int total = 0;
-  for (int k = 0; k < n_pairs; ++k) {
-    const PairMeta& pm = pl.pairs[k];
-    int c = 0;
-    for (int r = 0; r < pm.n_small; ++r) {
-      if (h_out[pm.out_off + r] == OUT_PENDING) {
-        pano_matches_free(out);
-        return ctx_fail(ctx, PANO_ERR_CUDA, "match: undecided row (internal error)");
-      }
-      c += h_out[pm.out_off + r] >= 0;
-    }
-    out->count[k] = c; out->offset[k] = total; total += c;
-  }
-  out->offset[n_pairs] = total;
-  out->idx = (int*)calloc(std::max(total, 1) * 2, sizeof(int));
-  for (int k = 0; k < n_pairs; ++k) {
-    const PairMeta& pm = pl.pairs[k];
-    int* dst = out->idx + 2 * out->offset[k];
-    for (int r = 0; r < pm.n_small; ++r) {
-      int j = h_out[pm.out_off + r];
-      if (j < 0) continue;
-      if (pl.rev[k]) { dst[0] = j; dst[1] = r; } else { dst[0] = r; dst[1] = j; }  // MatchData::reverse
-      dst += 2;
-    }
+  out->idx = (int*)calloc((size_t)std::max(total, 1) * 2, sizeof(int));
+  if (n_pairs > 0) {
+    memcpy(out->count, h_stage + 2, (size_t)n_pairs * sizeof(int));
+    memcpy(out->offset, h_stage + 2 + n_pairs, (size_t)(n_pairs + 1) * sizeof(int));
+    memcpy(out->idx, h_stage + n_hdr, (size_t)total * 2 * sizeof(int));
   }
   return PANO_OK;
 }

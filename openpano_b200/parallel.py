@@ -261,20 +261,18 @@ class DistributedStitcher:
 
         # ---- C1: all-gather of the descriptor sets
         def exchange():
-            counts_t = torch.zeros(n_images, dtype=torch.int64, device=dev)
-            if mine:
-                counts_t[torch.tensor(mine, device=dev)] = torch.tensor([fs_local.count(q) for q in range(len(mine))],
-                                                                         dtype=torch.int64, device=dev)
+            arr = np.zeros(n_images, np.int64)
+            for q, k in enumerate(mine):
+                arr[k] = fs_local.count(q)
+            counts_t = torch.from_numpy(arr).to(dev)
             dist.all_reduce(counts_t)
             counts = [int(c) for c in counts_t.tolist()]
             rows = [sum(counts[k] for k in owners[r]) for r in range(world)]
             pad = max(max(rows), 1)
-            my_d = torch.zeros((pad, 128), dtype=torch.float32, device=dev)
-            my_c = torch.zeros((pad, 2), dtype=torch.float64, device=dev)
-            off = 0
-            for q, k in enumerate(mine):
-                fs_local.export_dev(q, my_c.data_ptr() + off * 16, my_d.data_ptr() + off * 512)
-                off += counts[k]
+            my_d = torch.empty((pad, 128), dtype=torch.float32, device=dev)
+            my_c = torch.empty((pad, 2), dtype=torch.float64, device=dev)
+            if mine:
+                fs_local.export_all_dev(my_c.data_ptr(), my_d.data_ptr())      # one launch for all owned images
             all_d = torch.empty((world * pad, 128), dtype=torch.float32, device=dev)
             all_c = torch.empty((world * pad, 2), dtype=torch.float64, device=dev)
             dist.all_gather_into_tensor(all_d, my_d)
@@ -297,29 +295,34 @@ class DistributedStitcher:
         tasks = dealt[rank]
         results = self._timed("match", lambda: eng.match_pairs(fs_all, [pairs[t] for t in tasks], params) if tasks else [])
 
-        # ---- match lists to every rank: per-task counts (all-reduce) + one padded all-gather
+        # ---- match lists to rank 0: ONE fixed-size all-gather.  A pair yields at most min(N_i, N_j)
+        # matches and every rank knows the counts after C1, so the slot sizes need no extra round trip:
+        # rank r sends [number of matches per dealt task ..., (i, j) ...] padded to the largest bound.
         def gather_lists():
-            cnt = torch.zeros(len(pairs), dtype=torch.int64, device=dev)
+            bound = [sum(min(counts[pairs[t][0]], counts[pairs[t][1]]) for t in dealt[r]) for r in range(world)]
+            ntask = max(max(len(d) for d in dealt), 1)
+            pad = ntask + 2 * max(max(bound), 1)
+            host = np.zeros(pad, np.int32)
             if tasks:
-                cnt[torch.tensor(tasks, device=dev)] = torch.tensor([len(m) for m in results], dtype=torch.int64, device=dev)
-            dist.all_reduce(cnt)
-            cnt_h = cnt.tolist()
-            pad = max(max(sum(cnt_h[t] for t in dealt[r]) for r in range(world)), 1)
-            my = torch.zeros((pad, 2), dtype=torch.int32, device=dev)
-            if tasks and sum(len(m) for m in results):
-                flat = np.concatenate([m for m in results if len(m)]).astype(np.int32)
-                my[:len(flat)] = torch.from_numpy(flat).to(dev)
-            allm = torch.empty((world * pad, 2), dtype=torch.int32, device=dev)
+                host[:len(tasks)] = [len(m) for m in results]
+                flat = [m.reshape(-1) for m in results if len(m)]
+                if flat:
+                    cat = np.concatenate(flat).astype(np.int32)
+                    host[ntask:ntask + len(cat)] = cat
+            my = torch.from_numpy(host).to(dev, non_blocking=False)
+            allm = torch.empty(world * pad, dtype=torch.int32, device=dev)
             dist.all_gather_into_tensor(allm, my)
             if rank != 0:
                 return None
-            host = allm.cpu().numpy()
+            got = allm.cpu().numpy()
             full = [None] * len(pairs)
             for r in range(world):
-                off = r * pad
-                for t in dealt[r]:
-                    full[t] = host[off:off + cnt_h[t]]
-                    off += cnt_h[t]
+                seg = got[r * pad:(r + 1) * pad]
+                off = ntask
+                for q, t in enumerate(dealt[r]):
+                    c = int(seg[q])
+                    full[t] = seg[off:off + 2 * c].reshape(-1, 2)
+                    off += 2 * c
             return full
         matches = self._timed("gather_matches", gather_lists)
 
