@@ -710,7 +710,7 @@ k_expand_scan(const int* __restrict__ cand_count, const unsigned char* __restric
 #define DESC_WARPS 4
 #define DESC_THREADS (DESC_WARPS * 32)
 #ifndef DESC_REC_CAP
-#define DESC_REC_CAP 256                 // records per flush (more records simply flush again)
+#define DESC_REC_CAP 384                 // records per flush (more records simply flush again)
 #endif
 #define DESC_CHUNKS (DESC_REC_CAP / 32)
 #define DESC_SKIP 0xffffffffu
@@ -722,11 +722,7 @@ k_expand_scan(const int* __restrict__ cand_count, const unsigned char* __restric
 struct DescParams { int hist_scale_factor; int int_factor; };
 
 struct __align__(16) DescWarpSmem {
-  // one record per surviving sample, written by phase B with everything phase D needs already
-  // multiplied out in the reference's order (sift.cc:57-66): wyx[dy*2+dx] = (weight * fy) * fx,
-  // h = (1 - hbind, hbind); pk = (ybinf+2) | (xbinf+2)<<8 | hbinf<<16
-  float4 r_wyx[DESC_REC_CAP];
-  float2 r_h[DESC_REC_CAP];
+  float r_w[DESC_REC_CAP], r_yd[DESC_REC_CAP], r_xd[DESC_REC_CAP], r_hd[DESC_REC_CAP];
   uint32_t r_pk[DESC_REC_CAP];
   uint32_t mask[16][DESC_CHUNKS];
   uint32_t stage[64];                    // packed (xx+128)<<8 | (yy+128), in scan order
@@ -758,7 +754,6 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
   // has its parity.  A record adds to bins hbinf and hbinf+1 — one even, one odd — so
   // each bin has exactly one owner lane and the accumulators can live in registers.
   const int cell = lane >> 1, parity = lane & 1, by = cell >> 2, bx = cell & 3;
-  const int by2 = by + 2, bx2 = bx + 2;
   // Work is handed out one descriptor at a time from a global counter: window sizes vary
   // by an order of magnitude with the keypoint scale, and a static assignment left most
   // warps idle while the unlucky ones worked through their heavy keypoints.
@@ -813,11 +808,14 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
           const int t = ci * 32 + b;
           const uint32_t pk = S.r_pk[t];
           const int hbinf = (int)(pk >> 16);
-          const int dy = by2 - (int)(pk & 0xff);            // 0 or 1: the record touches this cell
-          const int dx = bx2 - (int)((pk >> 8) & 0xff);
-          // my parity's bin: hbinf itself (factor 1-hbind) or hbinf+1 (factor hbind)
+          const int dy = by - ((int)(pk & 0xff) - 2);
+          const int dx = bx - ((int)((pk >> 8) & 0xff) - 2);
+          const float yd = S.r_yd[t], xd = S.r_xd[t], hd = S.r_hd[t];
+          const float w_y = S.r_w[t] * (dy ? yd : 1 - yd);
+          const float w_x = w_y * (dx ? xd : 1 - xd);
+          // my parity's bin: hbinf itself (factor 1-hd) or hbinf+1 (factor hd)
           const int up = (hbinf ^ parity) & 1;
-          const float v = reinterpret_cast<const float*>(&S.r_wyx[t])[dy * 2 + dx] * reinterpret_cast<const float*>(&S.r_h[t])[up];
+          const float v = w_x * (up ? hd : 1 - hd);
           const int q = ((hbinf + up) & 7) >> 1;
           if (q == 0) a0 += v; else if (q == 1) a1 += v; else if (q == 2) a2 += v; else a3 += v;
         }
@@ -858,14 +856,7 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
           }
         }
         const int t = nrec + lane;
-        {
-          // sift.cc:57-66 in its own order: w_y = weight * (dy ? ybind : 1 - ybind); w_x = w_y * (dx ? ...)
-          const float wy0 = wgt * (1 - ybind), wy1 = wgt * ybind;
-          const float ix = 1 - xbind;
-          S.r_wyx[t] = make_float4(wy0 * ix, wy0 * xbind, wy1 * ix, wy1 * xbind);
-          S.r_h[t] = make_float2(1 - hbind, hbind);
-          S.r_pk[t] = pk;
-        }
+        S.r_pk[t] = pk; S.r_w[t] = wgt; S.r_yd[t] = ybind; S.r_xd[t] = xbind; S.r_hd[t] = hbind;
         const int ci = nrec >> 5;
         uint32_t mine = 0;
 #pragma unroll
