@@ -483,13 +483,22 @@ def main():
             t = kernels[top]
             # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this
             # same workload (profiles/*_traffic.json, written by tools/ncu_summary.py); null if absent
-            traffic = None
+            traffic, issue = None, None
             tr_files = sorted((ROOT / "profiles").glob("*_traffic.json"))
             if tr_files and not args.bands:
-                traffic = json.loads(tr_files[-1].read_text()).get(top, {}).get("dram_bytes_per_launch")
+                ent = json.loads(tr_files[-1].read_text()).get(top, {})
+                traffic = ent.get("dram_bytes_per_launch")
+                wi = ent.get("warp_instructions_per_launch")
+                if wi:
+                    # issue-slot roofline: a kernel cannot finish before its warp instructions have gone through
+                    # the 148 x 4 schedulers (one instruction per scheduler per cycle) at the SM clock seen in this run
+                    sm_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+                    floor_ms = wi / (148 * 4 * sm_hz) * 1e3
+                    issue = {"warp_instructions": wi, "floor_ms": floor_ms, "frac": floor_ms / t["avg_ms"],
+                             "source": tr_files[-1].name}
             roof = {"kernel": top, "bound": t.get("bound"), "achieved": t.get("achieved"), "peak": t.get("peak"),
                     "unit": t.get("unit"), "frac": t.get("frac"), "traffic": traffic, "peak_source": peak_src,
-                    "share_of_step": t["share"], "avg_ms": t["avg_ms"]}
+                    "share_of_step": t["share"], "avg_ms": t["avg_ms"], "issue": issue}
             # the dominant kernel (k_descriptor) is issue-bound: its §8d bytes are only its outputs, so its
             # HBM fraction says little.  Beside it, the largest kernel that IS bandwidth-limited.
             bw = [k for k, v in kernels.items() if v.get("bound") == "hbm" and (v.get("frac") or 0) >= 0.05]

@@ -38,6 +38,7 @@
 #define TC_TILE_BLOCKS 2               // target tile = 2 blocks = 256 rows
 #define TC_STAGES 2
 #define TC_THREADS 256
+#define TC_FILTER_FROM 4096            // columns after which the epilogue pre-filters against the running second best
 
 // ------------------------------------------------------------------ prep
 
@@ -297,26 +298,18 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
         const uint32_t as = gt & 1u;
         mbar_wait(smem_u32(&bars->acc_full[as]), (gt >> 1) & 1u);
         tc_fence_after();
-        // Four independent (best, second) pairs, column j -> pair j & 3: a single pair is a serial
-        // chain of dependent min/max (two per element, ~5 cycles each) that one warp per scheduler
-        // cannot hide — measured 1.7 us per 128x256 tile against 0.7 us of MMA; merged per tile below.
-        int k1[4], k2[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { k1[q] = 0x7fffffff; k2[q] = 0x7fffffff; }
-        // the next 32 columns are already on their way from TMEM while these are compared
-        uint32_t v[2][32];
-        tmem_ld32(lane_addr + (uint32_t)(as * 256), v[0]);
+        int k1 = 0x7fffffff, k2 = 0x7fffffff;
 #pragma unroll
         for (int c0 = 0; c0 < 256; c0 += 32) {
-          const int cur = (c0 >> 5) & 1;
+          uint32_t v[32];
+          tmem_ld32(lane_addr + (uint32_t)(as * 256 + c0), v);
           tmem_ld_wait();
-          if (c0 + 32 < 256) tmem_ld32(lane_addr + (uint32_t)(as * 256 + c0 + 32), v[cur ^ 1]);
           if (FILTER) {
             // branch-free hit mask first: a conditional body inside the 256-way unrolled compare
             // blows the loop up past the instruction cache (measured 3x slower per tile)
             unsigned hit = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) hit |= ((int)(v[cur][j] & 0xffffff00u) <= thr) ? (1u << j) : 0u;
+            for (int j = 0; j < 32; ++j) hit |= ((int)(v[j] & 0xffffff00u) <= thr) ? (1u << j) : 0u;
             while (hit) {
               const int j = __ffs(hit) - 1;
               hit &= hit - 1;
@@ -327,27 +320,36 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
               }
             }
           } else {
+            // The packed-key update below is four ALU-pipe instructions per element, and the ALU pipe
+            // issues one warp instruction per two cycles: 256 cycles per 32 columns, more than the MMA
+            // takes (ncu: tensor pipe 38 %, every epilogue stall "selected" or "wait").  Once a few
+            // thousand columns have been seen, almost no score is below the row's running second best
+            // any more: then one FADD (FMA pipe) and one funnel shift (ALU pipe) per element — the
+            // two pipes issue in parallel — collect the sign bits of (score - second best), and the
+            // update runs only for the rare 32-column chunk in which some row of the warp has a hit.
+            // Scores are positive finite floats, g2 has its low byte clear, so (v < g2) as floats is
+            // exactly (v & ~0xff) < g2 as the packed keys compare.
+            if (t * 256 >= TC_FILTER_FROM) {
+              const float lim = __int_as_float(g2);
+              unsigned hit = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) hit = __funnelshift_l(__float_as_uint(__uint_as_float(v[j]) - lim), hit, 1);
+              if (hit == 0) continue;
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int key = (int)((v[cur][j] & 0xffffff00u) | (uint32_t)(c0 + j));
-              k2[j & 3] = min(k2[j & 3], max(k1[j & 3], key));
-              k1[j & 3] = min(k1[j & 3], key);
+              const int key = (int)((v[j] & 0xffffff00u) | (uint32_t)(c0 + j));
+              k2 = min(k2, max(k1, key));
+              k1 = min(k1, key);
             }
           }
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->acc_empty[as]));
         if (!FILTER) {
-          // the four pairs -> the tile's top-2 (keys are distinct: the column sits in the low byte)
-          int m1 = k1[0], m2 = k2[0];
-#pragma unroll
-          for (int q = 1; q < 4; ++q) {
-            m2 = min(max(m1, k1[q]), min(m2, k2[q]));
-            m1 = min(m1, k1[q]);
-          }
           // merge the tile's top-2 into the running top-2
-          const int v1 = m1 & (int)0xffffff00, v2 = m2 & (int)0xffffff00;
-          if (v1 < g1) { g2 = min(g1, v2); g1 = v1; gi = t * 256 + (m1 & 0xff); }
+          const int v1 = k1 & (int)0xffffff00, v2 = k2 & (int)0xffffff00;
+          if (v1 < g1) { g2 = min(g1, v2); g1 = v1; gi = t * 256 + (k1 & 0xff); }
           else g2 = min(g2, v1);
         }
       }

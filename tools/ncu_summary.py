@@ -58,5 +58,33 @@ def full(path):
                 print(f"  {k:88s} {r[h.index(k)]:>16s} {units[h.index(k)]}")
 
 
+def traffic(path):
+    """JSON for bench.py's `roofline.traffic` / `roofline.issue`: per kernel (bench.py's short names) the DRAM
+    bytes and warp instructions of ONE launch (mean over the captured launches) from an `ncu --set full` report."""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h = rows[0]
+    acc = collections.OrderedDict()
+    alias = {"k_blur_dog_fast": "k_blur_dog", "k_tc_pass<0>": "k_tc_top2", "k_tc_pass<1>": "k_tc_filter",
+             "k_mb_blur_tma<6>": "k_mb_blur", "k_mb_blur_tma<9>": "k_mb_blur"}
+    for r in rows[2:]:
+        name = r[h.index("Kernel Name")].split("(")[0].replace("void ", "").strip()
+        name = alias.get(name, name)
+        a = acc.setdefault(name, {"n": 0, "dram": 0.0, "inst": 0.0, "ns": 0.0, "sm_hz": 0.0})
+        f = lambda k: float(r[h.index(k)].replace(",", "")) if k in h and r[h.index(k)] not in ("", "n/a") else 0.0
+        unit = lambda k: rows[1][h.index(k)] if k in h else ""
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        a["n"] += 1
+        a["dram"] += f("dram__bytes_read.sum") * scale.get(unit("dram__bytes_read.sum"), 1.0) + \
+            f("dram__bytes_write.sum") * scale.get(unit("dram__bytes_write.sum"), 1.0)
+        a["inst"] += f("smsp__inst_executed.sum")
+        a["ns"] += f("gpu__time_duration.sum") * {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}.get(unit("gpu__time_duration.sum"), 1.0)
+        a["sm_hz"] += f("sm__cycles_elapsed.avg.per_second") * {"Hz": 1.0, "Khz": 1e3, "Mhz": 1e6, "Ghz": 1e9}.get(unit("sm__cycles_elapsed.avg.per_second"), 1.0)
+    res = {k: {"dram_bytes_per_launch": v["dram"] / v["n"], "warp_instructions_per_launch": v["inst"] / v["n"],
+               "ncu_duration_ms": v["ns"] / v["n"] / 1e6, "ncu_sm_hz": v["sm_hz"] / v["n"]} for k, v in acc.items()}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
