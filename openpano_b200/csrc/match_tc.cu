@@ -36,9 +36,8 @@
 #define TC_LBO 2048u                   // byte stride between k-chunks
 #define TC_SBO 128u                    // byte stride between 8-row groups
 #define TC_TILE_BLOCKS 2               // target tile = 2 blocks = 256 rows
-#define TC_STAGES 2
+#define TC_STAGES 4                    // shared-memory stages of ONE target block (128 rows) each
 #define TC_THREADS 256
-#define TC_FILTER_FROM 4096            // columns after which the epilogue pre-filters against the running second best
 
 // ------------------------------------------------------------------ prep
 
@@ -205,8 +204,8 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
   const int task_end = n_tasks_dev ? *n_tasks_dev : n_tasks_host;
   if ((int)blockIdx.x >= task_end) return;   // uniform per CTA, before any barrier / TMEM use
   unsigned char* sA = tc_smem;                                        // 2 query blocks
-  unsigned char* sB = tc_smem + 2 * TC_BLOCK_BYTES;                   // TC_STAGES x 2 blocks
-  TcBarriers* bars = (TcBarriers*)(sB + (size_t)TC_STAGES * TC_TILE_BLOCKS * TC_BLOCK_BYTES);
+  unsigned char* sB = tc_smem + 2 * TC_BLOCK_BYTES;                   // TC_STAGES blocks
+  TcBarriers* bars = (TcBarriers*)(sB + (size_t)TC_STAGES * TC_BLOCK_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
@@ -238,12 +237,12 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
         mbar_expect_tx(smem_u32(&bars->a_full[as]), TC_BLOCK_BYTES);
         bulk_g2s(smem_u32(sA + (size_t)as * TC_BLOCK_BYTES), qbuf + (size_t)tk.q_blk * TC_BLOCK_BYTES, TC_BLOCK_BYTES,
                  smem_u32(&bars->a_full[as]));
-        for (int t = 0; t < ntile; ++t, ++gt) {
+        // one 128-row target block per stage: four loads in flight instead of two twice as large
+        for (int hb = 0; hb < ntile * TC_TILE_BLOCKS; ++hb, ++gt) {
           const uint32_t s = gt % TC_STAGES, ph = (gt / TC_STAGES) & 1u;
           mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
-          const uint32_t bytes = TC_TILE_BLOCKS * TC_BLOCK_BYTES;
-          mbar_expect_tx(smem_u32(&bars->full[s]), bytes);
-          bulk_g2s(smem_u32(sB + (size_t)s * bytes), tbuf + (size_t)(tk.t_blk0 + t * TC_TILE_BLOCKS) * TC_BLOCK_BYTES, bytes,
+          mbar_expect_tx(smem_u32(&bars->full[s]), TC_BLOCK_BYTES);
+          bulk_g2s(smem_u32(sB + (size_t)s * TC_BLOCK_BYTES), tbuf + (size_t)(tk.t_blk0 + hb) * TC_BLOCK_BYTES, TC_BLOCK_BYTES,
                    smem_u32(&bars->full[s]));
         }
       }
@@ -261,22 +260,24 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
         mbar_wait(smem_u32(&bars->a_full[asl]), (ti >> 1) & 1u);
         const uint32_t a0 = smem_u32(sA + (size_t)asl * TC_BLOCK_BYTES);
         for (int t = 0; t < ntile; ++t, ++gt) {
-          const uint32_t s = gt % TC_STAGES, as = gt & 1u;
-          mbar_wait(smem_u32(&bars->full[s]), (gt / TC_STAGES) & 1u);
+          const uint32_t as = gt & 1u;
           mbar_wait(smem_u32(&bars->acc_empty[as]), ((gt >> 1) & 1u) ^ 1u);
-          tc_fence_after();
-          const uint32_t b0 = smem_u32(sB + (size_t)s * TC_TILE_BLOCKS * TC_BLOCK_BYTES);
 #pragma unroll
           for (int half = 0; half < TC_TILE_BLOCKS; ++half) {
+            const uint32_t gh = gt * TC_TILE_BLOCKS + half;          // running half-tile (stage) counter
+            const uint32_t s = gh % TC_STAGES;
+            mbar_wait(smem_u32(&bars->full[s]), (gh / TC_STAGES) & 1u);
+            tc_fence_after();
+            const uint32_t b0 = smem_u32(sB + (size_t)s * TC_BLOCK_BYTES);
             const uint32_t d = tmem + (uint32_t)(as * 256 + half * 128);
 #pragma unroll
             for (int k = 0; k < TC_KC / 2; ++k) {
               const uint64_t ad = make_smem_desc(a0 + k * 2 * TC_LBO);
-              const uint64_t bd = make_smem_desc(b0 + half * TC_BLOCK_BYTES + k * 2 * TC_LBO);
+              const uint64_t bd = make_smem_desc(b0 + k * 2 * TC_LBO);
               umma_f16(d, ad, bd, idesc, k > 0 ? 1u : 0u);
             }
+            umma_commit(smem_u32(&bars->empty[s]));    // this block's smem slot is reusable once its MMAs retire
           }
-          umma_commit(smem_u32(&bars->empty[s]));      // smem slot reusable once these MMAs retire
           umma_commit(smem_u32(&bars->acc_full[as]));  // accumulators ready for the epilogue
         }
         umma_commit(smem_u32(&bars->a_empty[asl]));    // every MMA that reads this query block has retired
@@ -320,22 +321,6 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
               }
             }
           } else {
-            // The packed-key update below is four ALU-pipe instructions per element, and the ALU pipe
-            // issues one warp instruction per two cycles: 256 cycles per 32 columns, more than the MMA
-            // takes (ncu: tensor pipe 38 %, every epilogue stall "selected" or "wait").  Once a few
-            // thousand columns have been seen, almost no score is below the row's running second best
-            // any more: then one FADD (FMA pipe) and one funnel shift (ALU pipe) per element — the
-            // two pipes issue in parallel — collect the sign bits of (score - second best), and the
-            // update runs only for the rare 32-column chunk in which some row of the warp has a hit.
-            // Scores are positive finite floats, g2 has its low byte clear, so (v < g2) as floats is
-            // exactly (v & ~0xff) < g2 as the packed keys compare.
-            if (t * 256 >= TC_FILTER_FROM) {
-              const float lim = __int_as_float(g2);
-              unsigned hit = 0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) hit = __funnelshift_l(__float_as_uint(__uint_as_float(v[j]) - lim), hit, 1);
-              if (hit == 0) continue;
-            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int key = (int)((v[j] & 0xffffff00u) | (uint32_t)(c0 + j));
@@ -379,7 +364,7 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
 size_t tc_block_bytes() { return TC_BLOCK_BYTES; }
 
 size_t tc_smem_bytes() {
-  return (size_t)TC_BLOCK_BYTES * (2 + TC_STAGES * TC_TILE_BLOCKS) + sizeof(TcBarriers) + 1024;
+  return (size_t)TC_BLOCK_BYTES * (2 + TC_STAGES) + sizeof(TcBarriers) + 1024;
 }
 
 int tc_prepare(pano_ctx* ctx, const float* d_desc, const std::vector<TcImage>& imgs, TcOperands* ops) {
