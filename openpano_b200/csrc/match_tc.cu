@@ -22,9 +22,13 @@
 //   warp 1   MMA      : 2 x 9 tcgen05.mma (M128 N128 K16) per tile into one of two
 //                       256-column TMEM accumulator stages, tcgen05.commit -> mbarriers
 //   warp 2   TMEM alloc/dealloc (512 columns)
-//   warps 4-7 epilogue: tcgen05.ld 32 columns at a time; thread = query row keeps a
-//                       running (min, argmin, second-min) with the column packed into
-//                       the low mantissa bits (3 integer min/max + 1 LOP3 per element)
+//   warps 4-11 epilogue: two groups of four warps; group g owns the g-th 128-column half of
+//                       every accumulator stage (its own full/empty barriers), so each SM
+//                       sub-partition holds two epilogue warps and one computes while the
+//                       other waits for its tcgen05.ld.  32 columns at a time; thread = query
+//                       row keeps a running (min, argmin, second-min) with the column packed
+//                       into the low mantissa bits (3 integer min/max + 1 LOP3 per element);
+//                       the groups' results are merged through shared memory per task
 #include "sift.cuh"
 #include "match_tc.cuh"
 #include <cuda_fp16.h>
@@ -36,8 +40,9 @@
 #define TC_LBO 2048u                   // byte stride between k-chunks
 #define TC_SBO 128u                    // byte stride between 8-row groups
 #define TC_TILE_BLOCKS 2               // target tile = 2 blocks = 256 rows
-#define TC_STAGES 4                    // shared-memory stages of ONE target block (128 rows) each
-#define TC_THREADS 256
+#define TC_STAGES 2
+#define TC_THREADS 384
+#define TC_EPI_GROUPS 2
 
 // ------------------------------------------------------------------ prep
 
@@ -179,8 +184,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ------------------------------------------------------------------ the GEMM + top-2 kernel
 
 struct __align__(8) TcBarriers {
-  uint64_t full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2], a_full[2], a_empty[2];
+  uint64_t full[TC_STAGES], empty[TC_STAGES], acc_full[2][TC_EPI_GROUPS], acc_empty[2][TC_EPI_GROUPS], a_full[2], a_empty[2];
   uint32_t tmem_base;
+  int merge[2][128][3];   // group 1 -> group 0 hand-over of (best, second, argmin), by task parity
 };
 
 // FILTER = false: running top-2 per query row (the nomination pass).
@@ -204,8 +210,8 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
   const int task_end = n_tasks_dev ? *n_tasks_dev : n_tasks_host;
   if ((int)blockIdx.x >= task_end) return;   // uniform per CTA, before any barrier / TMEM use
   unsigned char* sA = tc_smem;                                        // 2 query blocks
-  unsigned char* sB = tc_smem + 2 * TC_BLOCK_BYTES;                   // TC_STAGES blocks
-  TcBarriers* bars = (TcBarriers*)(sB + (size_t)TC_STAGES * TC_BLOCK_BYTES);
+  unsigned char* sB = tc_smem + 2 * TC_BLOCK_BYTES;                   // TC_STAGES x 2 blocks
+  TcBarriers* bars = (TcBarriers*)(sB + (size_t)TC_STAGES * TC_TILE_BLOCKS * TC_BLOCK_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
@@ -214,7 +220,7 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&bars->acc_full[s]), 1); mbar_init(smem_u32(&bars->acc_empty[s]), 128);
+      for (int g = 0; g < TC_EPI_GROUPS; ++g) { mbar_init(smem_u32(&bars->acc_full[s][g]), 1); mbar_init(smem_u32(&bars->acc_empty[s][g]), 128); }
       mbar_init(smem_u32(&bars->a_full[s]), 1); mbar_init(smem_u32(&bars->a_empty[s]), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -237,12 +243,12 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
         mbar_expect_tx(smem_u32(&bars->a_full[as]), TC_BLOCK_BYTES);
         bulk_g2s(smem_u32(sA + (size_t)as * TC_BLOCK_BYTES), qbuf + (size_t)tk.q_blk * TC_BLOCK_BYTES, TC_BLOCK_BYTES,
                  smem_u32(&bars->a_full[as]));
-        // one 128-row target block per stage: four loads in flight instead of two twice as large
-        for (int hb = 0; hb < ntile * TC_TILE_BLOCKS; ++hb, ++gt) {
+        for (int t = 0; t < ntile; ++t, ++gt) {
           const uint32_t s = gt % TC_STAGES, ph = (gt / TC_STAGES) & 1u;
           mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
-          mbar_expect_tx(smem_u32(&bars->full[s]), TC_BLOCK_BYTES);
-          bulk_g2s(smem_u32(sB + (size_t)s * TC_BLOCK_BYTES), tbuf + (size_t)(tk.t_blk0 + hb) * TC_BLOCK_BYTES, TC_BLOCK_BYTES,
+          const uint32_t bytes = TC_TILE_BLOCKS * TC_BLOCK_BYTES;
+          mbar_expect_tx(smem_u32(&bars->full[s]), bytes);
+          bulk_g2s(smem_u32(sB + (size_t)s * bytes), tbuf + (size_t)(tk.t_blk0 + t * TC_TILE_BLOCKS) * TC_BLOCK_BYTES, bytes,
                    smem_u32(&bars->full[s]));
         }
       }
@@ -260,25 +266,23 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
         mbar_wait(smem_u32(&bars->a_full[asl]), (ti >> 1) & 1u);
         const uint32_t a0 = smem_u32(sA + (size_t)asl * TC_BLOCK_BYTES);
         for (int t = 0; t < ntile; ++t, ++gt) {
-          const uint32_t as = gt & 1u;
-          mbar_wait(smem_u32(&bars->acc_empty[as]), ((gt >> 1) & 1u) ^ 1u);
+          const uint32_t s = gt % TC_STAGES, as = gt & 1u;
+          mbar_wait(smem_u32(&bars->full[s]), (gt / TC_STAGES) & 1u);
+          const uint32_t b0 = smem_u32(sB + (size_t)s * TC_TILE_BLOCKS * TC_BLOCK_BYTES);
 #pragma unroll
           for (int half = 0; half < TC_TILE_BLOCKS; ++half) {
-            const uint32_t gh = gt * TC_TILE_BLOCKS + half;          // running half-tile (stage) counter
-            const uint32_t s = gh % TC_STAGES;
-            mbar_wait(smem_u32(&bars->full[s]), (gh / TC_STAGES) & 1u);
+            mbar_wait(smem_u32(&bars->acc_empty[as][half]), ((gt >> 1) & 1u) ^ 1u);
             tc_fence_after();
-            const uint32_t b0 = smem_u32(sB + (size_t)s * TC_BLOCK_BYTES);
             const uint32_t d = tmem + (uint32_t)(as * 256 + half * 128);
 #pragma unroll
             for (int k = 0; k < TC_KC / 2; ++k) {
               const uint64_t ad = make_smem_desc(a0 + k * 2 * TC_LBO);
-              const uint64_t bd = make_smem_desc(b0 + k * 2 * TC_LBO);
+              const uint64_t bd = make_smem_desc(b0 + half * TC_BLOCK_BYTES + k * 2 * TC_LBO);
               umma_f16(d, ad, bd, idesc, k > 0 ? 1u : 0u);
             }
-            umma_commit(smem_u32(&bars->empty[s]));    // this block's smem slot is reusable once its MMAs retire
+            umma_commit(smem_u32(&bars->acc_full[as][half]));  // this half is ready for its epilogue group
           }
-          umma_commit(smem_u32(&bars->acc_full[as]));  // accumulators ready for the epilogue
+          umma_commit(smem_u32(&bars->empty[s]));      // smem slot reusable once these MMAs retire
         }
         umma_commit(smem_u32(&bars->a_empty[asl]));    // every MMA that reads this query block has retired
       }
@@ -286,22 +290,25 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
   } else if (warp >= 4) {
     // ===== epilogue: thread <-> query row (TMEM lane)
     const int row = (warp & 3) * 32 + lane;
-    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t gt = 0;
-    for (int task = blockIdx.x; task < task_end; task += gridDim.x) {
+    const int grp = (warp - 4) >> 2;           // which 128-column half of every tile
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(grp * 128);
+    uint32_t gt = 0, ti = 0;
+    for (int task = blockIdx.x; task < task_end; task += gridDim.x, ++ti) {
       const TcTask tk = tasks[task];
       const int ntile = tk.t_blocks / TC_TILE_BLOCKS;
       int g1 = 0x7f7fff00, g2 = 0x7f7fff00;   // running best / second (value bits, low 8 cleared)
       int gi = 0x7fffffff;
       const int grow = tk.q_row0 + row;        // FILTER: index of this gathered row
+      uint32_t keymask;
+      asm volatile("mov.b32 %0, 0xffffff00;" : "=r"(keymask));
       const int thr = FILTER ? g_thr[grow] : 0;
       for (int t = 0; t < ntile; ++t, ++gt) {
         const uint32_t as = gt & 1u;
-        mbar_wait(smem_u32(&bars->acc_full[as]), (gt >> 1) & 1u);
+        mbar_wait(smem_u32(&bars->acc_full[as][grp]), (gt >> 1) & 1u);
         tc_fence_after();
         int k1 = 0x7fffffff, k2 = 0x7fffffff;
 #pragma unroll
-        for (int c0 = 0; c0 < 256; c0 += 32) {
+        for (int c0 = 0; c0 < 128; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(lane_addr + (uint32_t)(as * 256 + c0), v);
           tmem_ld_wait();
@@ -314,7 +321,7 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
             while (hit) {
               const int j = __ffs(hit) - 1;
               hit &= hit - 1;
-              const int col = t * 256 + c0 + j;
+              const int col = t * 256 + grp * 128 + c0 + j;
               if (col < tk.t_n) {
                 const int slot = atomicAdd(&cand_cnt[grow], 1);
                 if (slot < TC_CAND_CAP) cand[(size_t)grow * TC_CAND_CAP + slot] = col;
@@ -323,20 +330,38 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const int key = (int)((v[j] & 0xffffff00u) | (uint32_t)(c0 + j));
+              // (v & mask) | column in ONE LOP3: the mask has to sit in a register, because the
+              // instruction takes a single immediate (the compiler's and-imm / or-imm pair costs two
+              // ALU slots per element of a loop that is ALU-issue bound)
+              uint32_t ukey;
+              asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(ukey) : "r"(v[j]), "r"(keymask), "r"((uint32_t)(c0 + j)));
+              const int key = (int)ukey;
               k2 = min(k2, max(k1, key));
               k1 = min(k1, key);
             }
           }
         }
         tc_fence_before();
-        mbar_arrive(smem_u32(&bars->acc_empty[as]));
+        mbar_arrive(smem_u32(&bars->acc_empty[as][grp]));
         if (!FILTER) {
           // merge the tile's top-2 into the running top-2
           const int v1 = k1 & (int)0xffffff00, v2 = k2 & (int)0xffffff00;
-          if (v1 < g1) { g2 = min(g1, v2); g1 = v1; gi = t * 256 + (k1 & 0xff); }
+          if (v1 < g1) { g2 = min(g1, v2); g1 = v1; gi = t * 256 + grp * 128 + (k1 & 0xff); }
           else g2 = min(g2, v1);
         }
+      }
+      if (!FILTER) {
+        // the two column halves meet here: group 1 hands its running top-2 to group 0.  One named
+        // barrier per task is enough with two slots: group 1 cannot reach task ti+2 before group 0
+        // has arrived at the barrier of task ti+1, i.e. after it read slot ti.
+        int* mg = bars->merge[ti & 1u][row];
+        if (grp == 1) { mg[0] = g1; mg[1] = g2; mg[2] = gi; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (grp == 1) continue;
+        const int o1 = mg[0], o2 = mg[1], oi = mg[2];
+        // equal scores keep the lower column, as the single-chain scan did
+        if (o1 < g1 || (o1 == g1 && oi < gi)) { g2 = min(g1, o2); g1 = o1; gi = oi; }
+        else g2 = min(g2, o1);
       }
       const int qrow = tk.q_row0 + row;
       if (!FILTER && qrow < tk.q_n) {
@@ -364,7 +389,7 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
 size_t tc_block_bytes() { return TC_BLOCK_BYTES; }
 
 size_t tc_smem_bytes() {
-  return (size_t)TC_BLOCK_BYTES * (2 + TC_STAGES) + sizeof(TcBarriers) + 1024;
+  return (size_t)TC_BLOCK_BYTES * (2 + TC_STAGES * TC_TILE_BLOCKS) + sizeof(TcBarriers) + 1024;
 }
 
 int tc_prepare(pano_ctx* ctx, const float* d_desc, const std::vector<TcImage>& imgs, TcOperands* ops) {
