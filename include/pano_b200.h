@@ -111,6 +111,11 @@ long long pano_launch_count(const pano_ctx* ctx);
 /* Diagnostics: how many descriptor rows the last pano_match_pairs_dev call had to
  * re-scan exactly because the tensor-core nomination was not certain. */
 int pano_match_last_exact_rows(const pano_ctx* ctx);
+/* Diagnostics: rows of the LARGER sets that the last pano_match_pairs_dev call nominated on request
+ * ("columns on demand": on large runs only the smaller set of each pair goes through the first tensor
+ * pass; matcher.cc:57-61 walks column j only for rows that passed their own ratio test).  0 when
+ * both sets went through the first pass. */
+int pano_match_last_nominated_rows(const pano_ctx* ctx);
 
 /* ---------------------------------------------------------------- features
  * Replaces FeatureDetector::detect_feature / SIFTDetector::do_detect_feature

@@ -52,6 +52,7 @@ def _load():
         "pano_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, _ip, _dp]),
         "pano_launch_count": (C.c_longlong, [C.c_void_p]),
         "pano_match_last_exact_rows": (C.c_int, [C.c_void_p]),
+        "pano_match_last_nominated_rows": (C.c_int, [C.c_void_p]),
         "pano_sift_detect_batch": (C.c_int, [C.c_void_p, C.c_int, _vpp, _ip, _ip, P, _vpp]),
         "pano_sift_detect_batch_dev": (C.c_int, [C.c_void_p, C.c_int, _vpp, _ip, _ip, P, _vpp]),
         "pano_sift_detect": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, P, _vpp]),
@@ -275,6 +276,9 @@ class Engine:
 
     def match_last_exact_rows(self):
         return LIB.pano_match_last_exact_rows(self._h)
+
+    def match_last_nominated_rows(self):
+        return LIB.pano_match_last_nominated_rows(self._h)
 
     def profile(self, on: bool):
         self._check(LIB.pano_profile_enable(self._h, 1 if on else 0))

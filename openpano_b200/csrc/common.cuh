@@ -37,6 +37,7 @@ struct pano_ctx {
   std::map<std::string, std::pair<int, double>> prof_acc;  // name -> (launches, ms)
   long long launches = 0;
   int last_match_exact_rows = 0;   // rows the last match call had to decide exactly (gathered pass)
+  int last_match_nominated_rows = 0;   // columns on demand: rows of the larger sets nominated on request
   int last_match_full_rescans = 0; // of those, rows that needed a scan of every target
   int num_sms = 148;
   // cudaFuncSetAttribute is per device: remembered per context, never per process

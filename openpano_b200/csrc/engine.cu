@@ -486,6 +486,8 @@ long long pano_launch_count(const pano_ctx* ctx) {
   ctx_enter(ctx); return ctx->launches; }
 int pano_match_last_exact_rows(const pano_ctx* ctx) {
   ctx_enter(ctx); return ctx->last_match_exact_rows; }
+int pano_match_last_nominated_rows(const pano_ctx* ctx) {
+  ctx_enter(ctx); return ctx->last_match_nominated_rows; }
 
 // ---------------------------------------------------------------- device utilities
 int pano_dev_alloc(pano_ctx* ctx, size_t bytes, void** d_ptr) {

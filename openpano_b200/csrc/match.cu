@@ -19,6 +19,12 @@
 //    certain within those intervals are re-scanned exactly (k_exact_rows).  The
 //    outcome is the reference's, bit for bit; the tensor cores only decide how
 //    little exact work is left.
+//    COLUMNS ON DEMAND (large runs): the reference only walks column j (matcher.cc:57-61)
+//    for rows that passed their own ratio test, so the second reduction is needed for
+//    few rows of the larger set.  With enough work to fill the GPU anyway, only the
+//    smaller set's rows go through the first tensor pass; the rows of the larger set
+//    start UNKNOWN and the decide rounds request exactly the columns they need, which a
+//    gathered top-2 tensor pass then nominates (PANO_MATCH_LAZY=0/1 forces either way).
 //  * exact path (PANO_MATCH_PATH=exact): both reductions in fp32 on the CUDA
 //    cores (k_match_top2), kept as the in-engine cross-check.
 #include "sift.cuh"
@@ -61,7 +67,8 @@ struct MatchTask {       // one top-2 reduction: rows [q_row0, q_row0+MT) of Q a
 
 // Per-row knowledge, as certified intervals.  state bit 1: argmin certain (then
 // mn == mn_hi is the exact fp32 distance to idx); bit 0: second-best exact
-// (sec_lo == sec_hi).  With an uncertain argmin only the bounds are valid.
+// (sec_lo == sec_hi).  With an uncertain argmin only the bounds are valid.  Bit 2: nothing is
+// known yet (columns on demand: the row has not been through a tensor pass).
 struct RowInfo { float mn, mn_hi; int idx; float sec_lo, sec_hi; int state; int requested; int pad; };
 
 __global__ void __launch_bounds__(MT_THREADS)
@@ -169,16 +176,8 @@ __device__ __forceinline__ float tc_eps(float nq, float nmax) {
   return 0.00215f * sqrtf(nq * nmax) + 0.0005f * nmax + 1.0f;
 }
 
-__global__ void k_refine(const float* __restrict__ desc, const float* __restrict__ norms,
-                         const unsigned* __restrict__ maxnorm_bits, const SideMeta* __restrict__ sides,
-                         const TcTop2* __restrict__ approx, float ratio_sqr, RowInfo* __restrict__ info) {
-  const int side = blockIdx.y;
-  const SideMeta sm = sides[side];
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= sm.q_n) return;
-  const TcTop2 ap = approx[sm.res_off + r];
-  const float nmax = __uint_as_float(*maxnorm_bits);
-  const float eps = tc_eps(norms[sm.q_base + r], nmax);
+__device__ __forceinline__ RowInfo refine_row(const float* __restrict__ desc, const SideMeta& sm, int r, const TcTop2 ap,
+                                              float eps, float ratio_sqr) {
   RowInfo o;
   o.requested = 0; o.pad = 0;
   const bool idx_ok = ap.idx >= 0 && ap.idx < sm.t_n;
@@ -209,7 +208,44 @@ __global__ void k_refine(const float* __restrict__ desc, const float* __restrict
     o.sec_lo = fmaxf(ap.m2 - eps, 0.f); o.sec_hi = ap.m2 + eps;
     o.state = 0;
   }
-  info[sm.res_off + r] = o;
+  return o;
+}
+
+// lazy != 0: the sides of the larger sets (odd side indices) have not been through the tensor
+// pass; their rows start unknown and are nominated on request (k_refine_gathered).
+__global__ void k_refine(const float* __restrict__ desc, const float* __restrict__ norms,
+                         const unsigned* __restrict__ maxnorm_bits, const SideMeta* __restrict__ sides,
+                         const TcTop2* __restrict__ approx, float ratio_sqr, int lazy, RowInfo* __restrict__ info) {
+  const int side = blockIdx.y;
+  const SideMeta sm = sides[side];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= sm.q_n) return;
+  if (lazy && (side & 1) && sm.t_n > 0) {
+    RowInfo o; o.mn = 0.f; o.mn_hi = FLT_MAX; o.idx = 0; o.sec_lo = 0.f; o.sec_hi = FLT_MAX; o.state = 4; o.requested = 0; o.pad = 0;
+    info[sm.res_off + r] = o;
+    return;
+  }
+  const float nmax = __uint_as_float(*maxnorm_bits);
+  info[sm.res_off + r] = refine_row(desc, sm, r, approx[sm.res_off + r], tc_eps(norms[sm.q_base + r], nmax), ratio_sqr);
+}
+
+// The same certification for rows nominated on request: gathered row g carries (side, row) in
+// g_meta and its nomination in g_approx[g]; the nomination is also stored at the row's own slot,
+// where a later filter pass looks for its threshold.
+__global__ void k_refine_gathered(const float* __restrict__ desc, const float* __restrict__ norms,
+                                  const unsigned* __restrict__ maxnorm_bits, const SideMeta* __restrict__ sides,
+                                  const int2* __restrict__ g_meta, const TcTop2* __restrict__ g_approx,
+                                  const int* __restrict__ n_blocks, float ratio_sqr, TcTop2* __restrict__ approx,
+                                  RowInfo* __restrict__ info) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= *n_blocks * 128) return;
+  const int2 me = g_meta[g];
+  if (me.x < 0) return;
+  const SideMeta sm = sides[me.x];
+  const TcTop2 ap = g_approx[g];
+  const float nmax = __uint_as_float(*maxnorm_bits);
+  approx[sm.res_off + me.y] = ap;
+  info[sm.res_off + me.y] = refine_row(desc, sm, me.y, ap, tc_eps(norms[sm.q_base + me.y], nmax), ratio_sqr);
 }
 
 // Exact re-scan of listed rows: one 256-thread block per row, every thread strides
@@ -279,16 +315,24 @@ struct PairMeta {
 // intervals; rows that cannot be decided request exact re-scans and stay pending.
 // Requests go to per-side lists (list_rows[side.res_off + slot], side_cnt[side]) so
 // that the gathered second tensor pass can batch the rows of one side together.
+// Unknown rows (columns on demand) go to the second list of the side: they need a nomination
+// first, not a filter pass.  side_cnt holds [list][side] for this round.
 __device__ __forceinline__ void request_row(const SideMeta* __restrict__ sides, RowInfo* __restrict__ info, int side,
-                                            int row, int* __restrict__ list_rows, int* __restrict__ side_cnt) {
+                                            int row, int* list_rows, int* list_unknown,
+                                            int* __restrict__ side_cnt, int n_sides) {
   const long long off = sides[side].res_off;
-  if (atomicExch(&info[off + row].requested, 1) == 0) list_rows[off + atomicAdd(&side_cnt[side], 1)] = row;
+  RowInfo* ri = &info[off + row];
+  if (atomicExch(&ri->requested, 1) == 0) {
+    if (ri->state & 4) list_unknown[off + atomicAdd(&side_cnt[n_sides + side], 1)] = row;
+    else list_rows[off + atomicAdd(&side_cnt[side], 1)] = row;
+  }
 }
 
 __global__ void k_match_decide(const PairMeta* __restrict__ pairs, const SideMeta* __restrict__ sides,
                                RowInfo* __restrict__ info, float ratio_sqr, int first_round,
                                int* __restrict__ out, int* __restrict__ total,
-                               int* __restrict__ list_rows, int* __restrict__ side_cnt) {
+                               int* list_rows, int* list_unknown, int* __restrict__ side_cnt,
+                               int n_sides) {
   const PairMeta pm = pairs[blockIdx.y];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= pm.n_small) return;
@@ -303,27 +347,41 @@ __global__ void k_match_decide(const PairMeta* __restrict__ pairs, const SideMet
       if (r.mn > ratio_sqr * r.sec_hi) result = -1;
       else {
         result = OUT_PENDING;
-        request_row(sides, info, pm.side_small, k, list_rows, side_cnt);
+        request_row(sides, info, pm.side_small, k, list_rows, list_unknown, side_cnt, n_sides);
+        // columns on demand: the nominated column is most likely the one this row will need
+        if (info[sl.res_off + r.idx].state & 4)
+          request_row(sides, info, pm.side_large, r.idx, list_rows, list_unknown, side_cnt, n_sides);
       }
     } else {
       const RowInfo c = info[sl.res_off + r.idx];
-      float c_lo, c_hi;
-      bool need_c = false;
-      if (c.state & 2) {                                  // column's argmin certain
-        const bool mine = c.idx == k;
-        c_lo = mine ? c.sec_lo : c.mn; c_hi = mine ? c.sec_hi : c.mn_hi;
-        need_c = mine && !(c.state & 1);
-      } else {                                            // min_{kk != k} d(j, kk) lies between its best and second bounds
-        c_lo = c.mn; c_hi = c.sec_hi;
-        need_c = true;
-      }
-      const float nlo = fminf(r.sec_lo, c_lo), nhi = fminf(r.sec_hi, c_hi);
-      if (r.mn > ratio_sqr * nhi) result = -1;               // rejected for every admissible next_min
-      else if (!(r.mn > ratio_sqr * nlo)) result = r.idx;    // accepted for every admissible next_min
-      else {
-        result = OUT_PENDING;
-        if (!(r.state & 1)) request_row(sides, info, pm.side_small, k, list_rows, side_cnt);
-        if (need_c) request_row(sides, info, pm.side_large, r.idx, list_rows, side_cnt);
+      if (c.state & 4) {
+        // nothing is known about column r.idx yet: only the row's own test can reject, and only
+        // min == 0 accepts whatever the column holds (0 > R * next_min is false for every next_min)
+        if (r.mn > ratio_sqr * r.sec_hi) result = -1;
+        else if (!(r.mn > 0.f)) result = r.idx;
+        else {
+          result = OUT_PENDING;
+          request_row(sides, info, pm.side_large, r.idx, list_rows, list_unknown, side_cnt, n_sides);
+        }
+      } else {
+        float c_lo, c_hi;
+        bool need_c = false;
+        if (c.state & 2) {                                  // column's argmin certain
+          const bool mine = c.idx == k;
+          c_lo = mine ? c.sec_lo : c.mn; c_hi = mine ? c.sec_hi : c.mn_hi;
+          need_c = mine && !(c.state & 1);
+        } else {                                            // min_{kk != k} d(j, kk) lies between its best and second bounds
+          c_lo = c.mn; c_hi = c.sec_hi;
+          need_c = true;
+        }
+        const float nlo = fminf(r.sec_lo, c_lo), nhi = fminf(r.sec_hi, c_hi);
+        if (r.mn > ratio_sqr * nhi) result = -1;               // rejected for every admissible next_min
+        else if (!(r.mn > ratio_sqr * nlo)) result = r.idx;    // accepted for every admissible next_min
+        else {
+          result = OUT_PENDING;
+          if (!(r.state & 1)) request_row(sides, info, pm.side_small, k, list_rows, list_unknown, side_cnt, n_sides);
+          if (need_c) request_row(sides, info, pm.side_large, r.idx, list_rows, list_unknown, side_cnt, n_sides);
+        }
       }
     }
   }
@@ -500,7 +558,18 @@ struct MatchPlan {
   std::vector<char> rev;                // pair was swapped (first image is the larger set)
   long long res_total = 0, out_total = 0;
   int max_side_n = 0, max_small = 0;
+  bool lazy = false;                    // columns on demand: no first-pass tasks for the larger sets
+  long long large_blocks = 0;           // 128-row blocks of all larger sets
+  long long block_pairs = 0;            // sum over pairs of (blocks of the larger set) x (blocks of the smaller set)
 };
+
+// counters (ints): [0] matches, then per gather round r < 4: fallback rows, filter blocks, nomination
+// blocks; from MC_HEAD on, per decide round and list: requests per side ([round][list][side]).
+#define MC_FB(r) (1 + (r))
+#define MC_BLK_FILTER(r) (5 + (r))
+#define MC_BLK_NOMINATE(r) (9 + (r))
+#define MC_HEAD 16
+#define MC_ROUNDS 4
 
 static bool use_exact_path() {
   const char* e = getenv("PANO_MATCH_PATH");
@@ -513,6 +582,21 @@ static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int
     int i = ij[2 * k], j = ij[2 * k + 1];
     if (i < 0 || j < 0 || i >= fs->n_images || j >= fs->n_images)
       return ctx_fail(ctx, PANO_ERR_INVALID, "pair %d: image index out of range", k);
+    if (fs->h_count[i] > 0 && fs->h_count[j] > 0) {
+      const long long bl = (std::max(fs->h_count[i], fs->h_count[j]) + 127) / 128, bs = (std::min(fs->h_count[i], fs->h_count[j]) + 127) / 128;
+      pl.large_blocks += bl;
+      pl.block_pairs += bl * bs;
+    }
+  }
+  if (tcimgs) {
+    // Columns on demand halve the first pass but pay a nomination launch chain in each of three
+    // rounds (~20 us a round even when empty): measured, they win from 50 k x 50 k rows in one pair
+    // (153 k block pairs, 1.81 -> 1.60 ms) and lose on 13 pairs of ~2.9 k rows (6.9 k block pairs).
+    pl.lazy = pl.block_pairs >= 32768;
+    if (const char* e = getenv("PANO_MATCH_LAZY")) pl.lazy = atoi(e) != 0;
+  }
+  for (int k = 0; k < n_pairs; ++k) {
+    int i = ij[2 * k], j = ij[2 * k + 1];
     // matcher.cc:21-29: loop over the smaller one; rev = l1 > l2
     const bool rev = fs->h_count[i] > fs->h_count[j];
     const int is = rev ? j : i, il = rev ? i : j;
@@ -531,7 +615,7 @@ static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int
       if (nl > 0)
         for (int r0 = 0; r0 < ns; r0 += 128)
           pl.tc_tasks.push_back(TcTask{ts.blk0 + r0 / 128, r0, ns, tl.blk0, tl.n_pad / 128, nl, 0, a.res_off});
-      if (ns > 0)
+      if (ns > 0 && !pl.lazy)
         for (int r0 = 0; r0 < nl; r0 += 128)
           pl.tc_tasks.push_back(TcTask{tl.blk0 + r0 / 128, r0, nl, ts.blk0, ts.n_pad / 128, ns, 0, b.res_off});
       pl.gsides.push_back(TcGatherSide{a.q_base, a.res_off, a.res_off, ts.blk0, tl.blk0, tl.n_pad / 128, nl});
@@ -555,6 +639,10 @@ struct MatchBuffers {
   // gathered second tensor pass
   TcGatherSide* gsides = nullptr; int* list_rows = nullptr; TcTask* gtasks = nullptr; unsigned char* gq = nullptr;
   int2* g_meta = nullptr; int* g_thr = nullptr; int* cand_cnt = nullptr; int* cand = nullptr;
+  // columns on demand: gathered nomination pass over requested rows that are still unknown
+  int* list_unknown = nullptr; TcTask* ntasks = nullptr; unsigned char* nq = nullptr; int2* n_meta = nullptr;
+  TcTop2* n_approx = nullptr;
+  int rounds = 2;              // gather rounds run (the decide after the last one must leave nothing pending)
 };
 
 static void free_buffers(pano_ctx* ctx, MatchBuffers& b, bool keep_out) {
@@ -562,6 +650,8 @@ static void free_buffers(pano_ctx* ctx, MatchBuffers& b, bool keep_out) {
   ctx_free(ctx, b.approx); ctx_free(ctx, b.list);
   ctx_free(ctx, b.gsides); ctx_free(ctx, b.list_rows); ctx_free(ctx, b.gtasks); ctx_free(ctx, b.gq);
   ctx_free(ctx, b.g_meta); ctx_free(ctx, b.g_thr); ctx_free(ctx, b.cand_cnt); ctx_free(ctx, b.cand);
+  ctx_free(ctx, b.list_unknown); ctx_free(ctx, b.ntasks); ctx_free(ctx, b.nq); ctx_free(ctx, b.n_meta);
+  ctx_free(ctx, b.n_approx);
   if (!keep_out) { ctx_free(ctx, b.out); ctx_free(ctx, b.counters); b.out = nullptr; b.counters = nullptr; }
 }
 
@@ -579,7 +669,7 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
       (rc = ctx_alloc(ctx, (void**)&b.out, std::max<long long>(pl.out_total, 1) * sizeof(int))))
     return rc;
   const int n_sides = (int)pl.sides.size();
-  b.n_counters = 8 + 3 * n_sides;
+  b.n_counters = MC_HEAD + MC_ROUNDS * 2 * n_sides;
   if ((rc = ctx_alloc(ctx, (void**)&b.counters, b.n_counters * sizeof(int)))) return rc;
   const void* tsrc = tensor ? (const void*)pl.tc_tasks.data() : (const void*)pl.exact_tasks.data();
   const size_t bg = tensor ? pl.gsides.size() * sizeof(TcGatherSide) : 0;
@@ -606,7 +696,7 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
     if (pl.max_small > 0) {
       if ((rc = ctx_alloc(ctx, (void**)&b.list_rows, nres * sizeof(int)))) return rc;
       PANO_LAUNCH(ctx, "k_match_decide", k_match_decide, gd, 256, 0, b.pairs, b.sides, b.info, rs, 1, b.out,
-                  b.counters, b.list_rows, b.counters + 8);
+                  b.counters, b.list_rows, b.list_rows, b.counters + MC_HEAD, n_sides);
     }
     return PANO_OK;
   }
@@ -615,7 +705,7 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
   if (pl.max_side_n > 0) {
     dim3 gr(ceil_div(pl.max_side_n, 128), (unsigned)pl.sides.size());
     PANO_LAUNCH(ctx, "k_refine", k_refine, gr, 128, 0, fs->d_desc, ops->d_norms, ops->d_maxnorm, b.sides, b.approx, rs,
-                b.info);
+                pl.lazy ? 1 : 0, b.info);
   }
   if (pl.max_small > 0) {
     // Up to three decide rounds.  A round decides every row it can from the current
@@ -639,14 +729,42 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
       return rc;
     f.gq = b.gq; f.tasks = b.gtasks; f.gsides = b.gsides; f.list_rows = b.list_rows; f.approx = b.approx;
     f.g_meta = b.g_meta; f.g_thr = b.g_thr; f.cand_cnt = b.cand_cnt; f.cand = b.cand;
+    // columns on demand: requested rows that are still unknown get their nomination first
+    TcFilter nf;
+    int nom_cap = 0;
+    if (pl.lazy) {
+      nom_cap = (int)std::min<long long>(std::max<long long>(pl.large_blocks, 1), 8192);
+      const size_t nrow = (size_t)nom_cap * 128;
+      if ((rc = ctx_alloc(ctx, (void**)&b.list_unknown, nres * sizeof(int))) ||
+          (rc = ctx_alloc(ctx, (void**)&b.ntasks, (size_t)nom_cap * sizeof(TcTask))) ||
+          (rc = ctx_alloc(ctx, (void**)&b.nq, (size_t)nom_cap * tc_block_bytes())) ||
+          (rc = ctx_alloc(ctx, (void**)&b.n_meta, nrow * sizeof(int2))) ||
+          (rc = ctx_alloc(ctx, (void**)&b.n_approx, nrow * sizeof(TcTop2))))
+        return rc;
+      nf.gq = b.nq; nf.tasks = b.ntasks; nf.gsides = b.gsides; nf.list_rows = b.list_unknown; nf.approx = nullptr;
+      nf.g_meta = b.n_meta; nf.g_thr = nullptr; nf.cand_cnt = nullptr; nf.cand = nullptr;
+    }
+    int* list_unknown = pl.lazy ? b.list_unknown : b.list_rows;   // never written when nothing is unknown
     const int eg = ctx->num_sms * 4;
-    for (int round = 0; round < 3; ++round) {
-      int* side_cnt = b.counters + 8 + round * n_sides;
-      int* fb_cnt = b.counters + 1 + round;
-      int* n_blocks = b.counters + 4 + round;
+    // A row may need: its own exact top-2 (filter), then the nomination of a column it only now
+    // knows, then that column's exact top-2 — one more round than when every column starts nominated.
+    b.rounds = pl.lazy ? 3 : 2;
+    for (int round = 0; round <= b.rounds; ++round) {
+      int* side_cnt = b.counters + MC_HEAD + round * 2 * n_sides;
+      int* fb_cnt = b.counters + MC_FB(round);
+      int* n_blocks = b.counters + MC_BLK_FILTER(round);
       PANO_LAUNCH(ctx, "k_match_decide", k_match_decide, gd, 256, 0, b.pairs, b.sides, b.info, rs, round == 0 ? 1 : 0,
-                  b.out, b.counters, b.list_rows, side_cnt);
-      if (round == 2) break;
+                  b.out, b.counters, b.list_rows, list_unknown, side_cnt, n_sides);
+      if (round == b.rounds) break;
+      if (pl.lazy) {
+        int* nom_blocks = b.counters + MC_BLK_NOMINATE(round);
+        PANO_LAUNCH(ctx, "k_gather_plan", k_gather_plan, ceil_div(n_sides, 128), 128, 0, b.gsides, n_sides,
+                    side_cnt + n_sides, b.list_unknown, nom_cap, b.ntasks, nom_blocks, b.list, fb_cnt);
+        nf.n_tasks = nom_blocks;
+        if ((rc = tc_run_nominate(ctx, ops, &nf, nom_cap, b.n_approx))) return rc;
+        PANO_LAUNCH(ctx, "k_refine_gathered", k_refine_gathered, nom_cap, 128, 0, fs->d_desc, ops->d_norms, ops->d_maxnorm,
+                    b.sides, b.n_meta, b.n_approx, nom_blocks, rs, b.approx, b.info);
+      }
       PANO_LAUNCH(ctx, "k_gather_plan", k_gather_plan, ceil_div(n_sides, 128), 128, 0, b.gsides, n_sides, side_cnt,
                   b.list_rows, block_cap, b.gtasks, n_blocks, b.list, fb_cnt);
       f.n_tasks = n_blocks;
@@ -752,19 +870,27 @@ int pano_match_pairs_dev(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const 
   MatchBuffers b;
   int rc = match_common(ctx, fs, n_pairs, ij, p, pl, b);
   if (rc) { free_buffers(ctx, b, false); return rc; }
-  int* h = (int*)ctx_ring(ctx, (size_t)std::max(b.n_counters, 8) * sizeof(int));
+  int* h = (int*)ctx_ring(ctx, (size_t)std::max(b.n_counters, MC_HEAD) * sizeof(int));
   if (!h) { free_buffers(ctx, b, false); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned ring allocation failed"); }
-  const int n_counters = b.n_counters, n_sides = (int)pl.sides.size();
+  const int n_counters = b.n_counters, n_sides = (int)pl.sides.size(), rounds = b.rounds;
   rc = b.counters ? ctx_store(ctx, h, b.counters, (size_t)n_counters * sizeof(int)) : 0;
   cudaError_t e = ctx_spin_stream(ctx);
   free_buffers(ctx, b, false);
   if (rc) return rc;
   if (e != cudaSuccess) return ctx_cuda(ctx, e, "match total download");
-  if (n_counters < 8) { *total_matches = 0; return PANO_OK; }
-  long long requested = 0, undecided = 0;
-  for (int sidx = 0; sidx < n_sides; ++sidx) { requested += h[8 + sidx] + h[8 + n_sides + sidx]; undecided += h[8 + 2 * n_sides + sidx]; }
+  if (n_counters < MC_HEAD) { *total_matches = 0; return PANO_OK; }
+  long long requested = 0, nominated = 0, undecided = 0, rescans = 0;
+  for (int round = 0; round <= rounds; ++round)
+    for (int q = 0; q < 2 * n_sides; ++q) {
+      const int v = h[MC_HEAD + round * 2 * n_sides + q];
+      if (round == rounds) undecided += v;
+      else if (q < n_sides) requested += v;      // rows that went through the exact (filter) pass
+      else nominated += v;                       // columns on demand: rows nominated on request
+    }
+  for (int round = 0; round < rounds; ++round) rescans += h[MC_FB(round)];
+  ctx->last_match_nominated_rows = (int)nominated;
   ctx->last_match_exact_rows = (int)requested;
-  ctx->last_match_full_rescans = h[1] + h[2];
+  ctx->last_match_full_rescans = (int)rescans;
   if (undecided != 0) return ctx_fail(ctx, PANO_ERR_CUDA, "match: %lld rows undecided after the exact passes", undecided);
   *total_matches = h[0];
   return PANO_OK;

@@ -363,8 +363,10 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
         if (o1 < g1 || (o1 == g1 && oi < gi)) { g2 = min(g1, o2); g1 = o1; gi = oi; }
         else g2 = min(g2, o1);
       }
+      // device-planned tasks (n_tasks_dev) are GATHERED blocks: q_row0 is the block's first gathered
+      // row, q_n its real rows, and the nomination goes to the gathered row's slot
       const int qrow = tk.q_row0 + row;
-      if (!FILTER && qrow < tk.q_n) {
+      if (!FILTER && (n_tasks_dev ? row < tk.q_n : qrow < tk.q_n)) {
         const float s = tc_scale_from_maxnorm(__uint_as_float(*maxnorm_bits));
         const float inv = 1.f / (s * s);
         TcTop2 o;
@@ -372,7 +374,7 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
         o.m2 = g2 == 0x7f7fff00 ? FLT_MAX : (__int_as_float(g2) - 1.f) * inv;
         o.idx = gi;
         o.pad = 0;
-        res[tk.res_off + qrow] = o;
+        res[(n_tasks_dev ? 0 : tk.res_off) + qrow] = o;
       }
     }
   }
@@ -419,15 +421,20 @@ void tc_release(pano_ctx* ctx, TcOperands* ops) {
   *ops = TcOperands();
 }
 
+// function attributes are per DEVICE: one process may hold contexts on several GPUs
+static int tc_set_attrs(pano_ctx* ctx) {
+  if (ctx->attr_tc) return PANO_OK;
+  const size_t smem = tc_smem_bytes();
+  PANO_CUDA(ctx, cudaFuncSetAttribute(k_tc_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PANO_CUDA(ctx, cudaFuncSetAttribute(k_tc_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ctx->attr_tc = true;
+  return PANO_OK;
+}
+
 int tc_run_top2(pano_ctx* ctx, const TcOperands* ops, const TcTask* d_tasks, int n_tasks, TcTop2* d_res) {
   if (n_tasks == 0) return PANO_OK;
   const size_t smem = tc_smem_bytes();
-  // function attributes are per DEVICE: one process may hold contexts on several GPUs
-  if (!ctx->attr_tc) {
-    PANO_CUDA(ctx, cudaFuncSetAttribute(k_tc_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PANO_CUDA(ctx, cudaFuncSetAttribute(k_tc_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctx->attr_tc = true;
-  }
+  if (int rc = tc_set_attrs(ctx)) return rc;
   PANO_LAUNCH(ctx, "k_tc_top2", k_tc_pass<false>, std::min(n_tasks, ctx->num_sms), TC_THREADS, smem, ops->qbuf, ops->tbuf, d_tasks,
               (const int*)nullptr, n_tasks, ops->d_maxnorm, d_res, (const int*)nullptr, (int*)nullptr, (int*)nullptr);
   return PANO_OK;
@@ -436,7 +443,8 @@ int tc_run_top2(pano_ctx* ctx, const TcOperands* ops, const TcTask* d_tasks, int
 // ------------------------------------------------------------------ gathered second pass
 
 // Copies the query-form fp16 rows of the listed rows into gather blocks and sets
-// each gathered row's threshold key / bookkeeping.  One CTA per gather block.
+// each gathered row's threshold key / bookkeeping (approx == nullptr: a nomination pass over
+// rows that have no first-pass result yet — no thresholds).  One CTA per gather block.
 __global__ void __launch_bounds__(128)
 k_tc_gather_rows(const unsigned char* __restrict__ qbuf, unsigned char* __restrict__ gq,
                  const TcTask* __restrict__ tasks, const int* __restrict__ n_tasks_dev,
@@ -455,31 +463,47 @@ k_tc_gather_rows(const unsigned char* __restrict__ qbuf, unsigned char* __restri
     const unsigned char* src = qbuf + (size_t)(gs.q_blk0 + row / 128) * TC_BLOCK_BYTES + ((row % 128) / 8) * TC_SBO + (row % 8) * 16;
 #pragma unroll
     for (int kc = 0; kc < TC_KC; ++kc) *(uint4*)(dst + (size_t)kc * TC_LBO) = *(const uint4*)(src + (size_t)kc * TC_LBO);
-    const float nmax = __uint_as_float(*maxnorm_bits);
-    const float s = tc_scale_from_maxnorm(nmax);
-    const float nq = norms[gs.q_base + row];
-    const float eps = 0.00215f * sqrtf(nq * nmax) + 0.0005f * nmax + 1.0f;    // == tc_eps in match.cu
-    const TcTop2 ap = approx[gs.res_off + row];
-    // every column whose exact distance can be the best or the second best scores <= m2~ + 2 eps
-    float thr_v = ap.m2 == FLT_MAX ? FLT_MAX : (ap.m2 + 2.5f * eps) * (s * s) + 1.f;
-    g_thr[g] = (int)(__float_as_uint(thr_v) | 0xffu);
+    if (approx) {
+      const float nmax = __uint_as_float(*maxnorm_bits);
+      const float s = tc_scale_from_maxnorm(nmax);
+      const float nq = norms[gs.q_base + row];
+      const float eps = 0.00215f * sqrtf(nq * nmax) + 0.0005f * nmax + 1.0f;    // == tc_eps in match.cu
+      const TcTop2 ap = approx[gs.res_off + row];
+      // every column whose exact distance can be the best or the second best scores <= m2~ + 2 eps
+      float thr_v = ap.m2 == FLT_MAX ? FLT_MAX : (ap.m2 + 2.5f * eps) * (s * s) + 1.f;
+      g_thr[g] = (int)(__float_as_uint(thr_v) | 0xffu);
+      cand_cnt[g] = 0;
+    }
     g_meta[g] = make_int2(side, row);
-    cand_cnt[g] = 0;
   } else {
 #pragma unroll
     for (int kc = 0; kc < TC_KC; ++kc) *(uint4*)(dst + (size_t)kc * TC_LBO) = make_uint4(0, 0, 0, 0);
-    g_thr[g] = -1;
+    if (approx) { g_thr[g] = -1; cand_cnt[g] = 0; }
     g_meta[g] = make_int2(-1, -1);
-    cand_cnt[g] = 0;
   }
 }
 
 int tc_run_filter(pano_ctx* ctx, const TcOperands* ops, const TcFilter* f, int max_blocks) {
   if (max_blocks <= 0) return PANO_OK;
   const size_t smem = tc_smem_bytes();
+  if (int rc = tc_set_attrs(ctx)) return rc;
   PANO_LAUNCH(ctx, "k_tc_gather_rows", k_tc_gather_rows, max_blocks, 128, 0, ops->qbuf, f->gq, f->tasks, f->n_tasks,
               f->gsides, f->list_rows, f->approx, ops->d_norms, ops->d_maxnorm, f->g_meta, f->g_thr, f->cand_cnt);
   PANO_LAUNCH(ctx, "k_tc_filter", k_tc_pass<true>, std::min(max_blocks, ctx->num_sms), TC_THREADS, smem, f->gq, ops->tbuf, f->tasks, f->n_tasks,
               0, ops->d_maxnorm, (TcTop2*)nullptr, f->g_thr, f->cand_cnt, f->cand);
+  return PANO_OK;
+}
+
+// Nomination (running top-2) over gathered rows: the columns-on-demand pass of match.cu.
+// d_res[g] receives gathered row g's result.
+int tc_run_nominate(pano_ctx* ctx, const TcOperands* ops, const TcFilter* f, int max_blocks, TcTop2* d_res) {
+  if (max_blocks <= 0) return PANO_OK;
+  const size_t smem = tc_smem_bytes();
+  if (int rc = tc_set_attrs(ctx)) return rc;
+  PANO_LAUNCH(ctx, "k_tc_gather_rows", k_tc_gather_rows, max_blocks, 128, 0, ops->qbuf, f->gq, f->tasks, f->n_tasks,
+              f->gsides, f->list_rows, (const TcTop2*)nullptr, ops->d_norms, ops->d_maxnorm, f->g_meta, (int*)nullptr,
+              (int*)nullptr);
+  PANO_LAUNCH(ctx, "k_tc_nominate", k_tc_pass<false>, std::min(max_blocks, ctx->num_sms), TC_THREADS, smem, f->gq, ops->tbuf, f->tasks,
+              f->n_tasks, 0, ops->d_maxnorm, d_res, (const int*)nullptr, (int*)nullptr, (int*)nullptr);
   return PANO_OK;
 }

@@ -57,4 +57,5 @@ int  tc_prepare(pano_ctx* ctx, const float* d_desc, const std::vector<TcImage>& 
 void tc_release(pano_ctx* ctx, TcOperands* ops);
 int  tc_run_top2(pano_ctx* ctx, const TcOperands* ops, const TcTask* d_tasks, int n_tasks, TcTop2* d_res);
 int  tc_run_filter(pano_ctx* ctx, const TcOperands* ops, const TcFilter* f, int max_blocks);
+int  tc_run_nominate(pano_ctx* ctx, const TcOperands* ops, const TcFilter* f, int max_blocks, TcTop2* d_res);
 size_t tc_block_bytes();

@@ -128,10 +128,15 @@ def sweep_sets(n, seed=4):
     return a, b
 
 
-@pytest.mark.parametrize("n", [10000, 50000])
-def test_config4_sweep_vs_oracle(engine, omt, n):
+@pytest.mark.parametrize("n,lazy", [(10000, None), (10000, "1"), (50000, None), (50000, "0")])
+def test_config4_sweep_vs_oracle(engine, omt, monkeypatch, n, lazy):
+    """lazy=None: the matcher's own choice (both sides through the first pass at 10 k, columns on
+    demand at 50 k); "1"/"0" force the other way at each size."""
     a, b = sweep_sets(n)
+    if lazy is not None:
+        monkeypatch.setenv("PANO_MATCH_LAZY", lazy)
     got = engine.match_bruteforce(a, b)
+    monkeypatch.delenv("PANO_MATCH_LAZY", raising=False)
     want = omt.match(a, b)
     assert np.array_equal(got, want), (len(got), len(want))
     assert 0.3 * n < len(got) < 0.7 * n
@@ -220,15 +225,18 @@ def test_blend_more_than_64_images_on_one_tile(engine, omt):
         assert np.array_equal(bits(a), bits(b)), (bands, lazy)
 
 
-def test_match_full_rescan_fallback(engine, orc, monkeypatch):
+@pytest.mark.parametrize("lazy", ["0", "1"])
+def test_match_full_rescan_fallback(engine, orc, monkeypatch, lazy):
     """PANO_MATCH_BLOCK_CAP=1 leaves one gather block for the second tensor pass: every other
     undecided side goes through k_exact_rows (the whole-row fp32 re-scan)."""
     rng = np.random.RandomState(78)
     a = synth.rootsift_like(1500, 8)
     b = a[rng.permutation(1500)][:1300] + rng.randn(1300, 128).astype(np.float32) * 30.0
     monkeypatch.setenv("PANO_MATCH_BLOCK_CAP", "1")
+    monkeypatch.setenv("PANO_MATCH_LAZY", lazy)
     got = engine.match_bruteforce(a, b)
     monkeypatch.delenv("PANO_MATCH_BLOCK_CAP", raising=False)
+    monkeypatch.delenv("PANO_MATCH_LAZY", raising=False)
     assert np.array_equal(got, orc.match(a, b))
 
 

@@ -8,7 +8,18 @@ from openpano_b200._abi import default_params
 pytestmark = pytest.mark.gpu
 
 
-def test_match_pairs_bit_exact(engine, orc):
+@pytest.fixture(params=["auto", "columns_on_demand", "both_sides_first"])
+def match_mode(request, monkeypatch):
+    """The matcher picks by size whether the larger sets' rows go through the first tensor pass or
+    are nominated on request (match.cu: PANO_MATCH_LAZY); both ways must give the reference's pairs."""
+    if request.param == "auto":
+        monkeypatch.delenv("PANO_MATCH_LAZY", raising=False)
+    else:
+        monkeypatch.setenv("PANO_MATCH_LAZY", "1" if request.param == "columns_on_demand" else "0")
+    return request.param
+
+
+def test_match_pairs_bit_exact(engine, orc, match_mode):
     imgs, _ = synth.make_stack(4, 480, 360, 160, 41)
     fs = engine.sift_detect_batch(imgs)
     descs = [fs.download(i)[1] for i in range(4)]
@@ -23,7 +34,7 @@ def test_match_pairs_bit_exact(engine, orc):
 
 
 @pytest.mark.parametrize("n,m,noise", [(700, 600, 6.0), (600, 700, 25.0), (257, 1000, 40.0), (64, 64, 60.0), (1, 5, 1.0), (5, 1, 1.0)])
-def test_match_bruteforce_near_threshold(engine, orc, n, m, noise):
+def test_match_bruteforce_near_threshold(engine, orc, n, m, noise, match_mode):
     rng = np.random.RandomState(n + m)
     a = synth.rootsift_like(max(n, m), 4)
     b = a[rng.permutation(len(a))][:m] + rng.randn(m, 128).astype(np.float32) * noise
@@ -33,14 +44,14 @@ def test_match_bruteforce_near_threshold(engine, orc, n, m, noise):
     assert np.array_equal(got, want), (len(got), len(want))
 
 
-def test_match_duplicates_and_ties(engine, orc):
+def test_match_duplicates_and_ties(engine, orc, match_mode):
     a = synth.rootsift_like(300, 5)
     b = np.concatenate([a[:100], a[:100], a[200:]])  # exact duplicates -> zero-distance ties
     assert np.array_equal(engine.match_bruteforce(a, b), orc.match(a, b))
     assert np.array_equal(engine.match_bruteforce(b, a), orc.match(b, a))
 
 
-def test_match_empty(engine):
+def test_match_empty(engine, match_mode):
     a = synth.rootsift_like(10, 6)
     assert len(engine.match_bruteforce(a, np.zeros((0, 128), np.float32))) == 0
 
@@ -126,7 +137,7 @@ def test_blend_full_size_properties(engine):
     assert np.abs(mb[cov2] - canvas[cov2]).mean() < 5e-3
 
 
-def test_match_tensor_path_equals_exact_path(engine, orc, monkeypatch):
+def test_match_tensor_path_equals_exact_path(engine, orc, monkeypatch, match_mode):
     """The tcgen05 nomination + certified exact decisions must give the same pairs
     as the all-fp32 CUDA-core path and as the oracle, including near-threshold
     ratios (heavy noise) where the fp16 scores cannot decide on their own."""

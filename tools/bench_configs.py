@@ -298,6 +298,7 @@ def run_stack(eng, label, cfg_name, pairs_fn, bands, params, steps=5, max_output
                    "h2d_bytes": nimg * h * w * 3, "d2h_bytes": 256 + ow * oh * 3 + int(n_matches) * 8,
                    "boundary": "rgb8 in, cropped rgb8 mosaic + match lists out, one job at a time", "crop_ok": crop_ok},
            "features": int(sum(counts)), "matches": int(n_matches), "match_rows_rescanned_exactly": eng.match_last_exact_rows(),
+           "match_rows_nominated_on_request": eng.match_last_nominated_rows(),
            "roofline": top_roofline(kernels, peak_src),
            "kernels": {k: v for k, v in list(kernels.items())[:8]},
            "parity_sample": parity, "cpu_baseline": cpu}
@@ -338,7 +339,8 @@ def run_sweep(eng, sizes, params, cpu_n=10000, reps=3):
         out["sizes"][str(n)] = {"ms": ms, "matches": int(tot), "tflops_algorithmic": tf, "frac_of_peak": tf / tf_peak,
                                 "k_tc_top2_ms": gemm_ms,
                                 "k_tc_top2_tflops_algorithmic": (2.0 * n * n * 128 / (gemm_ms * 1e-3) / 1e12) if gemm_ms else None,
-                                "rows_rescanned_exactly": eng.match_last_exact_rows()}
+                                "rows_rescanned_exactly": eng.match_last_exact_rows(),
+                                "rows_nominated_on_request": eng.match_last_nominated_rows()}
         del a, b
     try:
         from tests.checker import get_checker, have
