@@ -569,6 +569,12 @@ def main():
                 sharded = bc.run_sharded(eng, rank, world, _dp())
             except Exception as ex:
                 sharded = {"error": repr(ex)}
+            try:
+                sweep = bc.run_sharded_sweep(eng, rank, world, _dp())
+            except Exception as ex:
+                sweep = {"error": repr(ex)}
+            if rank == 0 and isinstance(sharded, dict):
+                sharded["match_sweep_100k_row_sharded"] = sweep
 
         st.close()
         eng.close()

@@ -204,6 +204,17 @@ void pano_matches_free(pano_matches* m);
  * device, only the total match count is returned. */
 int  pano_match_pairs_dev(pano_ctx* ctx, pano_featureset* fs, int n_pairs,
                           const int* image_ij, const pano_params* p, int* total_matches);
+/* Row-sharded forms (multi-GPU brute-force match, BASELINE config 4): the loop of
+ * FeatureMatcher::match over the smaller set (matcher.cc:32: `#pragma omp parallel for` over k)
+ * is split into n_shards contiguous shares; this call decides share `shard` of EVERY pair —
+ * rows [n_small*shard/n_shards, n_small*(shard+1)/n_shards).  Each share still scans all of the
+ * larger set and, for its surviving rows, all of the smaller set (matcher.cc:57-61), so every
+ * rank holds both descriptor sets and no collective is needed; the shards' lists, concatenated
+ * in shard order, are pano_match_pairs' lists.  (0, 1) is the unsharded call. */
+int  pano_match_pairs_shard(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int* image_ij,
+                            const pano_params* p, int shard, int n_shards, pano_matches* out);
+int  pano_match_pairs_dev_shard(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int* image_ij,
+                                const pano_params* p, int shard, int n_shards, int* total_matches);
 /* FeatureMatcher(f1,f2).match() on two host descriptor arrays
  * (matcher.hh:27-38); pairs_out holds 2*min(n,m) ints. */
 int  pano_match_bruteforce(pano_ctx* ctx, const float* desc_a, int n,

@@ -65,6 +65,8 @@ def _load():
         "pano_match_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _ip, P, C.POINTER(PanoMatches)]),
         "pano_matches_free": (None, [C.POINTER(PanoMatches)]),
         "pano_match_pairs_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _ip, P, _ip]),
+        "pano_match_pairs_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _ip, P, C.c_int, C.c_int, C.POINTER(PanoMatches)]),
+        "pano_match_pairs_dev_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _ip, P, C.c_int, C.c_int, _ip]),
         "pano_match_bruteforce": (C.c_int, [C.c_void_p, _fp, C.c_int, _fp, C.c_int, P, _ip, _ip]),
         "pano_comm_unique_id": (C.c_int, [C.c_char_p]),
         "pano_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char_p, _vpp]),
@@ -423,11 +425,14 @@ class Engine:
                                             C.c_void_p(d_out_rows), out_w, out_h, row0, row1))
 
     # -- matching
-    def match_pairs(self, fs: FeatureSet, pairs, params=None):
+    def match_pairs(self, fs: FeatureSet, pairs, params=None, shard=(0, 1)):
+        """shard=(s, S): decide only share s of S of every pair's smaller set (row-sharded multi-GPU
+        match); the shares' lists concatenated in shard order are the unsharded lists."""
         params = params or default_params()
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         m = PanoMatches()
-        self._check(LIB.pano_match_pairs(self._h, fs._h, len(pairs), _i(pairs), C.byref(params), C.byref(m)))
+        self._check(LIB.pano_match_pairs_shard(self._h, fs._h, len(pairs), _i(pairs), C.byref(params), int(shard[0]),
+                                               int(shard[1]), C.byref(m)))
         n = m.n_pairs
         offs = np.ctypeslib.as_array(m.offset, shape=(n + 1,)).copy() if n else np.zeros(1, np.int32)
         total = int(offs[n]) if n else 0
@@ -436,11 +441,12 @@ class Engine:
         LIB.pano_matches_free(C.byref(m))
         return [idx[offs[k]:offs[k + 1]] for k in range(n)]
 
-    def match_pairs_dev(self, fs: FeatureSet, pairs, params=None) -> int:
+    def match_pairs_dev(self, fs: FeatureSet, pairs, params=None, shard=(0, 1)) -> int:
         params = params or default_params()
         pairs = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
         tot = C.c_int()
-        self._check(LIB.pano_match_pairs_dev(self._h, fs._h, len(pairs), _i(pairs), C.byref(params), C.byref(tot)))
+        self._check(LIB.pano_match_pairs_dev_shard(self._h, fs._h, len(pairs), _i(pairs), C.byref(params), int(shard[0]),
+                                                   int(shard[1]), C.byref(tot)))
         return tot.value
 
     def match_bruteforce(self, a, b, params=None):

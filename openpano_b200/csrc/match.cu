@@ -166,6 +166,8 @@ struct SideMeta {        // one query set of one pair
   long long q_base, t_base;   // descriptor rows in the featureset
   int q_n, t_n;
   long long res_off;          // RowInfo / TcTop2 offset of this side
+  int r0, r1;                 // rows of this side that went through the first pass (a row-sharded call
+                              // nominates only its own rows of the smaller set; otherwise 0 .. q_n)
 };
 
 // Bound on |approx d^2 - exact fp32 d^2| for a query of squared norm nq against
@@ -220,6 +222,7 @@ __global__ void k_refine(const float* __restrict__ desc, const float* __restrict
   const SideMeta sm = sides[side];
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= sm.q_n) return;
+  if (r < sm.r0 || r >= sm.r1) return;      // another shard's row: never decided, never a column here
   if (lazy && (side & 1) && sm.t_n > 0) {
     RowInfo o; o.mn = 0.f; o.mn_hi = FLT_MAX; o.idx = 0; o.sec_lo = 0.f; o.sec_hi = FLT_MAX; o.state = 4; o.requested = 0; o.pad = 0;
     info[sm.res_off + r] = o;
@@ -307,6 +310,7 @@ struct PairMeta {
   int n_small, n_large;
   long long out_off;             // per-row decision of the smaller set
   int rev, pad;                  // the pair was swapped (its first image is the larger set): MatchData::reverse
+  int k0, k1;                    // rows of the smaller set this call decides (row-sharded calls; else 0 .. n_small)
 };
 
 #define OUT_PENDING (-2)
@@ -334,8 +338,8 @@ __global__ void k_match_decide(const PairMeta* __restrict__ pairs, const SideMet
                                int* list_rows, int* list_unknown, int* __restrict__ side_cnt,
                                int n_sides) {
   const PairMeta pm = pairs[blockIdx.y];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= pm.n_small) return;
+  const int k = pm.k0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= pm.k1) return;
   const size_t oslot = pm.out_off + k;
   if (!first_round && out[oslot] != OUT_PENDING) return;
   int result = -1;
@@ -468,7 +472,7 @@ k_match_count(const PairMeta* __restrict__ pairs, const int* __restrict__ out, i
   __shared__ int s_c[8], s_p[8];
   const PairMeta pm = pairs[blockIdx.x];
   int c = 0, pend = 0;
-  for (int r = threadIdx.x; r < pm.n_small; r += 256) {
+  for (int r = pm.k0 + threadIdx.x; r < pm.k1; r += 256) {
     const int v = out[pm.out_off + r];
     c += v >= 0; pend += v == OUT_PENDING;
   }
@@ -523,9 +527,9 @@ k_match_write(const PairMeta* __restrict__ pairs, const int* __restrict__ out, i
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) s_base = 0;
   __syncthreads();
-  for (int r0 = 0; r0 < pm.n_small; r0 += 256) {
+  for (int r0 = pm.k0; r0 < pm.k1; r0 += 256) {
     const int r = r0 + tid;
-    const int j = r < pm.n_small ? out[pm.out_off + r] : -1;
+    const int j = r < pm.k1 ? out[pm.out_off + r] : -1;
     const unsigned bal = __ballot_sync(0xffffffffu, j >= 0);
     if (lane == 0) s_w[wid] = __popc(bal);
     __syncthreads();
@@ -558,6 +562,7 @@ struct MatchPlan {
   std::vector<char> rev;                // pair was swapped (first image is the larger set)
   long long res_total = 0, out_total = 0;
   int max_side_n = 0, max_small = 0;
+  int shard = 0, n_shards = 1;          // row-sharded call: this call decides share `shard` of every pair's smaller set
   bool lazy = false;                    // columns on demand: no first-pass tasks for the larger sets
   long long large_blocks = 0;           // 128-row blocks of all larger sets
   long long block_pairs = 0;            // sum over pairs of (blocks of the larger set) x (blocks of the smaller set)
@@ -594,6 +599,9 @@ static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int
     // (153 k block pairs, 1.81 -> 1.60 ms) and lose on 13 pairs of ~2.9 k rows (6.9 k block pairs).
     pl.lazy = pl.block_pairs >= 32768;
     if (const char* e = getenv("PANO_MATCH_LAZY")) pl.lazy = atoi(e) != 0;
+    // a shard nominates its own rows of the smaller sets only; whatever it needs of the larger sets
+    // (against ALL rows of the smaller set, matcher.cc:57-61) comes on request
+    if (pl.n_shards > 1) pl.lazy = true;
   }
   for (int k = 0; k < n_pairs; ++k) {
     int i = ij[2 * k], j = ij[2 * k + 1];
@@ -601,19 +609,21 @@ static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int
     const bool rev = fs->h_count[i] > fs->h_count[j];
     const int is = rev ? j : i, il = rev ? i : j;
     const int ns = fs->h_count[is], nl = fs->h_count[il];
-    SideMeta a{fs->base[is], fs->base[il], ns, nl, pl.res_total}; pl.res_total += ns;
-    SideMeta b{fs->base[il], fs->base[is], nl, ns, pl.res_total}; pl.res_total += nl;
-    PairMeta pm{(int)pl.sides.size(), (int)pl.sides.size() + 1, ns, nl, pl.out_total, rev ? 1 : 0, 0};
+    // rows [k0, k1) of the smaller set are this call's share (all of them unless row-sharded)
+    const int k0 = (int)((long long)ns * pl.shard / pl.n_shards), k1 = (int)((long long)ns * (pl.shard + 1) / pl.n_shards);
+    SideMeta a{fs->base[is], fs->base[il], ns, nl, pl.res_total, k0, k1}; pl.res_total += ns;
+    SideMeta b{fs->base[il], fs->base[is], nl, ns, pl.res_total, 0, nl}; pl.res_total += nl;
+    PairMeta pm{(int)pl.sides.size(), (int)pl.sides.size() + 1, ns, nl, pl.out_total, rev ? 1 : 0, 0, k0, k1};
     pl.out_total += ns;
     pl.sides.push_back(a); pl.sides.push_back(b);
     pl.pairs.push_back(pm);
     pl.rev.push_back(rev ? 1 : 0);
     pl.max_side_n = std::max(pl.max_side_n, std::max(ns, nl));
-    pl.max_small = std::max(pl.max_small, ns);
+    pl.max_small = std::max(pl.max_small, k1 - k0);
     if (tcimgs) {
       const TcImage &ts = (*tcimgs)[is], &tl = (*tcimgs)[il];
       if (nl > 0)
-        for (int r0 = 0; r0 < ns; r0 += 128)
+        for (int r0 = k0 / 128 * 128; r0 < k1; r0 += 128)
           pl.tc_tasks.push_back(TcTask{ts.blk0 + r0 / 128, r0, ns, tl.blk0, tl.n_pad / 128, nl, 0, a.res_off});
       if (ns > 0 && !pl.lazy)
         for (int r0 = 0; r0 < nl; r0 += 128)
@@ -621,7 +631,7 @@ static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int
       pl.gsides.push_back(TcGatherSide{a.q_base, a.res_off, a.res_off, ts.blk0, tl.blk0, tl.n_pad / 128, nl});
       pl.gsides.push_back(TcGatherSide{b.q_base, b.res_off, b.res_off, tl.blk0, ts.blk0, ts.n_pad / 128, ns});
     } else {
-      for (int r0 = 0; r0 < ns; r0 += MT) pl.exact_tasks.push_back(MatchTask{a.q_base, a.t_base, ns, nl, r0, a.res_off});
+      for (int r0 = k0 / MT * MT; r0 < k1; r0 += MT) pl.exact_tasks.push_back(MatchTask{a.q_base, a.t_base, ns, nl, r0, a.res_off});
       for (int r0 = 0; r0 < nl; r0 += MT) pl.exact_tasks.push_back(MatchTask{b.q_base, b.t_base, nl, ns, r0, b.res_off});
     }
   }
@@ -795,7 +805,9 @@ static int ensure_tc_operands(pano_ctx* ctx, pano_featureset* fs, std::vector<Tc
 }
 
 static int match_common(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int* ij, const pano_params* p,
-                        MatchPlan& pl, MatchBuffers& b) {
+                        int shard, int n_shards, MatchPlan& pl, MatchBuffers& b) {
+  if (n_shards < 1 || shard < 0 || shard >= n_shards) return ctx_fail(ctx, PANO_ERR_INVALID, "shard %d of %d", shard, n_shards);
+  pl.shard = shard; pl.n_shards = n_shards;
   int rc = featureset_sync_counts(fs);
   if (rc) return rc;
   const bool tensor = !use_exact_path();
@@ -810,12 +822,17 @@ extern "C" {
 
 int pano_match_pairs(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int* ij, const pano_params* p,
                      pano_matches* out) {
+  return pano_match_pairs_shard(ctx, fs, n_pairs, ij, p, 0, 1, out);
+}
+
+int pano_match_pairs_shard(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int* ij, const pano_params* p,
+                           int shard, int n_shards, pano_matches* out) {
   ctx_enter(ctx);
   if (!ctx || !fs || !out || n_pairs < 0 || (n_pairs && !ij) || !p) return PANO_ERR_INVALID;
   memset(out, 0, sizeof(*out));
   MatchPlan pl;
   MatchBuffers b;
-  int rc = match_common(ctx, fs, n_pairs, ij, p, pl, b);
+  int rc = match_common(ctx, fs, n_pairs, ij, p, shard, n_shards, pl, b);
   if (rc) { free_buffers(ctx, b, false); return rc; }
   // count -> offsets -> ordered compaction on the device; one read-back of header + matches
   const size_t n_hdr = 3 + 2 * (size_t)n_pairs;
@@ -864,11 +881,16 @@ void pano_matches_free(pano_matches* m) {
 
 int pano_match_pairs_dev(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int* ij, const pano_params* p,
                          int* total_matches) {
+  return pano_match_pairs_dev_shard(ctx, fs, n_pairs, ij, p, 0, 1, total_matches);
+}
+
+int pano_match_pairs_dev_shard(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int* ij, const pano_params* p,
+                               int shard, int n_shards, int* total_matches) {
   ctx_enter(ctx);
   if (!ctx || !fs || n_pairs < 0 || (n_pairs && !ij) || !p || !total_matches) return PANO_ERR_INVALID;
   MatchPlan pl;
   MatchBuffers b;
-  int rc = match_common(ctx, fs, n_pairs, ij, p, pl, b);
+  int rc = match_common(ctx, fs, n_pairs, ij, p, shard, n_shards, pl, b);
   if (rc) { free_buffers(ctx, b, false); return rc; }
   int* h = (int*)ctx_ring(ctx, (size_t)std::max(b.n_counters, MC_HEAD) * sizeof(int));
   if (!h) { free_buffers(ctx, b, false); return ctx_fail(ctx, PANO_ERR_CUDA, "pinned ring allocation failed"); }

@@ -51,6 +51,28 @@ def test_match_duplicates_and_ties(engine, orc, match_mode):
     assert np.array_equal(engine.match_bruteforce(b, a), orc.match(b, a))
 
 
+def test_match_row_shards_concatenate(engine, orc):
+    """pano_match_pairs_shard: share s of S of every pair's smaller set; the shares' lists in shard
+    order are the unsharded lists (the multi-GPU split of FeatureMatcher::match's loop over k)."""
+    rng = np.random.RandomState(5)
+    a = synth.rootsift_like(900, 9)
+    b = a[rng.permutation(900)][:700] + rng.randn(700, 128).astype(np.float32) * 20.0
+    c = np.concatenate([a[:300] + rng.randn(300, 128).astype(np.float32) * 8.0, synth.rootsift_like(250, 10)])
+    fs = engine.featureset_upload([a, b, c])
+    pairs = [(0, 1), (1, 2), (2, 0), (1, 0)]
+    full = engine.match_pairs(fs, pairs)
+    sets = [a, b, c]
+    for (i, j), m in zip(pairs, full):
+        assert np.array_equal(m, orc.match(sets[i], sets[j])), (i, j)
+    assert sum(len(m) for m in full) > 300
+    for S in (2, 3, 7):
+        parts = [engine.match_pairs(fs, pairs, shard=(s, S)) for s in range(S)]
+        for k in range(len(pairs)):
+            assert np.array_equal(np.concatenate([p[k] for p in parts]), full[k]), (S, k)
+        assert sum(engine.match_pairs_dev(fs, pairs, shard=(s, S)) for s in range(S)) == sum(len(m) for m in full)
+    fs.free()
+
+
 def test_match_empty(engine, match_mode):
     a = synth.rootsift_like(10, 6)
     assert len(engine.match_bruteforce(a, np.zeros((0, 128), np.float32))) == 0

@@ -430,3 +430,56 @@ def run_sharded(eng, rank, world, params, cfg_name="unordered_38x1300x867", band
                "mosaic_identical": same_o}
     dist.barrier()
     return res
+
+
+def run_sharded_sweep(eng, rank, world, params, n=100000, reps=3):
+    """Config 4 row-sharded across the ranks: every rank holds both descriptor sets and decides its
+    contiguous share of the smaller set's rows (pano_match_pairs_shard: the reference's `parallel for`
+    over k, matcher.cc:32); no collective on the data path.  Timed on the device as the max over
+    ranks; rank 0 repeats the match alone and compares the concatenated lists pair for pair."""
+    import torch
+    import torch.distributed as dist
+
+    a, b = sweep_sets(n)
+    fs = eng.featureset_upload([a, b])
+    del a, b
+    eng.match_pairs_dev(fs, [(0, 1)], params, shard=(rank, world))       # fp16 operands + pool warm-up
+    times = []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.match_pairs_dev(fs, [(0, 1)], params, shard=(rank, world))
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times.append(float(t.item()))
+    mine = eng.match_pairs(fs, [(0, 1)], params, shard=(rank, world))[0]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    res = None
+    if rank == 0:
+        one = []
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            eng.match_pairs_dev(fs, [(0, 1)], params)
+            s1.record()
+            torch.cuda.synchronize()
+            one.append(s0.elapsed_time(s1))
+        full = eng.match_pairs(fs, [(0, 1)], params)[0]
+        cat = np.concatenate(gathered) if gathered else np.zeros((0, 2), np.int32)
+        ms, one_ms = sorted(times)[len(times) // 2], sorted(one)[len(one) // 2]
+        _, tf_peak, _ = load_peaks()
+        tf = 2.0 * n * n * 128 / (ms * 1e-3) / 1e12
+        res = {"workload": f"descriptor brute-force match, {n} x {n} rows, rows of the smaller set split over the ranks",
+               "n_gpus": world, "partition": "rank r decides rows [n*r/G, n*(r+1)/G) of the smaller set against all rows; no data-path collective",
+               "ms_sharded": ms, "ms_one_gpu": one_ms, "speedup_vs_one_gpu": one_ms / ms, "efficiency_vs_one_gpu": one_ms / (world * ms),
+               "tflops_algorithmic": tf, "frac_of_peak_all_gpus": tf / (tf_peak * world), "matches": int(len(full)),
+               "pairs_identical": bool(np.array_equal(cat, full))}
+    fs.free()
+    dist.barrier()
+    return res
