@@ -113,9 +113,21 @@ int  ctx_copy_blocks(pano_ctx* ctx, int n, void* const* dst, const void* const* 
 void ctx_prof_begin(pano_ctx* ctx, const char* name);
 void ctx_prof_end(pano_ctx* ctx);
 
+// Diagnostics (PANO_TRACE_SLOW_MS=<ms>): report every wrapped driver-facing call that blocks the host
+// longer than the threshold — which call a stall sits in, not how long the GPU takes.
+double pano_now_ms();
+extern double g_trace_slow_ms;       // 0 = off
+void pano_trace_slow(const char* what, double ms);
+struct SlowCall {
+  const char* what; double t0;
+  explicit SlowCall(const char* w) : what(w), t0(g_trace_slow_ms > 0 ? pano_now_ms() : 0.0) {}
+  ~SlowCall() { if (g_trace_slow_ms > 0) { const double d = pano_now_ms() - t0; if (d > g_trace_slow_ms) pano_trace_slow(what, d); } }
+};
+
 #define PANO_CUDA(ctx, call)                                          \
   do {                                                                \
-    cudaError_t _e = (call);                                          \
+    cudaError_t _e;                                                   \
+    { SlowCall _sc(#call); _e = (call); }                             \
     if (_e != cudaSuccess) return ctx_cuda((ctx), _e, #call);         \
   } while (0)
 
@@ -124,7 +136,7 @@ void ctx_prof_end(pano_ctx* ctx);
   do {                                                                              \
     (ctx)->launches++;                                                              \
     if ((ctx)->profiling) ctx_prof_begin((ctx), (name));                            \
-    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                \
+    { SlowCall _sc(name); kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); } \
     if ((ctx)->profiling) ctx_prof_end((ctx));                                      \
     cudaError_t _e = cudaGetLastError();                                            \
     if (_e != cudaSuccess) return ctx_cuda((ctx), _e, name);                        \

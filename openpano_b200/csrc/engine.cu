@@ -2,7 +2,9 @@
 // libpano_b200.so that are not pure kernel drivers (see include/pano_b200.h).
 #include <mutex>
 #include "sift.cuh"
+#include <pthread.h>
 #include <stdarg.h>
+#include <time.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -24,7 +26,17 @@ int ctx_cuda(pano_ctx* ctx, cudaError_t e, const char* what) {
   return ctx_fail(ctx, PANO_ERR_CUDA, "CUDA error %s (%s) at %s", cudaGetErrorName(e), cudaGetErrorString(e), what);
 }
 
+double g_trace_slow_ms = [] { const char* e = getenv("PANO_TRACE_SLOW_MS"); return e ? atof(e) : 0.0; }();
+double pano_now_ms() {
+  timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+void pano_trace_slow(const char* what, double ms) {
+  fprintf(stderr, "[pano slow call] %-28s %9.1f ms  (thread %lx, at %.3f s)\n", what, ms, (unsigned long)pthread_self(), pano_now_ms() * 1e-3);
+}
+
 int ctx_alloc(pano_ctx* ctx, void** p, size_t bytes) {
+  SlowCall sc("ctx_alloc");
   *p = nullptr;
   bytes = (bytes + 15) / 16 * 16;      // word-granular helper kernels may touch the padding
   if (bytes == 0) bytes = 16;
@@ -34,6 +46,7 @@ int ctx_alloc(pano_ctx* ctx, void** p, size_t bytes) {
 }
 
 void ctx_free(pano_ctx* ctx, void* p) {
+  SlowCall sc("ctx_free");
   if (p) cudaFreeAsync(p, ctx->stream);
 }
 
@@ -77,6 +90,7 @@ __global__ void k_set_flag(volatile unsigned* flag, unsigned seq) {
 }
 
 cudaError_t ctx_signal(pano_ctx* ctx, unsigned* token) {
+  SlowCall sc("ctx_signal");
   if (!ctx->flag) {
     void* p = nullptr;
     cudaError_t e = cudaHostAlloc(&p, 64, cudaHostAllocMapped | cudaHostAllocPortable);
@@ -92,6 +106,7 @@ cudaError_t ctx_signal(pano_ctx* ctx, unsigned* token) {
 }
 
 cudaError_t ctx_wait_signal(pano_ctx* ctx, unsigned token) {
+  SlowCall sc("ctx_wait_signal(gpu)");
   if (!ctx->flag) return cudaStreamSynchronize(ctx->stream);
   for (long long spins = 0;; ++spins) {
     if ((int)(*ctx->flag - token) >= 0) return cudaSuccess;
@@ -116,6 +131,7 @@ __global__ void k_zero_u32(uint32_t* __restrict__ dst, size_t n) {
 }
 
 void* ctx_ring(pano_ctx* ctx, size_t bytes) {
+  SlowCall sc("ctx_ring");
   bytes = (bytes + 63) / 64 * 64;
   if (!ctx->ring || bytes > ctx->ring_cap) {
     if (ctx->ring) { cudaStreamSynchronize(ctx->stream); cudaFreeHost(ctx->ring); ctx->ring = nullptr; }
@@ -163,12 +179,14 @@ int ctx_fetch(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
   return PANO_OK;
 }
 int ctx_store(pano_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  SlowCall sc("ctx_store");
   if (!bytes) return PANO_OK;
   const size_t words = (bytes + 3) / 4;
   PANO_LAUNCH(ctx, "k_copy_u32", k_copy_u32, small_grid(words), 256, 0, (uint32_t*)h_dst, (const uint32_t*)d_src, words);
   return PANO_OK;
 }
 int ctx_put(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  SlowCall sc("ctx_put");
   if (!bytes) return PANO_OK;
   if (bytes <= 960 * 4) return ctx_put_many(ctx, 1, &d_dst, &h_src, &bytes);
   void* st = ctx_ring(ctx, bytes + 4);
@@ -177,6 +195,7 @@ int ctx_put(pano_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
   return ctx_fetch(ctx, d_dst, st, bytes);
 }
 int ctx_zero(pano_ctx* ctx, void* d_dst, size_t bytes) {
+  SlowCall sc("ctx_zero");
   if (!bytes) return PANO_OK;
   const size_t words = (bytes + 3) / 4;
   PANO_LAUNCH(ctx, "k_zero_u32", k_zero_u32, small_grid(words), 256, 0, (uint32_t*)d_dst, words);
@@ -254,6 +273,7 @@ static int put_many_params(pano_ctx* ctx, int n, void* const* d_dst, const void*
 }
 
 int ctx_put_many(pano_ctx* ctx, int n, void* const* d_dst, const void* const* h_src, const size_t* bytes) {
+  SlowCall sc("ctx_put_many");
   if (n > CTX_MAX_SEGS) return ctx_fail(ctx, PANO_ERR_INVALID, "ctx_put_many: %d segments", n);
   {
     size_t words = 0;
@@ -285,6 +305,7 @@ int ctx_put_many(pano_ctx* ctx, int n, void* const* d_dst, const void* const* h_
 }
 
 int ctx_store_many(pano_ctx* ctx, int n, void* const* h_pinned_dst, const void* const* d_src, const size_t* bytes) {
+  SlowCall sc("ctx_store_many");
   if (n > CTX_MAX_SEGS) return ctx_fail(ctx, PANO_ERR_INVALID, "ctx_store_many: %d segments", n);
   CopySegs segs;
   int m = 0;
@@ -316,6 +337,7 @@ __global__ void k_copy_blocks(const CopySeg* __restrict__ segs) {
 
 // dst / src must be 16-byte aligned device pointers (or bytes[i] < 16)
 int ctx_copy_blocks(pano_ctx* ctx, int n, void* const* dst, const void* const* src, const size_t* bytes) {
+  SlowCall sc("ctx_copy_blocks");
   std::vector<CopySeg> segs;
   size_t mx = 0;
   for (int i = 0; i < n; ++i)

@@ -168,6 +168,8 @@ struct SideMeta {        // one query set of one pair
   long long res_off;          // RowInfo / TcTop2 offset of this side
   int r0, r1;                 // rows of this side that went through the first pass (a row-sharded call
                               // nominates only its own rows of the smaller set; otherwise 0 .. q_n)
+  int parts, pad;             // first pass split into `parts` column ranges (tail balance); part p's
+                              // nominations sit at approx[p * res_total + res_off + row]
 };
 
 // Bound on |approx d^2 - exact fp32 d^2| for a query of squared norm nq against
@@ -217,7 +219,8 @@ __device__ __forceinline__ RowInfo refine_row(const float* __restrict__ desc, co
 // pass; their rows start unknown and are nominated on request (k_refine_gathered).
 __global__ void k_refine(const float* __restrict__ desc, const float* __restrict__ norms,
                          const unsigned* __restrict__ maxnorm_bits, const SideMeta* __restrict__ sides,
-                         const TcTop2* __restrict__ approx, float ratio_sqr, int lazy, RowInfo* __restrict__ info) {
+                         TcTop2* __restrict__ approx, long long res_total, float ratio_sqr, int lazy,
+                         RowInfo* __restrict__ info) {
   const int side = blockIdx.y;
   const SideMeta sm = sides[side];
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -229,7 +232,18 @@ __global__ void k_refine(const float* __restrict__ desc, const float* __restrict
     return;
   }
   const float nmax = __uint_as_float(*maxnorm_bits);
-  info[sm.res_off + r] = refine_row(desc, sm, r, approx[sm.res_off + r], tc_eps(norms[sm.q_base + r], nmax), ratio_sqr);
+  TcTop2 ap = approx[sm.res_off + r];
+  if (sm.parts > 1) {
+    // the column ranges ascend with the part index, so on equal scores the earlier part keeps the
+    // argmin: the same "lowest column" rule as inside one part
+    for (int p = 1; p < sm.parts; ++p) {
+      const TcTop2 q = approx[(long long)p * res_total + sm.res_off + r];
+      if (q.m1 < ap.m1) { ap.m2 = fminf(ap.m1, q.m2); ap.m1 = q.m1; ap.idx = q.idx; }
+      else ap.m2 = fminf(ap.m2, q.m1);
+    }
+    approx[sm.res_off + r] = ap;     // where the filter pass looks for the row's threshold
+  }
+  info[sm.res_off + r] = refine_row(desc, sm, r, ap, tc_eps(norms[sm.q_base + r], nmax), ratio_sqr);
 }
 
 // The same certification for rows nominated on request: gathered row g carries (side, row) in
@@ -558,10 +572,12 @@ struct MatchPlan {
   std::vector<PairMeta> pairs;
   std::vector<MatchTask> exact_tasks;   // exact path
   std::vector<TcTask> tc_tasks;         // tensor path
+  std::vector<int> task_part;           // tensor path: column-range index of each task
   std::vector<TcGatherSide> gsides;     // tensor path: per side, for the gathered second pass
   std::vector<char> rev;                // pair was swapped (first image is the larger set)
   long long res_total = 0, out_total = 0;
   int max_side_n = 0, max_small = 0;
+  int parts = 1;                        // first-pass tasks are split into up to this many column ranges
   int shard = 0, n_shards = 1;          // row-sharded call: this call decides share `shard` of every pair's smaller set
   bool lazy = false;                    // columns on demand: no first-pass tasks for the larger sets
   long long large_blocks = 0;           // 128-row blocks of all larger sets
@@ -602,6 +618,29 @@ static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int
     // a shard nominates its own rows of the smaller sets only; whatever it needs of the larger sets
     // (against ALL rows of the smaller set, matcher.cc:57-61) comes on request
     if (pl.n_shards > 1) pl.lazy = true;
+    // Tail balance.  The persistent CTAs walk equal tasks round-robin, so n tasks take
+    // ceil(n / SMs) task times: 782 tasks (100 k rows) on 148 SMs waste 12 % in the last wave.
+    // Splitting every task into P column ranges (merged in k_refine) makes the waves P times finer.
+    long long n1 = 0, tile_sum = 0;       // first-pass tasks, and their target tiles
+    for (int k = 0; k < n_pairs; ++k) {
+      const int ci = fs->h_count[ij[2 * k]], cj = fs->h_count[ij[2 * k + 1]];
+      if (ci <= 0 || cj <= 0) continue;
+      const long long bs = (std::min(ci, cj) + 127) / 128, bl = (std::max(ci, cj) + 127) / 128;
+      const long long ts = (std::min(ci, cj) + 255) / 256, tl = (std::max(ci, cj) + 255) / 256;
+      const long long mine = pl.lazy ? (bs + pl.n_shards - 1) / pl.n_shards : bs;
+      n1 += mine; tile_sum += mine * tl;
+      if (!pl.lazy) { n1 += bl; tile_sum += bl * ts; }
+    }
+    const long long W = std::max(1, ctx->num_sms);
+    if (n1 > 0 && n1 < 12 * W) {
+      // waves x (tiles per part + ~0.7 tile of per-task prologue / merge); split only for a real gain
+      const double T = (double)tile_sum / (double)n1;
+      auto cost = [&](int P) { return (double)((n1 * P + W - 1) / W) * (T / P + 0.7); };
+      double best = cost(1) * 0.96;
+      for (int P = 2; P <= 8; ++P)
+        if (T / P >= 4.0 && cost(P) < best * 0.99) { best = cost(P); pl.parts = P; }
+    }
+    if (const char* e = getenv("PANO_MATCH_PARTS")) pl.parts = std::max(1, std::min(8, atoi(e)));
   }
   for (int k = 0; k < n_pairs; ++k) {
     int i = ij[2 * k], j = ij[2 * k + 1];
@@ -611,8 +650,11 @@ static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int
     const int ns = fs->h_count[is], nl = fs->h_count[il];
     // rows [k0, k1) of the smaller set are this call's share (all of them unless row-sharded)
     const int k0 = (int)((long long)ns * pl.shard / pl.n_shards), k1 = (int)((long long)ns * (pl.shard + 1) / pl.n_shards);
-    SideMeta a{fs->base[is], fs->base[il], ns, nl, pl.res_total, k0, k1}; pl.res_total += ns;
-    SideMeta b{fs->base[il], fs->base[is], nl, ns, pl.res_total, 0, nl}; pl.res_total += nl;
+    // a part must keep >= 4 target tiles (256 rows each), or its prologue costs more than it balances
+    const int tiles_l = tcimgs ? (*tcimgs)[il].n_pad / 256 : 0, tiles_s = tcimgs ? (*tcimgs)[is].n_pad / 256 : 0;
+    const int parts_a = std::max(1, std::min(pl.parts, tiles_l / 4)), parts_b = pl.lazy ? 1 : std::max(1, std::min(pl.parts, tiles_s / 4));
+    SideMeta a{fs->base[is], fs->base[il], ns, nl, pl.res_total, k0, k1, parts_a, 0}; pl.res_total += ns;
+    SideMeta b{fs->base[il], fs->base[is], nl, ns, pl.res_total, 0, nl, parts_b, 0}; pl.res_total += nl;
     PairMeta pm{(int)pl.sides.size(), (int)pl.sides.size() + 1, ns, nl, pl.out_total, rev ? 1 : 0, 0, k0, k1};
     pl.out_total += ns;
     pl.sides.push_back(a); pl.sides.push_back(b);
@@ -622,12 +664,19 @@ static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int
     pl.max_small = std::max(pl.max_small, k1 - k0);
     if (tcimgs) {
       const TcImage &ts = (*tcimgs)[is], &tl = (*tcimgs)[il];
-      if (nl > 0)
-        for (int r0 = k0 / 128 * 128; r0 < k1; r0 += 128)
-          pl.tc_tasks.push_back(TcTask{ts.blk0 + r0 / 128, r0, ns, tl.blk0, tl.n_pad / 128, nl, 0, a.res_off});
-      if (ns > 0 && !pl.lazy)
-        for (int r0 = 0; r0 < nl; r0 += 128)
-          pl.tc_tasks.push_back(TcTask{tl.blk0 + r0 / 128, r0, nl, ts.blk0, ts.n_pad / 128, ns, 0, b.res_off});
+      // part p covers target tiles [tiles * p / parts, tiles * (p + 1) / parts); its first column rides
+      // in t_pad and its part index is folded into res_off once res_total is known (below)
+      auto add_tasks = [&](const TcImage& tq, const TcImage& tt, int row_lo, int row_hi, int q_n, int t_n, long long res_off, int parts) {
+        const int tiles = tt.n_pad / 256;
+        for (int r0 = row_lo / 128 * 128; r0 < row_hi; r0 += 128)
+          for (int pp = 0; pp < parts; ++pp) {
+            const int t0 = (int)((long long)tiles * pp / parts), t1 = (int)((long long)tiles * (pp + 1) / parts);
+            pl.tc_tasks.push_back(TcTask{tq.blk0 + r0 / 128, r0, q_n, tt.blk0 + 2 * t0, 2 * (t1 - t0), t_n, t0 * 256, res_off});
+            pl.task_part.push_back(pp);
+          }
+      };
+      if (nl > 0) add_tasks(ts, tl, k0, k1, ns, nl, a.res_off, parts_a);
+      if (ns > 0 && !pl.lazy) add_tasks(tl, ts, 0, nl, nl, ns, b.res_off, parts_b);
       pl.gsides.push_back(TcGatherSide{a.q_base, a.res_off, a.res_off, ts.blk0, tl.blk0, tl.n_pad / 128, nl});
       pl.gsides.push_back(TcGatherSide{b.q_base, b.res_off, b.res_off, tl.blk0, ts.blk0, ts.n_pad / 128, ns});
     } else {
@@ -635,6 +684,7 @@ static int build_plan(pano_ctx* ctx, pano_featureset* fs, int n_pairs, const int
       for (int r0 = 0; r0 < nl; r0 += MT) pl.exact_tasks.push_back(MatchTask{b.q_base, b.t_base, nl, ns, r0, b.res_off});
     }
   }
+  for (size_t t = 0; t < pl.tc_tasks.size(); ++t) pl.tc_tasks[t].res_off += (long long)pl.task_part[t] * pl.res_total;
   return PANO_OK;
 }
 
@@ -674,7 +724,7 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
   const long long nres = std::max<long long>(pl.res_total, 1);
   if ((rc = ctx_alloc(ctx, &b.tasks, bt)) || (rc = ctx_alloc(ctx, (void**)&b.pairs, bp)) ||
       (rc = ctx_alloc(ctx, (void**)&b.sides, bs)) || (rc = ctx_alloc(ctx, (void**)&b.info, nres * sizeof(RowInfo))) ||
-      (rc = ctx_alloc(ctx, (void**)&b.approx, nres * sizeof(TcTop2))) ||
+      (rc = ctx_alloc(ctx, (void**)&b.approx, nres * std::max(pl.parts, 1) * sizeof(TcTop2))) ||
       (rc = ctx_alloc(ctx, (void**)&b.list, nres * sizeof(int2))) ||
       (rc = ctx_alloc(ctx, (void**)&b.out, std::max<long long>(pl.out_total, 1) * sizeof(int))))
     return rc;
@@ -714,8 +764,8 @@ static int run_plan(pano_ctx* ctx, pano_featureset* fs, const MatchPlan& pl, flo
   if (rc) return rc;
   if (pl.max_side_n > 0) {
     dim3 gr(ceil_div(pl.max_side_n, 128), (unsigned)pl.sides.size());
-    PANO_LAUNCH(ctx, "k_refine", k_refine, gr, 128, 0, fs->d_desc, ops->d_norms, ops->d_maxnorm, b.sides, b.approx, rs,
-                pl.lazy ? 1 : 0, b.info);
+    PANO_LAUNCH(ctx, "k_refine", k_refine, gr, 128, 0, fs->d_desc, ops->d_norms, ops->d_maxnorm, b.sides, b.approx,
+                (long long)pl.res_total, rs, pl.lazy ? 1 : 0, b.info);
   }
   if (pl.max_small > 0) {
     // Up to three decide rounds.  A round decides every row it can from the current

@@ -299,6 +299,7 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
       int g1 = 0x7f7fff00, g2 = 0x7f7fff00;   // running best / second (value bits, low 8 cleared)
       int gi = 0x7fffffff;
       const int grow = tk.q_row0 + row;        // FILTER: index of this gathered row
+      const int col0 = (FILTER || n_tasks_dev) ? 0 : tk.t_pad;   // first pass: first column of this task's range
       uint32_t keymask;
       asm volatile("mov.b32 %0, 0xffffff00;" : "=r"(keymask));
       const int thr = FILTER ? g_thr[grow] : 0;
@@ -346,7 +347,7 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
         if (!FILTER) {
           // merge the tile's top-2 into the running top-2
           const int v1 = k1 & (int)0xffffff00, v2 = k2 & (int)0xffffff00;
-          if (v1 < g1) { g2 = min(g1, v2); g1 = v1; gi = t * 256 + grp * 128 + (k1 & 0xff); }
+          if (v1 < g1) { g2 = min(g1, v2); g1 = v1; gi = col0 + t * 256 + grp * 128 + (k1 & 0xff); }
           else g2 = min(g2, v1);
         }
       }

@@ -20,7 +20,8 @@ struct TcTask {       // one CTA: 128 query rows against every target row
   int q_row0, q_n;    // top2: first query row of this block within its image, rows in the image
                       // filter: index of the block's first gathered row, real rows in the block
   int t_blk0, t_blocks;  // target image: first block, number of blocks (even)
-  int t_n, t_pad;     // real target rows; filter: first list slot of this block
+  int t_n, t_pad;     // real target rows; filter: first list slot of this block; first pass: the first
+                      // target column of this task (a task may cover only a range of the target tiles)
   long long res_off;  // top2: where the query image's results start; filter: side index
 };
 

@@ -981,6 +981,7 @@ typedef CUresult (*tma_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 int ctx_tma_encode(pano_ctx* ctx, TmaDesc* out, void* base, int rank, const unsigned long long* dims,
                    const unsigned long long* strides_bytes, const unsigned* box) {
+  SlowCall sc("ctx_tma_encode");
   if (!ctx->tma_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -1210,6 +1211,7 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
 // again with doubled lists — the sources are still there (pano_b200.h) — and the larger
 // capacity becomes this context's starting point.  A failure is sticky.
 int featureset_sync_counts(pano_featureset* fs) {
+  SlowCall sc("featureset_sync_counts");
   if (fs->error) return fs->error;
   if (fs->counts_on_host) return PANO_OK;
   pano_ctx* ctx = fs->ctx;

@@ -51,6 +51,26 @@ def test_match_duplicates_and_ties(engine, orc, match_mode):
     assert np.array_equal(engine.match_bruteforce(b, a), orc.match(b, a))
 
 
+@pytest.mark.parametrize("parts", ["2", "3", "8"])
+@pytest.mark.parametrize("lazy", ["0", "1"])
+def test_match_first_pass_column_ranges(engine, orc, monkeypatch, parts, lazy):
+    """PANO_MATCH_PARTS splits every first-pass task into column ranges merged in k_refine (tail
+    balance on large runs).  Exact duplicates placed in different ranges tie on the score: the
+    lowest column has to win, as in one range."""
+    rng = np.random.RandomState(11)
+    a = synth.rootsift_like(1100, 12)
+    far = synth.rootsift_like(2400, 13)
+    b = np.concatenate([a[:150], far[:1200], a[:150], far[1200:], a[100:400] + rng.randn(300, 128).astype(np.float32) * 15.0])
+    monkeypatch.setenv("PANO_MATCH_PARTS", parts)
+    monkeypatch.setenv("PANO_MATCH_LAZY", lazy)
+    got_ab, got_ba = engine.match_bruteforce(a, b), engine.match_bruteforce(b, a)
+    monkeypatch.delenv("PANO_MATCH_PARTS", raising=False)
+    monkeypatch.delenv("PANO_MATCH_LAZY", raising=False)
+    assert np.array_equal(got_ab, orc.match(a, b))
+    assert np.array_equal(got_ba, orc.match(b, a))
+    assert len(got_ab) > 50
+
+
 def test_match_row_shards_concatenate(engine, orc):
     """pano_match_pairs_shard: share s of S of every pair's smaller set; the shares' lists in shard
     order are the unsharded lists (the multi-GPU split of FeatureMatcher::match's loop over k)."""
