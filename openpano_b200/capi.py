@@ -51,6 +51,7 @@ def _load():
         "pano_profile_reset": (C.c_int, [C.c_void_p]),
         "pano_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, _ip, _dp]),
         "pano_launch_count": (C.c_longlong, [C.c_void_p]),
+        "pano_trim": (C.c_int, [C.c_void_p]),
         "pano_match_last_exact_rows": (C.c_int, [C.c_void_p]),
         "pano_match_last_nominated_rows": (C.c_int, [C.c_void_p]),
         "pano_sift_detect_batch": (C.c_int, [C.c_void_p, C.c_int, _vpp, _ip, _ip, P, _vpp]),
@@ -272,6 +273,10 @@ class Engine:
     @property
     def stream(self):
         return LIB.pano_stream(self._h)
+
+    def trim(self):
+        """Hand the freed device blocks this context keeps for reuse back to its pool."""
+        self._check(LIB.pano_trim(self._h))
 
     def launch_count(self):
         return LIB.pano_launch_count(self._h)

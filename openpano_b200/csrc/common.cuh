@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <unordered_map>
 
 #include "../../include/pano_b200.h"
 
@@ -30,6 +31,12 @@ struct pano_ctx {
   cudaStream_t stream = nullptr;
   bool owns_stream = false;
   cudaMemPool_t pool = nullptr;   // this context's own stream-ordered pool (see ctx_alloc)
+  // Freed blocks kept for the next request of (about) the same size: see ctx_alloc
+  struct CachedBlock { void* p; unsigned long long stamp; };
+  std::multimap<size_t, CachedBlock> cache;        // size -> free block
+  std::unordered_map<void*, size_t> live;           // blocks handed out -> their true size
+  size_t cached_bytes = 0, cache_limit = (size_t)8 << 30;
+  unsigned long long cache_stamp = 0;
   std::string err;
   bool profiling = false;
   std::vector<ProfEvent> prof_pending;
@@ -72,7 +79,16 @@ int  ctx_cuda(pano_ctx* ctx, cudaError_t e, const char* what);
 // default pool hand each other freed blocks, and the allocator then makes the taking
 // stream wait for the giving stream ("internal dependencies"): concurrent stitch lanes
 // drifted from 2.3 to 5+ ms per job as their arenas started to cross over.
+// On top of the pool sits a per-context cache of freed blocks, matched by size (best fit within
+// 25 %): a stitch job asks for the same ~40 sizes every time, up to a 0.9 GB pyramid arena, and
+// cudaMallocFromPoolAsync was seen to block the host for 0.1 - 1.5 s a few times per second when
+// it had to re-arrange the pool's mappings for such a request — with the allocator's lock held,
+// so every other lane of the process stalled with it (profiles/r02s_e2e_pause_probe.txt).
+// Everything a context allocates is used on its one stream, so handing a block freed after its
+// last enqueued use to the next request is ordered by the stream itself.  PANO_CACHE_MB bounds
+// the cache (default 8192, 0 = off); pano_trim() gives the cached blocks back to the pool.
 int  ctx_alloc(pano_ctx* ctx, void** p, size_t bytes);
+void ctx_cache_release(pano_ctx* ctx, size_t keep_bytes);
 void ctx_free(pano_ctx* ctx, void* p);
 void* ctx_pinned(pano_ctx* ctx, size_t bytes);   // staging buffer A (inputs)
 void* ctx_pinned2(pano_ctx* ctx, size_t bytes);  // staging buffer B (results)

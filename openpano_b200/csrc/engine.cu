@@ -40,14 +40,51 @@ int ctx_alloc(pano_ctx* ctx, void** p, size_t bytes) {
   *p = nullptr;
   bytes = (bytes + 15) / 16 * 16;      // word-granular helper kernels may touch the padding
   if (bytes == 0) bytes = 16;
+  if (ctx->cache_limit) {
+    // smallest cached block that fits and wastes at most a quarter (+64 KB for the small ones)
+    auto it = ctx->cache.lower_bound(bytes);
+    if (it != ctx->cache.end() && it->first <= bytes + bytes / 4 + 65536) {
+      *p = it->second.p;
+      ctx->live[*p] = it->first;
+      ctx->cached_bytes -= it->first;
+      ctx->cache.erase(it);
+      return PANO_OK;
+    }
+  }
   cudaError_t e = ctx->pool ? cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream) : cudaMallocAsync(p, bytes, ctx->stream);
+  if (e != cudaSuccess && ctx->cached_bytes) {      // out of memory with blocks parked here: give them back, retry
+    cudaGetLastError();
+    ctx_cache_release(ctx, 0);
+    e = ctx->pool ? cudaMallocFromPoolAsync(p, bytes, ctx->pool, ctx->stream) : cudaMallocAsync(p, bytes, ctx->stream);
+  }
   if (e != cudaSuccess) return ctx_cuda(ctx, e, "cudaMallocAsync");
+  if (ctx->cache_limit) ctx->live[*p] = bytes;
   return PANO_OK;
+}
+
+void ctx_cache_release(pano_ctx* ctx, size_t keep_bytes) {
+  // oldest blocks first: what has not been asked for again is least likely to be
+  while (ctx->cached_bytes > keep_bytes && !ctx->cache.empty()) {
+    auto oldest = ctx->cache.begin();
+    for (auto it = ctx->cache.begin(); it != ctx->cache.end(); ++it)
+      if (it->second.stamp < oldest->second.stamp) oldest = it;
+    cudaFreeAsync(oldest->second.p, ctx->stream);
+    ctx->cached_bytes -= oldest->first;
+    ctx->cache.erase(oldest);
+  }
 }
 
 void ctx_free(pano_ctx* ctx, void* p) {
   SlowCall sc("ctx_free");
-  if (p) cudaFreeAsync(p, ctx->stream);
+  if (!p) return;
+  auto f = ctx->live.find(p);
+  if (f == ctx->live.end()) { cudaFreeAsync(p, ctx->stream); return; }
+  const size_t size = f->second;
+  ctx->live.erase(f);
+  if (!ctx->cache_limit || size > ctx->cache_limit) { cudaFreeAsync(p, ctx->stream); return; }
+  ctx->cache.emplace(size, pano_ctx::CachedBlock{p, ++ctx->cache_stamp});
+  ctx->cached_bytes += size;
+  if (ctx->cached_bytes > ctx->cache_limit) ctx_cache_release(ctx, ctx->cache_limit);
 }
 
 static void* grow_pinned(void** buf, size_t* cap, size_t bytes) {
@@ -442,13 +479,22 @@ int pano_create(pano_ctx** out, int device, void* cuda_stream) {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(ctx->pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
+  if (const char* e = getenv("PANO_CACHE_MB")) ctx->cache_limit = (size_t)std::max(0LL, atoll(e)) << 20;
   *out = ctx;
+  return PANO_OK;
+}
+
+int pano_trim(pano_ctx* ctx) {
+  if (!ctx) return PANO_ERR_INVALID;
+  ctx_enter(ctx);
+  ctx_cache_release(ctx, 0);
   return PANO_OK;
 }
 
 void pano_destroy(pano_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  ctx_cache_release(ctx, 0);
   cudaStreamSynchronize(ctx->stream);
   prof_drain(ctx);
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
