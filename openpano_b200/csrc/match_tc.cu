@@ -37,7 +37,8 @@
 
 #define TC_KC 18                       // 16-byte k-chunks per row: 144 fp16
 #define TC_BLOCK_BYTES (TC_KC * 2048)  // 128 rows x 144 fp16 = 36864 B
-#define TC_LBO 2048u                   // byte stride between k-chunks
+#define TC_LBO 2048u                   // byte stride between k-chunks (128-row query blocks)
+#define TC_TLBO 4096u                  // the same for the 256-row target tiles
 #define TC_SBO 128u                    // byte stride between 8-row groups
 #define TC_TILE_BLOCKS 2               // target tile = 2 blocks = 256 rows
 #define TC_STAGES 2
@@ -83,7 +84,11 @@ __global__ void k_tc_prep(const float* __restrict__ desc, const float* __restric
   const size_t blk = (size_t)(im.blk0 + r / 128);
   const int rr = r % 128;
   unsigned char* qd = qbuf + blk * TC_BLOCK_BYTES + (rr / 8) * TC_SBO + (rr % 8) * 16;
-  unsigned char* td = tbuf + blk * TC_BLOCK_BYTES + (rr / 8) * TC_SBO + (rr % 8) * 16;
+  // targets are laid out in 256-ROW tiles (one N = 256 MMA reads a whole tile: 32 row groups at SBO
+  // per k-chunk, k-chunks TC_TLBO apart); n_pad is a multiple of 256, so tile t of an image starts
+  // at block blk0 + 2 t either way
+  const int tr = r % 256;
+  unsigned char* td = tbuf + (size_t)(im.blk0 + (r / 256) * 2) * TC_BLOCK_BYTES + (tr / 8) * TC_SBO + (tr % 8) * 16;
   const bool real = r < im.n;
   const float4* p = (const float4*)(desc + (size_t)(im.row0 + (real ? r : 0)) * 128);
 #pragma unroll 4
@@ -99,7 +104,7 @@ __global__ void k_tc_prep(const float* __restrict__ desc, const float* __restric
     qv.x = *(unsigned*)&q0; qv.y = *(unsigned*)&q1; qv.z = *(unsigned*)&q2; qv.w = *(unsigned*)&q3;
     tv.x = *(unsigned*)&t0; tv.y = *(unsigned*)&t1; tv.z = *(unsigned*)&t2; tv.w = *(unsigned*)&t3;
     *(uint4*)(qd + (size_t)kc * TC_LBO) = qv;
-    *(uint4*)(td + (size_t)kc * TC_LBO) = tv;
+    *(uint4*)(td + (size_t)kc * TC_TLBO) = tv;
   }
   // extra k-step: chunks 16 and 17
   float n = real ? norms[im.row0 + r] * s * s : 0.f;
@@ -113,9 +118,9 @@ __global__ void k_tc_prep(const float* __restrict__ desc, const float* __restric
     qx[2] = zero; qx[3] = zero;
   }
   *(uint4*)(qd + (size_t)16 * TC_LBO) = *(uint4*)qx;
-  *(uint4*)(td + (size_t)16 * TC_LBO) = *(uint4*)tx;
+  *(uint4*)(td + (size_t)16 * TC_TLBO) = *(uint4*)tx;
   *(uint4*)(qd + (size_t)17 * TC_LBO) = make_uint4(0, 0, 0, 0);
-  *(uint4*)(td + (size_t)17 * TC_LBO) = make_uint4(0, 0, 0, 0);
+  *(uint4*)(td + (size_t)17 * TC_TLBO) = make_uint4(0, 0, 0, 0);
 }
 
 // ------------------------------------------------------------------ PTX helpers
@@ -150,9 +155,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo) {
   // UMMA::SmemDescriptor (K-major, SWIZZLE_NONE): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48)
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(TC_LBO >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) |
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(TC_SBO >> 4) << 32) |
          (1ull << 46);
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -257,7 +262,7 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
     // ===== MMA issuer (one thread)
     if (lane == 0) {
       // UMMA::InstrDescriptor: c_format F32 [4,6)=1, a/b F16 = 0, K-major both, N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24);   // M 128, N 256
       uint32_t gt = 0, ti = 0;
       for (int task = blockIdx.x; task < task_end; task += gridDim.x, ++ti) {
         const TcTask tk = tasks[task];
@@ -270,18 +275,19 @@ k_tc_pass(const unsigned char* __restrict__ qbuf, const unsigned char* __restric
           mbar_wait(smem_u32(&bars->full[s]), (gt / TC_STAGES) & 1u);
           const uint32_t b0 = smem_u32(sB + (size_t)s * TC_TILE_BLOCKS * TC_BLOCK_BYTES);
 #pragma unroll
-          for (int half = 0; half < TC_TILE_BLOCKS; ++half) {
-            mbar_wait(smem_u32(&bars->acc_empty[as][half]), ((gt >> 1) & 1u) ^ 1u);
-            tc_fence_after();
-            const uint32_t d = tmem + (uint32_t)(as * 256 + half * 128);
+          for (int half = 0; half < TC_EPI_GROUPS; ++half) mbar_wait(smem_u32(&bars->acc_empty[as][half]), ((gt >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+          // one M128 N256 K16 instruction per k-step covers the whole 256-row target tile: the query
+          // block is read from shared memory once per tile and k-step instead of once per half
+          const uint32_t d = tmem + (uint32_t)(as * 256);
 #pragma unroll
-            for (int k = 0; k < TC_KC / 2; ++k) {
-              const uint64_t ad = make_smem_desc(a0 + k * 2 * TC_LBO);
-              const uint64_t bd = make_smem_desc(b0 + half * TC_BLOCK_BYTES + k * 2 * TC_LBO);
-              umma_f16(d, ad, bd, idesc, k > 0 ? 1u : 0u);
-            }
-            umma_commit(smem_u32(&bars->acc_full[as][half]));  // this half is ready for its epilogue group
+          for (int k = 0; k < TC_KC / 2; ++k) {
+            const uint64_t ad = make_smem_desc(a0 + k * 2 * TC_LBO, TC_LBO);
+            const uint64_t bd = make_smem_desc(b0 + k * 2 * TC_TLBO, TC_TLBO);
+            umma_f16(d, ad, bd, idesc, k > 0 ? 1u : 0u);
           }
+#pragma unroll
+          for (int half = 0; half < TC_EPI_GROUPS; ++half) umma_commit(smem_u32(&bars->acc_full[as][half]));   // both column halves are ready
           umma_commit(smem_u32(&bars->empty[s]));      // smem slot reusable once these MMAs retire
         }
         umma_commit(smem_u32(&bars->a_empty[asl]));    // every MMA that reads this query block has retired

@@ -1,6 +1,8 @@
 #!/usr/bin/env python
 """Profiling target: the brute-force match of the config-4 sweep at one size, N times.
-  ncu --set full -k regex:k_tc_pass --launch-skip 3 -c 1 -o gpurun_out/sweep python tools/sweep_step.py 100000 2
+  ncu --set full -k regex:k_tc_pass --launch-skip 7 -c 2 -o gpurun_out/sweep python tools/sweep_step.py 100000 2
+(a match call launches k_tc_pass seven times with columns on demand — first pass, then nomination and
+filter in each of three rounds — so skip 7 lands on the second call's first pass and nomination)
 """
 import sys
 from pathlib import Path
