@@ -13,21 +13,28 @@
 //     target form: [ -2*s*x     | n_hi, n_lo, 1, 1, 1, 0... ]     n = s^2*|x|^2
 // so that  q . t = s^2 * |xq - xt|^2 + 1   (>= ~1: positive floats order like
 // ints).  s is a power of two making n <= 1024 (s = 1/16 for RootSIFT, |x| = 512).
-// Rows are stored PRE-BLOCKED in the UMMA canonical K-major no-swizzle layout
-// (128-row blocks, 8x16-byte core matrices, SBO = 128 B, LBO = 2 KiB), so one
-// contiguous cp.async.bulk brings a block into shared memory ready for the MMA.
+// Rows are stored PRE-BLOCKED in the UMMA canonical K-major no-swizzle layout (8x16-byte core
+// matrices, SBO = 128 B): query rows in 128-row blocks (LBO = 2 KiB), target rows in 256-row
+// tiles (LBO = 4 KiB), so one contiguous cp.async.bulk brings a block / tile into shared memory
+// ready for the MMA.
 //
-// Kernel k_tc_top2, one CTA per (query block of 128 rows) x (all target rows):
-//   warp 0   producer : cp.async.bulk of target tiles (256 rows) into a 2-stage ring
-//   warp 1   MMA      : 2 x 9 tcgen05.mma (M128 N128 K16) per tile into one of two
-//                       256-column TMEM accumulator stages, tcgen05.commit -> mbarriers
+// Kernel k_tc_pass, persistent, one CTA per SM walking tasks = (query block of 128 rows) x (a range
+// of target tiles):
+//   warp 0   producer : cp.async.bulk of target tiles (256 rows, 72 KiB) into a 2-stage ring,
+//                       query blocks into two buffers
+//   warp 1   MMA      : 9 tcgen05.mma (M128 N256 K16) per tile into one of two 256-column TMEM
+//                       accumulator stages, tcgen05.commit -> mbarriers (N = 256: the query block
+//                       is read from shared memory once per tile and k-step; two N = 128
+//                       instructions per k-step measured 13 % slower at 100 k x 100 k)
 //   warp 2   TMEM alloc/dealloc (512 columns)
 //   warps 4-11 epilogue: two groups of four warps; group g owns the g-th 128-column half of
 //                       every accumulator stage (its own full/empty barriers), so each SM
 //                       sub-partition holds two epilogue warps and one computes while the
 //                       other waits for its tcgen05.ld.  32 columns at a time; thread = query
 //                       row keeps a running (min, argmin, second-min) with the column packed
-//                       into the low mantissa bits (3 integer min/max + 1 LOP3 per element);
+//                       into the low mantissa bits (3.5 ALU instructions per element: one LOP3,
+//                       2.5 VIMNMX / VIMNMX3); on long target sets a chunk whose 32-way minimum
+//                       is not below the row's running second best is skipped (0.5 per element);
 //                       the groups' results are merged through shared memory per task
 #include "sift.cuh"
 #include "match_tc.cuh"
