@@ -7,6 +7,7 @@
 // feature/orientation.cc:22-100, feature/sift.cc:15-152, lib/imgproc.cc:22-80,
 // :237-249.  One launch per stage covers every image and octave of the batch.
 #include "sift.cuh"
+#include "desc_interval.h"
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -514,7 +515,7 @@ __global__ void k_refine(const OctMeta* __restrict__ octs, const float* __restri
 #define SIFT_MAX_IMG 512                // images per SIFT batch (prefix tables in shared memory)
 
 __global__ void __launch_bounds__(ORI_WARPS * 32)
-k_orientation(const OctMeta* __restrict__ octs, const float* __restrict__ arena, int n_oct, int n_img, int cap,
+k_orientation_v1(const OctMeta* __restrict__ octs, const float* __restrict__ arena, int n_oct, int n_img, int cap,
               const int* __restrict__ cand_count, const pano_sspoint* __restrict__ pts,
               const unsigned char* __restrict__ valid, float ori_radius, int smooth_count,
               int* __restrict__ npeaks, float* __restrict__ dirs, int* __restrict__ work_counter) {
@@ -633,6 +634,144 @@ k_orientation(const OctMeta* __restrict__ octs, const float* __restrict__ arena,
   }
 }
 
+// K5, quad design.  Same contract as k_orientation_v1 (bit-identical output).  FOUR LANES
+// per keypoint, eight keypoints per warp: a trip bins four window positions per keypoint and
+// adds them to the keypoint's shared-memory histogram one lane after the other — lane order is
+// the reference's scan order — so nothing is staged and replayed (v1: every lane replayed all
+// 256 staged positions for its own bin, most of the kernel), and the strictly sequential
+// parts (in-place smoothing, the maximum) run for eight keypoints at once instead of on one
+// lane of a warp.  Window positions are carried as (xx, yy) per lane instead of a divide.
+#define ORI_QUADS 8
+__global__ void __launch_bounds__(ORI_WARPS * 32)
+k_orientation(const OctMeta* __restrict__ octs, const float* __restrict__ arena, int n_oct, int n_img, int cap,
+              const int* __restrict__ cand_count, const pano_sspoint* __restrict__ pts,
+              const unsigned char* __restrict__ valid, float ori_radius, int smooth_count,
+              int* __restrict__ npeaks, float* __restrict__ dirs, int* __restrict__ work_counter) {
+  __shared__ float s_hist[ORI_WARPS][ORI_BINS][ORI_QUADS];   // [bin][quad]: one bank per quad and bin mod 4
+  __shared__ uint64_t s_exptab[32];
+  __shared__ int s_pref[SIFT_MAX_IMG + 1];      // first flat index of each image's candidates
+  load_exp2f_tab(s_exptab, threadIdx.x);
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < n_img; ++i) { s_pref[i] = acc; acc += min(cand_count[i], cap); }
+    s_pref[n_img] = acc;
+  }
+  __syncthreads();
+  const unsigned FULL = 0xffffffffu;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, l = lane & 3;
+  const int total_work = s_pref[n_img];
+  float* hist = &s_hist[wid][0][g];             // my keypoint's bin b at hist[b * ORI_QUADS]
+  const float halfipi = (float)(0.5 / PANO_PI);   // 0.5f / M_PI evaluated in double
+  int img = 0;
+  while (true) {
+    int flat = 0;
+    if (lane == 0) flat = atomicAdd(work_counter, ORI_QUADS);
+    flat = __shfl_sync(FULL, flat, 0);
+    if (flat >= total_work) break;
+    flat += g;
+    // ---- per-keypoint constants (identical in the 4 lanes of a quad); rejected candidates get an empty window
+    bool live = flat < total_work;
+    size_t slot = 0;
+    int px = 0, py = 0, w = 0, h = 0, pitch = 0, rad = 0;
+    float exp_denom = 1.f;
+    const float* lvl = arena;
+    if (live) {
+      while (flat >= s_pref[img + 1]) ++img;
+      slot = (size_t)img * cap + (flat - s_pref[img]);
+      if (!valid[slot]) {
+        if (l == 0) npeaks[slot] = 0;
+        live = false;
+      } else {
+        const pano_sspoint p = pts[slot];
+        const OctMeta om = octs[img * n_oct + p.pyr_id];
+        lvl = arena + om.gauss_off + (size_t)p.scale_id * om.plane;
+        px = p.x; py = p.y; w = om.w; h = om.h; pitch = om.pitch;
+        const float gws = p.scale_factor * 1.5f;
+        rad = (int)roundf(p.scale_factor * ori_radius);
+        exp_denom = 2 * (gws * gws);
+      }
+    }
+    const float fr2 = (float)rad * (float)rad;
+    const int side = 2 * rad, total = side * side;
+    for (int b = l; b < ORI_BINS; b += 4) hist[b * ORI_QUADS] = 0.f;
+    __syncwarp();
+    const int total_mx = __reduce_max_sync(FULL, total);
+    int xx = -rad, yy = -rad + l;                 // position base + l as (xx, yy), scan order xx outer
+    if (side > 0) while (yy >= rad) { yy -= side; ++xx; }
+    for (int base = 0; base < total_mx; base += 4) {
+      int bin = -1;
+      float val = 0.f;
+      if (base + l < total) {
+        const int newx = px + xx, newy = py + yy;
+        if (DBETWEEN(newx, 1, w - 1) && DBETWEEN(newy, 1, h - 1)) {
+          const float fx = (float)xx, fy = (float)yy;
+          const float d2 = fx * fx + fy * fy;
+          if (!(d2 > fr2)) {
+            float mag, ort;
+            mag_ort_at(lvl, pitch, newx, newy, &mag, &ort);
+            int b = (int)roundf((float)ORI_BINS * halfipi * ort);
+            if (b == ORI_BINS) b = 0;
+            const float weight = glibc_expf(-d2 / exp_denom, s_exptab);
+            bin = b;
+            val = weight * mag;
+          }
+        }
+        yy += 4;
+        while (yy >= rad) { yy -= side; ++xx; }
+      }
+      // the quad's four positions in scan order
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (l == j && bin >= 0) hist[bin * ORI_QUADS] = hist[bin * ORI_QUADS] + val;
+        __syncwarp();
+      }
+    }
+    if (l == 0 && live) {  // in-place sequential smoothing (orientation.cc:70-75)
+      for (int K = smooth_count; K--;)
+        for (int b = 0; b < ORI_BINS; ++b) {
+          float prev = hist[(b == 0 ? ORI_BINS - 1 : b - 1) * ORI_QUADS];
+          float next = hist[(b == ORI_BINS - 1 ? 0 : b + 1) * ORI_QUADS];
+          hist[b * ORI_QUADS] = (float)((double)hist[b * ORI_QUADS] * 0.5 + (double)(prev + next) * 0.25);
+        }
+    }
+    __syncwarp();
+    if (live) {
+      float mx = 0.f;
+      for (int b = 0; b < ORI_BINS; ++b) if (mx < hist[b * ORI_QUADS]) mx = hist[b * ORI_QUADS];
+      const float thres = mx * 0.8f;
+      // peaks in ascending bin order: lane l owns bins [9 l, 9 l + 9)
+      float my_dir[5];                            // a peak needs two lower neighbours: at most 5 in 9 bins
+      int mine = 0;
+      for (int b = l * 9; b < l * 9 + 9; ++b) {
+        const float hb = hist[b * ORI_QUADS];
+        const float prev = hist[(b == 0 ? ORI_BINS - 1 : b - 1) * ORI_QUADS];
+        const float next = hist[(b == ORI_BINS - 1 ? 0 : b + 1) * ORI_QUADS];
+        if (hb > thres && hb > (prev < next ? next : prev)) {
+          double newbin = (double)(float)b - 0.5 + (double)((hb - prev) / (prev + next - 2 * hb));
+          if (newbin < 0) newbin += ORI_BINS;
+          else if (newbin >= ORI_BINS) newbin -= ORI_BINS;
+          const float dir = (float)(newbin / ORI_BINS * 2 * PANO_PI);
+          if (mine < 5) my_dir[mine] = dir;
+          ++mine;
+        }
+      }
+      // exclusive prefix of the quad's peak counts (live is uniform inside a quad; lanes of dead quads sit out)
+      const unsigned qmask = 0xfu << (g * 4);
+      int before = 0;
+      const int m0 = __shfl_sync(qmask, mine, g * 4 + 0), m1 = __shfl_sync(qmask, mine, g * 4 + 1),
+                m2 = __shfl_sync(qmask, mine, g * 4 + 2), m3 = __shfl_sync(qmask, mine, g * 4 + 3);
+      if (l > 0) before += m0;
+      if (l > 1) before += m1;
+      if (l > 2) before += m2;
+      for (int k = 0; k < mine && k < 5; ++k)
+        if (before + k < SIFT_MAX_PEAKS) dirs[slot * SIFT_MAX_PEAKS + before + k] = my_dir[k];
+      if (l == 0) npeaks[slot] = min(m0 + m1 + m2 + m3, SIFT_MAX_PEAKS);
+    }
+    __syncwarp();
+  }
+}
+
 // ============================================================ K5b expansion scan
 // OrientationAssign::work (orientation.cc:22-32): keypoint order is preserved,
 // peaks ascending.  One block per image: exclusive scan of npeaks.
@@ -730,7 +869,7 @@ struct __align__(16) DescWarpSmem {
 };
 
 __global__ void __launch_bounds__(DESC_THREADS)
-k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
+k_descriptor_v1(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
              const float* __restrict__ arena, int n_oct, int n_img, int cap,
              const pano_sspoint* __restrict__ pts, const int* __restrict__ n_desc,
              const int* __restrict__ desc_cand, const float* __restrict__ desc_dir,
@@ -938,6 +1077,238 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
       }
       __syncwarp();
     }
+  }
+}
+
+// ------------------------------------------------------------ K6, quad design
+// Same contract as k_descriptor_v1 (bit-identical output); what changed and why
+// (profiles/r02x_*: the v1 walk ran 47 instructions per cell visit, and a half-warp-per-
+// keypoint variant with one lane per cell kept only 10 of 32 lanes busy, because a batch of
+// consecutive scan positions is a few window columns and touches 4-6 of the 16 cells):
+//   * FOUR LANES per oriented keypoint, eight keypoints per warp.  Lane (ly, lx) of a quad
+//     owns the four cells whose row parity is ly and column parity is lx.  A sample adds to
+//     the 2x2 block of cells around it — one cell of every parity class — so EVERY record
+//     gives every lane of its quad exactly one visit: the walk is balanced by construction,
+//     needs no per-cell visit lists (no ballots, no masks, no record buffer) and runs right
+//     behind the four records a quad produces per trip.
+//   * the 32 accumulators a lane owns live in shared memory at bank == lane (conflict-free
+//     read-modify-write).  Cells outside the 4x4 grid, rejected positions and idle lanes add
+//     +0.0f, which is an exact no-op on these non-negative sums — the walk has no branches.
+//   * the window is enumerated by COLUMN INTERVALS (desc_interval.h): the accepted yy of a
+//     column form one interval (rotated box ∩ circle ∩ image are convex), so lanes visit only
+//     a ~3 % superset of the accepted positions, in scan order, with no compaction ring; the
+//     reference's exact tests still decide every position.
+// Order of every float sum is the reference's scan order: a quad's records are produced in
+// (xx, yy) order, four per trip, and each lane applies them in that order to bins only it
+// touches.
+#define DQ_COLS 96                       // window columns per interval-table block (wider windows take more blocks)
+
+struct __align__(16) DescQuadSmem {
+  float acc[32 * 32];                    // [bin * 4 + (cy >> 1) * 2 + (cx >> 1)][lane]
+  float r_q[4][32];                      // [record of the trip][reader lane]: weight * wy * wx of the reader's cell (or 0)
+  float2 r_h[4][8];                      // [record of the trip][quad]: {hbin - floor(hbin), packed word}
+  unsigned char col_len[8][DQ_COLS];     // per quad and table column: interval length ...
+  signed char col_y0[8][DQ_COLS];        // ... and first yy
+};
+
+#ifndef DESC_MIN_CTAS
+#define DESC_MIN_CTAS 6                  // resident CTAs per SM the register allocation is held to
+#endif
+__global__ void __launch_bounds__(DESC_THREADS, DESC_MIN_CTAS)
+k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
+             const float* __restrict__ arena, int n_oct, int n_img, int cap,
+             const pano_sspoint* __restrict__ pts, const int* __restrict__ n_desc,
+             const int* __restrict__ desc_cand, const float* __restrict__ desc_dir,
+             DescParams dp, float* __restrict__ out_desc, double* __restrict__ out_coor,
+             int* __restrict__ work_counter) {
+  extern __shared__ __align__(16) unsigned char desc_smem_raw[];
+  __shared__ uint64_t s_exptab[32];
+  __shared__ int s_pref[DESC_MAX_IMG + 1];      // first flat index of each image's descriptors
+  load_exp2f_tab(s_exptab, threadIdx.x);
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int i = 0; i < n_img; ++i) { s_pref[i] = acc; acc += min(n_desc[i], cap); }
+    s_pref[n_img] = acc;
+  }
+  __syncthreads();
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int g = lane >> 2, l = lane & 3;        // quad, lane of the quad = record slot of a trip = cell parity class
+  DescQuadSmem& S = reinterpret_cast<DescQuadSmem*>(desc_smem_raw)[wid];
+  float* const acc = S.acc + lane;              // my 32 accumulators: acc[32 * k]
+  const float pi2 = (float)(2 * PANO_PI);
+  const float nbin_per_rad = 8 / pi2;
+  const float exp_denom = 2 * (4.f * 4.f);
+  const int hi_shift = 4 + 2 * l;               // my 2-bit field of the packed word
+  const int total = s_pref[n_img];
+  int img = 0;
+  while (true) {
+    int flat = 0;
+    if (lane == 0) flat = atomicAdd(work_counter, 8);
+    flat = __shfl_sync(FULL, flat, 0);
+    if (flat >= total) break;
+    flat += g;
+    const bool live = flat < total;               // the last warp-load may have fewer than 8 keypoints
+
+    // ---- per-keypoint constants (identical in the 4 lanes of a quad)
+    int px = 0, py = 0, w = 0, h = 0, pitch = 0, radius = 0, side = 0;
+    float ort = 0.f, hist_w = 1.f, sinort = 0.f, cosort = 1.f;
+    const float* lvl = arena;
+    size_t dslot = 0, pslot = 0;
+    if (live) {
+      while (flat >= s_pref[img + 1]) ++img;      // indices only grow: resume from the last image
+      dslot = (size_t)img * cap + (flat - s_pref[img]);
+      pslot = (size_t)img * cap + desc_cand[dslot];
+      const pano_sspoint p = pts[pslot];
+      ort = desc_dir[dslot];
+      const OctMeta om = octs[img * n_oct + p.pyr_id];
+      lvl = arena + om.gauss_off + (size_t)p.scale_id * om.plane;
+      px = p.x; py = p.y; w = om.w; h = om.h; pitch = om.pitch;
+      hist_w = p.scale_factor * (float)dp.hist_scale_factor;
+      radius = (int)round(PANO_SQRT1_2 * (double)hist_w * (4 + 1));
+      glibc_sincosf(ort, &sinort, &cosort);
+      side = 2 * radius + 1;
+    }
+    const float fr2 = (float)radius * (float)radius;
+    // conservative bounds on the un-normalised rotated coordinates:
+    // bin in [-1,3]  <=>  rot in [-2.5, 1.5] * hist_w (the exact test follows per position)
+    const float lo = -2.5f * hist_w - 0.02f * hist_w - 1e-3f, hi = 1.5f * hist_w + 0.02f * hist_w + 1e-3f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) acc[32 * k] = 0.f;
+
+    const int side_mx = __reduce_max_sync(FULL, side);
+    for (int cb = 0; cb < side_mx; cb += DQ_COLS) {
+      // ---- interval table of window columns [cb, cb + DQ_COLS): 4 columns per trip and quad
+      int nblk = 0;                               // positions of my keypoint in this block
+      const int ncol_mx = min(DQ_COLS, side_mx - cb);
+      for (int c0 = 0; c0 < ncol_mx; c0 += 4) {
+        const int c = c0 + l;                     // table column; window column cb + c
+        int len = 0;
+        if (c < DQ_COLS && cb + c < side) {
+          int y0, y1;
+          desc_col_interval(cb + c - radius, radius, px, py, w, h, sinort, cosort, lo, hi, &y0, &y1);
+          len = max(0, y1 - y0 + 1);
+          S.col_len[g][c] = (unsigned char)len;
+          S.col_y0[g][c] = (signed char)y0;
+        }
+        len += __shfl_xor_sync(FULL, len, 1);
+        len += __shfl_xor_sync(FULL, len, 2);
+        nblk += len;
+      }
+      __syncwarp();
+      const int nblk_mx = __reduce_max_sync(FULL, nblk);
+      int col = 0, cstart = 0, clen = nblk > 0 ? (int)S.col_len[g][0] : 0;   // my position's column, its first index, its length
+
+      for (int base = 0; base < nblk_mx; base += 4) {
+        // ---- one position per lane: the reference's tests and the sample's record
+        const int s = base + l;
+        float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f, hd = 0.f;
+        uint32_t pk = 0;
+        if (s < nblk) {
+          while (s >= cstart + clen) { cstart += clen; ++col; clen = (int)S.col_len[g][col]; }
+          const int xx = cb + col - radius, yy = (int)S.col_y0[g][col] + (s - cstart);
+          const int nowx = px + xx, nowy = py + yy;
+          const float fx = (float)xx, fy = (float)yy;
+          if (DBETWEEN(nowx, 1, w - 1) && DBETWEEN(nowy, 1, h - 1) && !(fx * fx + fy * fy > fr2)) {
+            const float y_rot = ((float)(-xx) * sinort + fy * cosort) / hist_w;
+            const float x_rot = (fx * cosort + fy * sinort) / hist_w;
+            const float ybin = (float)((double)(y_rot + 2.f) - 0.5);
+            const float xbin = (float)((double)(x_rot + 2.f) - 0.5);
+            if (ybin >= -1.f && ybin <= 3.f && xbin >= -1.f && xbin <= 3.f) {
+              float now_mag, now_ort;
+              mag_ort_at(lvl, pitch, nowx, nowy, &now_mag, &now_ort);
+              float weight = glibc_expf(-(x_rot * x_rot + y_rot * y_rot) / exp_denom, s_exptab);
+              weight = weight * now_mag;
+              now_ort -= ort;
+              if (now_ort < 0) now_ort += pi2;
+              if (now_ort > pi2) now_ort -= pi2;
+              const float hbin = now_ort * nbin_per_rad;
+              const int ybinf = (int)floorf(ybin), xbinf = (int)floorf(xbin), hbinf = (int)floorf(hbin);
+              const float yd = ybin - (float)ybinf, xd = xbin - (float)xbinf;
+              hd = hbin - (float)hbinf;
+              // trilinear_interpolate (sift.cc:48-67): w_y = weight * (dy ? yd : 1 - yd), w_x = w_y * (dx ? xd : 1 - xd).
+              // Row parity class 0 / 1 of the 2x2 block: the row with that parity, its factor, or 0 outside the grid.
+              const float wy_lo = weight * (1 - yd), wy_hi = weight * yd;    // rows ybinf, ybinf + 1
+              const float fx_lo = 1 - xd, fx_hi = xd;                        // columns xbinf, xbinf + 1
+              const int yodd = ybinf & 1, xodd = xbinf & 1;                  // parity of the block's first row / column
+              // class p takes the first row when its parity matches, the second otherwise
+              const int cy0 = ybinf + yodd, cy1 = ybinf + 1 - yodd;          // rows of parity 0 and 1
+              const int cx0 = xbinf + xodd, cx1 = xbinf + 1 - xodd;
+              const bool vy0 = (unsigned)cy0 <= 3u, vy1 = (unsigned)cy1 <= 3u;
+              const bool vx0 = (unsigned)cx0 <= 3u, vx1 = (unsigned)cx1 <= 3u;
+              const float wy0 = yodd ? wy_hi : wy_lo, wy1 = yodd ? wy_lo : wy_hi;
+              const float fx0 = xodd ? fx_hi : fx_lo, fx1 = xodd ? fx_lo : fx_hi;
+              q0 = (vy0 && vx0) ? wy0 * fx0 : 0.f;                           // class (ly, lx) = (0, 0)
+              q1 = (vy0 && vx1) ? wy0 * fx1 : 0.f;                           // (0, 1)
+              q2 = (vy1 && vx0) ? wy1 * fx0 : 0.f;                           // (1, 0)
+              q3 = (vy1 && vx1) ? wy1 * fx1 : 0.f;                           // (1, 1)
+              // packed word: hbinf, then per class (cy >> 1) * 2 + (cx >> 1) (0 where the cell is outside: it adds 0)
+              const uint32_t hy0 = vy0 ? (uint32_t)(cy0 >> 1) : 0u, hy1 = vy1 ? (uint32_t)(cy1 >> 1) : 0u;
+              const uint32_t hx0 = vx0 ? (uint32_t)(cx0 >> 1) : 0u, hx1 = vx1 ? (uint32_t)(cx1 >> 1) : 0u;
+              pk = (uint32_t)hbinf | ((hy0 * 2 + hx0) << 4) | ((hy0 * 2 + hx1) << 6) | ((hy1 * 2 + hx0) << 8) | ((hy1 * 2 + hx1) << 10);
+            }
+          }
+        }
+        // record l of my quad: reader lane (g, r) finds its factor at r_q[l][g * 4 + r]
+        *reinterpret_cast<float4*>(&S.r_q[l][g * 4]) = make_float4(q0, q1, q2, q3);
+        S.r_h[l][g] = make_float2(hd, __uint_as_float(pk));
+        __syncwarp();
+        // ---- the walk: the quad's four records in scan order, my cell of each
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float q = S.r_q[j][lane];
+          const float2 hh = S.r_h[j][g];
+          const uint32_t word = __float_as_uint(hh.y);
+          const float v0 = q * (1 - hh.x), v1 = q * hh.x;
+          const uint32_t cell_hi = (word >> hi_shift) & 3u;
+          float* a0 = acc + 32 * ((word & 7u) * 4 + cell_hi);
+          float* a1 = acc + 32 * (((word + 1u) & 7u) * 4 + cell_hi);
+          *a0 = *a0 + v0;
+          *a1 = *a1 + v1;
+        }
+        __syncwarp();
+      }
+    }
+
+    // ---- RootSIFT: L1 normalise (sequential sum in descriptor order = cell-major), sqrt, * DESC_INT_FACTOR
+    __syncwarp();
+    const float* qacc = S.acc + g * 4;            // my quad's accumulators: class r at qacc[32 * k + r]
+    float sum = 0.f;
+    if (l == 0) {
+      for (int c = 0; c < 16; ++c) {
+        const int cy = c >> 2, cx = c & 3;
+        const float* a = qacc + ((cy & 1) * 2 + (cx & 1)) + 32 * ((cy >> 1) * 2 + (cx >> 1));
+#pragma unroll
+        for (int b = 0; b < 8; ++b) sum += a[32 * 4 * b];
+      }
+    }
+    sum = __shfl_sync(FULL, sum, g * 4);
+    if (live) {
+      const float fac = (float)dp.int_factor;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int e = l * 4 + 16 * k;             // descriptor elements e .. e+3: cell e >> 3, bins (e & 7) .. +3
+        const int c = e >> 3, b = e & 7, cy = c >> 2, cx = c & 3;
+        const float* a = qacc + ((cy & 1) * 2 + (cx & 1)) + 32 * ((cy >> 1) * 2 + (cx >> 1));
+        float4 o;
+        o.x = sqrtf(a[32 * 4 * (b + 0)] / sum) * fac;
+        o.y = sqrtf(a[32 * 4 * (b + 1)] / sum) * fac;
+        o.z = sqrtf(a[32 * 4 * (b + 2)] / sum) * fac;
+        o.w = sqrtf(a[32 * 4 * (b + 3)] / sum) * fac;
+        *reinterpret_cast<float4*>(out_desc + dslot * 128 + e) = o;
+      }
+      if (l == 0) {
+        const pano_sspoint p = pts[pslot];
+        const ImgMeta im = imgs[img];
+        out_coor[dslot * 2] = (p.real_x - 0.5) * im.in_w;
+        out_coor[dslot * 2 + 1] = (p.real_y - 0.5) * im.in_h;
+        // second half of the coordinate buffer: SSPoint::real_coor, what do_detect_feature returns (sift.cc:150)
+        double* out_real = out_coor + (size_t)n_img * cap * 2;
+        out_real[dslot * 2] = p.real_x;
+        out_real[dslot * 2 + 1] = p.real_y;
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -1172,17 +1543,34 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     dim3 g4(16, n);
     SIFT_LAUNCH("k_refine", k_refine, g4, 128, 0, wk->d_oct, wk->arena, n_oct, wk->cand_count, wk->sorted_keys, rp, cap,
                 wk->refined, wk->kp_valid);
-    SIFT_LAUNCH("k_orientation", k_orientation, ctx->num_sms * 8, ORI_WARPS * 32, 0, wk->d_oct, wk->arena, n_oct, n, cap,
-                wk->cand_count, wk->refined, wk->kp_valid, p->ori_radius, p->ori_hist_smooth_count, wk->npeaks, wk->dirs,
-                wk->cand_count + n + 1);
+    // PANO_ORI_V1=1: the first design (staged replay), kept as an in-engine cross-check
+    static const bool ori_v1 = getenv("PANO_ORI_V1") && atoi(getenv("PANO_ORI_V1")) != 0;
+    if (ori_v1)
+      SIFT_LAUNCH("k_orientation", k_orientation_v1, ctx->num_sms * 8, ORI_WARPS * 32, 0, wk->d_oct, wk->arena, n_oct, n, cap,
+                  wk->cand_count, wk->refined, wk->kp_valid, p->ori_radius, p->ori_hist_smooth_count, wk->npeaks, wk->dirs,
+                  wk->cand_count + n + 1);
+    else
+      SIFT_LAUNCH("k_orientation", k_orientation, ctx->num_sms * 8, ORI_WARPS * 32, 0, wk->d_oct, wk->arena, n_oct, n, cap,
+                  wk->cand_count, wk->refined, wk->kp_valid, p->ori_radius, p->ori_hist_smooth_count, wk->npeaks, wk->dirs,
+                  wk->cand_count + n + 1);
     SIFT_LAUNCH("k_expand_scan", k_expand_scan, n, SCAN_THREADS, 0, wk->cand_count, wk->kp_valid, wk->npeaks,
                 wk->dirs, cap, fs->d_count, wk->n_refined, wk->desc_cand, wk->desc_dir);
     DescParams dp{p->desc_hist_scale_factor, p->desc_int_factor};
-    const size_t dsm = sizeof(DescWarpSmem) * DESC_WARPS;
-    SIFT_CUDA(cudaFuncSetAttribute(k_descriptor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+    // PANO_DESC_V1=1: the first design (warp per keypoint, full-window scan), kept as an in-engine cross-check
+    static const bool desc_v1 = getenv("PANO_DESC_V1") && atoi(getenv("PANO_DESC_V1")) != 0;
     int grid = ctx->num_sms * DESC_CTAS_PER_SM;
-    SIFT_LAUNCH("k_descriptor", k_descriptor, grid, DESC_THREADS, dsm, wk->d_oct, wk->d_img, wk->arena, n_oct, n, cap,
-                wk->refined, fs->d_count, wk->desc_cand, wk->desc_dir, dp, fs->d_desc, fs->d_coor, wk->cand_count + n);
+    if (desc_v1) {
+      const size_t dsm = sizeof(DescWarpSmem) * DESC_WARPS;
+      SIFT_CUDA(cudaFuncSetAttribute(k_descriptor_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      SIFT_LAUNCH("k_descriptor", k_descriptor_v1, grid, DESC_THREADS, dsm, wk->d_oct, wk->d_img, wk->arena, n_oct, n, cap,
+                  wk->refined, fs->d_count, wk->desc_cand, wk->desc_dir, dp, fs->d_desc, fs->d_coor, wk->cand_count + n);
+    } else {
+      const size_t dsm = sizeof(DescQuadSmem) * DESC_WARPS;
+      SIFT_CUDA(cudaFuncSetAttribute(k_descriptor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      grid = ctx->num_sms * DESC_MIN_CTAS;
+      SIFT_LAUNCH("k_descriptor", k_descriptor, grid, DESC_THREADS, dsm, wk->d_oct, wk->d_img, wk->arena, n_oct, n, cap,
+                  wk->refined, fs->d_count, wk->desc_cand, wk->desc_dir, dp, fs->d_desc, fs->d_coor, wk->cand_count + n);
+    }
   }
   wk->n_desc = fs->d_count;
 
