@@ -246,6 +246,34 @@ typedef struct pano_ransac_pair {
 int pano_ransac_score_pairs(pano_ctx* ctx, int n_pairs, const pano_ransac_pair* pairs, int* best_hyp,
                             int* best_count, int* const* hyp_counts, unsigned char* const* inlier_flags);
 
+/* ------------------------------------- bundle-adjustment Jacobian assembly
+ * Replaces the per-point part of IncrementalBundleAdjuster::calcJacobianSymbolic
+ * (stitch/incremental_bundle_adjuster.cc:306-383): the two rows of J of every point match
+ * (:355-361) and the sums of J^T J (:363-382), bit-identical to the reference's loops.
+ * The per-pair 3x3 algebra in front of them (:288-304 and the loop-invariant products inside
+ * the loop) is Eigen-backed in the reference (Homography::operator*, inverse,
+ * Camera::rotation_to_angle) and stays with the caller, who hands in per pair:
+ *   m[0]      Hto_to_from = (fromK * c_from.R) * (toRinv * toKinv)            (:304)
+ *   m[1]      c_from.R * toRinv * toKinv                                       (:323)
+ *   m[2]      toRinv * toKinv                                                  (:332)
+ *   m[3..5]   fromK * dRfromdvi[k]                                             (:333-335)
+ *   m[6]      toKinv                                                           (:339,349)
+ *   m[7..9]   m * dKdfocal, m * dKdppx, m * dKdppy,  m = fromK * c_from.R * toRinv * toKinv  (:338-345)
+ *   m[10..12] (fromK * c_from.R) * dRtodviT[k]                                 (:348-352)
+ * row-major Homography::data each. */
+typedef struct pano_ba_pair {
+  int from, to;         /* camera slots: index_map[pair.from], index_map[pair.to] */
+  int match_begin;      /* match_cnt_prefix_sum[pair_idx]: pairs are consecutive, the first starts at 0 */
+  int n_match;          /* pair.m.match.size() */
+  double m[13][9];
+} pano_ba_pair;
+/* pts_to: p.first of every match (2 doubles each), all pairs concatenated.
+ * j_rows (optional, 24 doubles per match): J(idx, param_idx_from + 0..5), J(idx, param_idx_to + 0..5),
+ *   then the same 12 entries of row idx + 1 — every other entry of those rows is zero.
+ * jtj: (6 n_cam)^2 doubles, row-major, fully written (JtJ.setZero() + the sums). */
+int pano_ba_jacobian(pano_ctx* ctx, int n_cam, int n_pair, const pano_ba_pair* pairs, const double* pts_to,
+                     double* j_rows, double* jtj);
+
 /* ---------------------------------------------------------- cylinder warp
  * Replaces CylinderWarper(h_factor).warp(Mat32f&, vector<Vec2D>&)
  * (stitch/warp.hh:41-66, warp.cc:25-75). */

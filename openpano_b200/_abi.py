@@ -95,4 +95,12 @@ class PanoRansacPair(C.Structure):
     ]
 
 
+class PanoBaPair(C.Structure):
+    _fields_ = [
+        ("from_", C.c_int), ("to", C.c_int),
+        ("match_begin", C.c_int), ("n_match", C.c_int),
+        ("m", C.c_double * 9 * 13),
+    ]
+
+
 PROJ_FLAT, PROJ_CYLINDRICAL, PROJ_SPHERICAL = 0, 1, 2

@@ -11,7 +11,7 @@ from pathlib import Path
 
 import numpy as np
 
-from ._abi import (PanoBlendGeom, PanoBlendImage, PanoMatches, PanoParams, PanoRansacPair, PanoSSPoint,
+from ._abi import (PanoBaPair, PanoBlendGeom, PanoBlendImage, PanoMatches, PanoParams, PanoRansacPair, PanoSSPoint,
                    default_params)
 
 LIB_PATH = Path(__file__).resolve().parent / "libpano_b200.so"
@@ -78,6 +78,7 @@ def _load():
         "pano_comm_allgather_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, _vpp]),
         "pano_comm_allgather_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
         "pano_ransac_score_pairs": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PanoRansacPair), _ip, _ip, _vpp, _vpp]),
+        "pano_ba_jacobian": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(PanoBaPair), _dp, _dp, _dp]),
         "pano_cyl_warp_shape": (C.c_int, [C.c_int, C.c_int, C.c_double, P, _ip, _ip, _dp, _dp]),
         "pano_cyl_warp": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, C.c_double, P, _fp, C.c_int,
                                     C.c_int, _dp, C.c_int]),
@@ -485,6 +486,24 @@ class Engine:
         fp = (C.c_void_p * max(n, 1))(*[f.ctypes.data for f in flags])
         self._check(LIB.pano_ransac_score_pairs(self._h, n, arr, _i(best), _i(bcnt), cp, fp))
         return [(int(best[k]), int(bcnt[k]), counts[k][:len(keep[k][2])], flags[k][:len(keep[k][0])]) for k in range(n)]
+
+    # -- bundle-adjustment Jacobian assembly
+    def ba_jacobian(self, n_cam, pairs, pts_to, want_rows=True):
+        """pairs: list of (from_slot, to_slot, n_match, mats [13, 9] f64) in match order; pts_to: [n_match_total, 2].
+        Returns (j_rows [n_match_total, 24] or None, jtj [6 n_cam, 6 n_cam])."""
+        n = len(pairs)
+        arr = (PanoBaPair * max(n, 1))()
+        begin = 0
+        for k, (f, t, nm, mats) in enumerate(pairs):
+            arr[k].from_, arr[k].to, arr[k].match_begin, arr[k].n_match = f, t, begin, nm
+            C.memmove(arr[k].m, np.ascontiguousarray(mats, np.float64).ctypes.data, 13 * 9 * 8)
+            begin += nm
+        pts_to = np.ascontiguousarray(pts_to, np.float64).reshape(-1, 2)
+        assert len(pts_to) == begin
+        rows = np.zeros((max(begin, 1), 24), np.float64) if want_rows else None
+        jtj = np.full((6 * n_cam, 6 * n_cam), np.nan, np.float64)
+        self._check(LIB.pano_ba_jacobian(self._h, n_cam, n, arr, _d(pts_to), _d(rows) if want_rows else None, _d(jtj)))
+        return (rows[:begin] if want_rows else None), jtj
 
     # -- cylinder warp
     @staticmethod

@@ -75,6 +75,24 @@ extern "C" {
 ORACLE_DECLARE(orc)
 ORACLE_DECLARE(ref)
 
+/* ---- bundle-adjustment Jacobian (stitch/incremental_bundle_adjuster.cc:276-385).
+ * The restatement works from the 13 per-pair matrices the CUDA entry point takes (same layout as
+ * pano_ba_pair, include/pano_b200.h); the reference build works from cameras through the reference's
+ * own calcJacobianSymbolic and also evaluates the per-pair matrices with the reference's own
+ * Homography / Camera operations. */
+typedef struct orc_ba_pair {
+  int from, to, match_begin, n_match;
+  double m[13][9];
+} orc_ba_pair;
+int orc_ba_jacobian(int n_cam, int n_pair, const orc_ba_pair* pairs, const double* pts_to,
+                    double* j_rows /* 24 per match, may be NULL */, double* jtj /* (6 n_cam)^2 */);
+/* cams: 12 doubles per camera {focal, ppx, ppy, R[9]}; pairs: from/to camera slots and match ranges
+ * (m is written by ref_ba_pair_mats, ignored by ref_ba_jacobian); pts: 4 doubles per match
+ * {to.x, to.y, from.x, from.y}. */
+int ref_ba_pair_mats(int n_cam, const double* cams, int n_pair, orc_ba_pair* pairs);
+int ref_ba_jacobian(int n_cam, const double* cams, int n_pair, const orc_ba_pair* pairs, const double* pts,
+                    double* j_rows, double* jtj);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,7 +9,7 @@ from pathlib import Path
 
 import numpy as np
 
-from openpano_b200._abi import (PanoBlendGeom, PanoBlendImage, PanoParams, PanoSSPoint,
+from openpano_b200._abi import (PanoBaPair, PanoBlendGeom, PanoBlendImage, PanoParams, PanoSSPoint,
                                 default_params)
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -204,6 +204,54 @@ class Checker:
 
     def num_threads(self):
         return self._fn("num_threads")()
+
+    # ---- bundle-adjustment Jacobian (incremental_bundle_adjuster.cc:276-385)
+    @staticmethod
+    def _ba_pairs(pairs, mats=None):
+        arr = (PanoBaPair * max(len(pairs), 1))()
+        begin = 0
+        for k, (f, t, nm) in enumerate(pairs):
+            arr[k].from_, arr[k].to, arr[k].match_begin, arr[k].n_match = f, t, begin, nm
+            if mats is not None:
+                C.memmove(arr[k].m, np.ascontiguousarray(mats[k], np.float64).ctypes.data, 13 * 9 * 8)
+            begin += nm
+        return arr, begin
+
+    def ba_pair_mats(self, cams, pairs):
+        """ref_ only: the 13 per-pair matrices, evaluated with the reference's own Homography / Camera
+        operations.  cams [n, 12] = focal, ppx, ppy, R; pairs = [(from, to, n_match)].  -> [n_pair, 13, 9]."""
+        cams = np.ascontiguousarray(cams, np.float64).reshape(-1, 12)
+        arr, _ = self._ba_pairs(pairs)
+        fn = self.lib.ref_ba_pair_mats
+        fn.argtypes = [C.c_int, _dp, C.c_int, C.POINTER(PanoBaPair)]
+        assert fn(len(cams), _d(cams), len(pairs), arr) == 0
+        return np.array([np.ctypeslib.as_array(arr[k].m).reshape(13, 9).copy() for k in range(len(pairs))])
+
+    def ba_jacobian_ref(self, cams, pairs, pts):
+        """ref_ only: the reference's own calcJacobianSymbolic.  pts [n_match, 4] = to.x, to.y, from.x, from.y.
+        -> (j_rows [n_match, 24], jtj [6n, 6n])."""
+        cams = np.ascontiguousarray(cams, np.float64).reshape(-1, 12)
+        pts = np.ascontiguousarray(pts, np.float64).reshape(-1, 4)
+        arr, total = self._ba_pairs(pairs)
+        assert total == len(pts)
+        rows = np.zeros((max(total, 1), 24), np.float64)
+        jtj = np.full((6 * len(cams), 6 * len(cams)), np.nan, np.float64)
+        fn = self.lib.ref_ba_jacobian
+        fn.argtypes = [C.c_int, _dp, C.c_int, C.POINTER(PanoBaPair), _dp, _dp, _dp]
+        assert fn(len(cams), _d(cams), len(pairs), arr, _d(pts), _d(rows), _d(jtj)) == 0
+        return rows[:total], jtj
+
+    def ba_jacobian(self, n_cam, pairs, mats, pts_to):
+        """orc_ only: the restatement, from the per-pair matrices.  -> (j_rows, jtj)."""
+        pts_to = np.ascontiguousarray(pts_to, np.float64).reshape(-1, 2)
+        arr, total = self._ba_pairs(pairs, mats)
+        assert total == len(pts_to)
+        rows = np.zeros((max(total, 1), 24), np.float64)
+        jtj = np.full((6 * n_cam, 6 * n_cam), np.nan, np.float64)
+        fn = self.lib.orc_ba_jacobian
+        fn.argtypes = [C.c_int, C.c_int, C.POINTER(PanoBaPair), _dp, _dp, _dp]
+        assert fn(n_cam, len(pairs), arr, _d(pts_to), _d(rows), _d(jtj)) == 0
+        return rows[:total], jtj
 
     def sift_trace(self, img, params=None) -> SiftTrace:
         params = params or default_params()

@@ -49,13 +49,29 @@ def imgio(ref):
     print("imgio: crop", rect, cropped.shape)
 
 
+def ba(ref):
+    """The reference's own calcJacobianSymbolic (incremental_bundle_adjuster.cc:276-385) and the per-pair
+    matrices, evaluated by the reference's own Homography / Camera operations (oracle/refshim/ref_ba.cc)."""
+    from tests.ba_util import ba_case
+    cams, pairs, pts = ba_case(5, 40, 5, extra_pairs=3)
+    mats = ref.ba_pair_mats(cams, pairs)
+    rows, jtj = ref.ba_jacobian_ref(cams, pairs, pts)
+    np.savez_compressed(OUT / "ba_5cams.npz", input_sha=np.array(sha(cams, np.array(pairs), pts)),
+                        mats=mats, rows=rows, jtj=jtj)
+    print("ba:", len(pairs), "pairs,", len(pts), "matches")
+
+
 def main():
     ref = get_checker("ref")
     assert ref.num_threads() == 1
     if sys.argv[1:] == ["imgio"]:      # add this fixture without rewriting the others
         imgio(ref)
         return
+    if sys.argv[1:] == ["ba"]:
+        ba(ref)
+        return
     imgio(ref)
+    ba(ref)
 
     # ---- SIFT chain on one 240x180 view
     img = synth.make_canvas(180, 240, 101)

@@ -69,3 +69,13 @@ def test_oracle_imgio_matches_golden(orc):
     assert gu.same_bits(cropped, mos[y0:y0 + ch, x0:x0 + cw])
     assert gu.same_bits(orc.write_rgb8(mos), g["write_full"])
     assert gu.same_bits(orc.write_rgb8(cropped), g["write_cropped"])
+
+
+def test_oracle_ba_jacobian_matches_golden(orc):
+    """J rows and J^T J of the reference's calcJacobianSymbolic (fixture made by its own TU)."""
+    from tests.ba_util import ba_case
+    g = gu.load("ba_5cams.npz")
+    cams, pairs, pts = ba_case(5, 40, 5, extra_pairs=3)
+    assert gu.sha(cams, np.array(pairs), pts) == str(g["input_sha"])
+    rows, jtj = orc.ba_jacobian(5, pairs, g["mats"], pts[:, :2])
+    assert gu.same_bits(rows, g["rows"]) and gu.same_bits(jtj, g["jtj"])

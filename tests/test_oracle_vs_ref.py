@@ -218,3 +218,18 @@ def test_ransac_scoring(orc, ref, n_match, n_hyp, seed):
     assert a[0] == b[0] and a[1] == b[1]
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
     assert a[1] > 0.5 * n_match
+
+
+@pytest.mark.parametrize("n_cam,per_pair,seed,extra", [(4, 50, 1, 2), (8, 300, 2, 6), (3, 1, 3, 0), (16, 1000, 4, 30)])
+def test_ba_jacobian(orc, ref, n_cam, per_pair, seed, extra):
+    """IncrementalBundleAdjuster::calcJacobianSymbolic itself (the reference TU, compiled where it lies
+    by oracle/refshim/ref_ba.cc) against the restatement: every J row and every J^T J entry, bit for bit —
+    including reversed pairs, repeated camera pairs and the identity camera's small-angle branch."""
+    from tests.ba_util import ba_case
+    cams, pairs, pts = ba_case(n_cam, per_pair, seed, extra_pairs=extra)
+    mats = ref.ba_pair_mats(cams, pairs)
+    r_rows, r_jtj = ref.ba_jacobian_ref(cams, pairs, pts)
+    o_rows, o_jtj = orc.ba_jacobian(n_cam, pairs, mats, pts[:, :2])
+    assert gu.same_bits(r_rows, o_rows)
+    assert gu.same_bits(r_jtj, o_jtj)
+    assert np.isfinite(r_rows).all() and (r_jtj != 0).any()
