@@ -92,7 +92,7 @@ void pano_destroy(pano_ctx* ctx);
 /* Device memory: every buffer a ctx needs comes stream-ordered from its own pool, and freed blocks
  * are kept by the ctx for the next request of about the same size (a stitch job asks for the same
  * sizes every time; re-arranging the pool for a 0.9 GB arena was seen to block the host for up to
- * 1.5 s).  The environment variable PANO_CACHE_MB bounds what a ctx keeps (default 8192, 0 = keep
+ * 1.5 s).  The environment variable PANO_CACHE_MB bounds what a ctx keeps (default 32768, 0 = keep
  * nothing); pano_trim hands everything it keeps back to the pool, e.g. before a long idle period. */
 int  pano_trim(pano_ctx* ctx);
 /* Message of the last failure on this ctx ("" if none).  ctx may be NULL for

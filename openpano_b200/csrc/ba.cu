@@ -122,13 +122,13 @@ extern "C" int pano_ba_jacobian(pano_ctx* ctx, int n_cam, int n_pair, const pano
     max_match = std::max(max_match, p.n_match);
   }
   const size_t N = (size_t)n_cam * 6;
-  const size_t b_pairs = (size_t)n_pair * sizeof(BaPairDev), b_pts = (size_t)nm * 16;
+  const size_t b_pairs = align_up((size_t)n_pair * sizeof(BaPairDev), 16), b_pts = (size_t)nm * 16;   // double2 loads behind the pair table
   const size_t b_rows = (size_t)nm * 24 * sizeof(double), b_jtj = N * N * sizeof(double);
   PANO_CUDA(ctx, cudaStreamSynchronize(ctx->stream));            // the staging buffers may still feed earlier copies
   char* st = (char*)ctx_pinned(ctx, b_pairs + b_pts + 64);
   char* so = (char*)ctx_pinned2(ctx, (j_rows ? b_rows : 0) + b_jtj + 64);
   if (!st || !so) return ctx_fail(ctx, PANO_ERR_CUDA, "ba: pinned staging allocation failed");
-  if (b_pairs) memcpy(st, pairs, b_pairs);
+  if (n_pair) memcpy(st, pairs, (size_t)n_pair * sizeof(BaPairDev));
   if (b_pts) memcpy(st + b_pairs, pts_to, b_pts);
   char* d_in = nullptr; char* d_out = nullptr;
   int rc = ctx_alloc(ctx, (void**)&d_in, b_pairs + b_pts + 64);

@@ -35,7 +35,7 @@ struct pano_ctx {
   struct CachedBlock { void* p; unsigned long long stamp; };
   std::multimap<size_t, CachedBlock> cache;        // size -> free block
   std::unordered_map<void*, size_t> live;           // blocks handed out -> their true size
-  size_t cached_bytes = 0, cache_limit = (size_t)8 << 30;
+  size_t cached_bytes = 0, cache_limit = (size_t)32 << 30;   // one 64-view multiband job parks ~8 GB; the GPU has 180
   unsigned long long cache_stamp = 0;
   std::string err;
   bool profiling = false;
