@@ -236,6 +236,9 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------- our arm
+SHARDED_TIMEOUT_S = 420          # watchdog of the N > 1 sharded legs (collectives: one failed rank would hang the rest)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -562,7 +565,62 @@ def main():
                     eng, "uav_64x4000x3000, MULTIBAND 5, LAZY_READ 0, MAX_OUTPUT_SIZE 8000", "uav_64x4000x3000",
                     lambda n: [(i, i + 1) for i in range(n - 1)], 5, _dp(multiband=5, lazy_read=0), steps=3,
                     max_output=8000, cpu_views=16, cpu_loader=loader, all_cpus=all_cpus))
+
+        def build_line(sharded):
+            return {
+                "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_dict(imgs, pairs, args.bands, world),
+                "notes": {"cpu_affinity_cpus": numa_cpus,
+                          "l2_policy": "inputs_exceed_l2 (260 MB of images + 0.9 GB pyramid arena per step)",
+                          "features": int(sum(counts)), "matches": int(n_matches),
+                          "match_rows_rescanned_exactly": int(exact_rows)},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                        "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_per_step * 1e3,
+                        "mode": f"StitchLanes: {args.lanes} concurrent pipelined jobs per GPU (one host thread each); every job "
+                                "uploads its own images and downloads its own mosaic + match lists",
+                        "one_lane": {"value": world * mpx / one_lane_per_step, "ms_per_step": one_lane_per_step * 1e3},
+                        "reported": f"median of {E2E_TRIALS} trials of {args.steps} jobs each (trials interleaved across legs)",
+                        "trials_ms_per_step": e2e_trials,
+                        "best_trial_ms_per_step": min(e2e_trials["lanes"]),
+                        "boundary": "rgb8: decoded 8-bit pixels in (read_img's input), crop()+write_rgb 8-bit mosaic out; "
+                                    "u8<->f32 conversions and crop run on the device inside the timed region",
+                        "mat32f_boundary": {"value": world * mpx / f32_per_step, "ms_per_step": f32_per_step * 1e3,
+                                            "h2d_bytes_per_step": int(f32_h2d), "d2h_bytes_per_step": int(f32_d2h)},
+                        "single_job_latency_ms_mat32f": e2e_latency * 1e3,
+                        "single_job_value_mat32f": world * mpx / e2e_latency,
+                        # the same figures as flat scalars (nested objects get dropped by some JSON consumers)
+                        "one_lane_ms_per_step": one_lane_per_step * 1e3, "one_lane_value": world * mpx / one_lane_per_step,
+                        "mat32f_ms_per_step": f32_per_step * 1e3, "mat32f_value": world * mpx / f32_per_step,
+                        "mat32f_h2d_bytes_per_step": int(f32_h2d), "mat32f_d2h_bytes_per_step": int(f32_d2h),
+                        "single_job_ms": e2e_latency * 1e3, "single_job_value": world * mpx / e2e_latency,
+                        "lanes_trials_ms": e2e_trials["lanes"], "lanes_worst_trial_ms": max(e2e_trials["lanes"]),
+                        # a slow trial is ONE long pause between two job completions (a descheduled host thread /
+                        # another tenant's PCIe burst on the shared box), not a uniformly slower pipeline:
+                        "longest_pause_between_jobs_ms": e2e_gaps},
+                "gpu_launches": int(launches * world),
+                "roofline": roof,
+                "cpu_baseline": cpu,
+                "kernels": kernels,
+                "configs": configs,
+                "sharded": sharded,
+            }
+
         if world > 1:
+            # The sharded legs are collectives over all ranks: if one rank fails inside them the others would
+            # wait for ever.  A watchdog prints the line without them (rank 0) and leaves, so the headline survives.
+            import threading
+
+            def _bail():
+                if rank == 0:
+                    print(json.dumps(build_line({"error": f"sharded legs did not finish within {SHARDED_TIMEOUT_S} s"})),
+                          file=RESULT_OUT, flush=True)
+                os._exit(0)
+            dog = threading.Timer(SHARDED_TIMEOUT_S, _bail)
+            dog.daemon = True
+            dog.start()
             from openpano_b200._abi import default_params as _dp
             from tools import bench_configs as bc
             try:
@@ -573,53 +631,15 @@ def main():
                 sweep = bc.run_sharded_sweep(eng, rank, world, _dp())
             except Exception as ex:
                 sweep = {"error": repr(ex)}
+            dog.cancel()
             if rank == 0 and isinstance(sharded, dict):
                 sharded["match_sweep_100k_row_sharded"] = sweep
 
+        line = build_line(sharded) if rank == 0 else None
         st.close()
         eng.close()
 
     if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(imgs, pairs, args.bands, world),
-            "notes": {"cpu_affinity_cpus": numa_cpus,
-                      "l2_policy": "inputs_exceed_l2 (260 MB of images + 0.9 GB pyramid arena per step)",
-                      "features": int(sum(counts)), "matches": int(n_matches),
-                      "match_rows_rescanned_exactly": int(exact_rows)},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                    "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_per_step * 1e3,
-                    "mode": f"StitchLanes: {args.lanes} concurrent pipelined jobs per GPU (one host thread each); every job "
-                            "uploads its own images and downloads its own mosaic + match lists",
-                    "one_lane": {"value": world * mpx / one_lane_per_step, "ms_per_step": one_lane_per_step * 1e3},
-                    "reported": f"median of {E2E_TRIALS} trials of {args.steps} jobs each (trials interleaved across legs)",
-                    "trials_ms_per_step": e2e_trials,
-                    "best_trial_ms_per_step": min(e2e_trials["lanes"]),
-                    "boundary": "rgb8: decoded 8-bit pixels in (read_img's input), crop()+write_rgb 8-bit mosaic out; "
-                                "u8<->f32 conversions and crop run on the device inside the timed region",
-                    "mat32f_boundary": {"value": world * mpx / f32_per_step, "ms_per_step": f32_per_step * 1e3,
-                                        "h2d_bytes_per_step": int(f32_h2d), "d2h_bytes_per_step": int(f32_d2h)},
-                    "single_job_latency_ms_mat32f": e2e_latency * 1e3,
-                    "single_job_value_mat32f": world * mpx / e2e_latency,
-                    # the same figures as flat scalars (nested objects get dropped by some JSON consumers)
-                    "one_lane_ms_per_step": one_lane_per_step * 1e3, "one_lane_value": world * mpx / one_lane_per_step,
-                    "mat32f_ms_per_step": f32_per_step * 1e3, "mat32f_value": world * mpx / f32_per_step,
-                    "mat32f_h2d_bytes_per_step": int(f32_h2d), "mat32f_d2h_bytes_per_step": int(f32_d2h),
-                    "single_job_ms": e2e_latency * 1e3, "single_job_value": world * mpx / e2e_latency,
-                    "lanes_trials_ms": e2e_trials["lanes"], "lanes_worst_trial_ms": max(e2e_trials["lanes"]),
-                    # a slow trial is ONE long pause between two job completions (a descheduled host thread /
-                    # another tenant's PCIe burst on the shared box), not a uniformly slower pipeline:
-                    "longest_pause_between_jobs_ms": e2e_gaps},
-            "gpu_launches": int(launches * world),
-            "roofline": roof,
-            "cpu_baseline": cpu,
-            "kernels": kernels,
-            "configs": configs,
-            "sharded": sharded,
-        }
         print(json.dumps(line), file=RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
