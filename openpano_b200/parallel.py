@@ -183,6 +183,16 @@ class DistributedStitcher:
         self.ms = {}
         self.host_ms = {}         # host wall time spent inside each phase's calls (launch / sync overhead)
         self._side = None
+        self._stage = {}
+
+    def _pinned(self, key, n):
+        """A pinned int32 staging buffer of at least n elements, kept across jobs (cudaHostAlloc is slow)."""
+        import torch
+        buf = self._stage.get(key)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 1 << 16), dtype=torch.int32).pin_memory()
+            self._stage[key] = buf
+        return buf
 
     def _timed(self, name, fn):
         import time
@@ -295,33 +305,44 @@ class DistributedStitcher:
         tasks = dealt[rank]
         results = self._timed("match", lambda: eng.match_pairs(fs_all, [pairs[t] for t in tasks], params) if tasks else [])
 
-        # ---- match lists to rank 0: ONE fixed-size all-gather.  A pair yields at most min(N_i, N_j)
-        # matches and every rank knows the counts after C1, so the slot sizes need no extra round trip:
-        # rank r sends [number of matches per dealt task ..., (i, j) ...] padded to the largest bound.
+        # ---- match lists to rank 0: the largest per-rank total (one scalar all-reduce), then ONE all-gather of
+        # [number of matches per dealt task ..., (i, j) ...] padded to it, through pinned staging both ways.
+        # (Padding to the a-priori bound min(N_i, N_j) per pair needs no scalar round trip but moved 14 MB at
+        # 4 ranks where the lists are 1 MB: 2.5 of 6.7 ms, profiles/r02ab_rundist_u38.json.)
         def gather_lists():
-            bound = [sum(min(counts[pairs[t][0]], counts[pairs[t][1]]) for t in dealt[r]) for r in range(world)]
             ntask = max(max(len(d) for d in dealt), 1)
-            pad = ntask + 2 * max(max(bound), 1)
-            host = np.zeros(pad, np.int32)
+            tot = sum(len(m) for m in results) if tasks else 0
+            t = torch.tensor([tot], dtype=torch.int32, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pad = ntask + 2 * max(int(t.item()), 1)
+            stage = self._pinned("send", pad)
+            host = stage.numpy()
+            host[:pad] = 0
             if tasks:
                 host[:len(tasks)] = [len(m) for m in results]
-                flat = [m.reshape(-1) for m in results if len(m)]
-                if flat:
-                    cat = np.concatenate(flat).astype(np.int32)
-                    host[ntask:ntask + len(cat)] = cat
-            my = torch.from_numpy(host).to(dev, non_blocking=False)
+                off = ntask
+                for m in results:
+                    if len(m):
+                        host[off:off + 2 * len(m)] = m.reshape(-1)
+                        off += 2 * len(m)
+            my = torch.empty(pad, dtype=torch.int32, device=dev)
+            my.copy_(stage[:pad], non_blocking=True)
             allm = torch.empty(world * pad, dtype=torch.int32, device=dev)
             dist.all_gather_into_tensor(allm, my)
             if rank != 0:
+                torch.cuda.current_stream().synchronize()      # the staging buffer is reused by the next job
                 return None
-            got = allm.cpu().numpy()
+            back = self._pinned("recv", world * pad)
+            back[:world * pad].copy_(allm, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            got = back.numpy()
             full = [None] * len(pairs)
             for r in range(world):
                 seg = got[r * pad:(r + 1) * pad]
                 off = ntask
-                for q, t in enumerate(dealt[r]):
+                for q, t_ in enumerate(dealt[r]):
                     c = int(seg[q])
-                    full[t] = seg[off:off + 2 * c].reshape(-1, 2)
+                    full[t_] = seg[off:off + 2 * c].reshape(-1, 2).copy()
                     off += 2 * c
             return full
         matches = self._timed("gather_matches", gather_lists)

@@ -85,6 +85,20 @@ def test_sift_other_params(engine, orc):
     g.close(); o.close()
 
 
+@pytest.mark.parametrize("hist_scale,ori_radius", [(8, 4.5), (17, 9.0)])
+def test_sift_wide_descriptor_windows(engine, orc, hist_scale, ori_radius):
+    """Descriptor windows wider than one interval-table block of k_descriptor (96 columns: DESC_HIST_SCALE_FACTOR 8
+    gives windows of up to ~110 columns, 17 of up to ~215, close to the 255 the kernel's tables hold) and wide
+    orientation windows."""
+    img = synth.make_canvas(360, 480, 41)
+    p = default_params(desc_hist_scale_factor=hist_scale, ori_radius=ori_radius)
+    c, d = engine.sift_detect(img, p)
+    co, do = orc.sift_detect(img, p)
+    assert len(do) > 300
+    assert_same("coor", c, co)
+    assert_same("desc", d, do)
+
+
 def test_sift_flat_image_has_no_features(engine, orc):
     img = np.full((200, 300, 3), 0.5, np.float32)
     c, d = engine.sift_detect(img)
