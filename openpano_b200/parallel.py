@@ -305,26 +305,36 @@ class DistributedStitcher:
         tasks = dealt[rank]
         results = self._timed("match", lambda: eng.match_pairs(fs_all, [pairs[t] for t in tasks], params) if tasks else [])
 
-        # ---- match lists to rank 0: the largest per-rank total (one scalar all-reduce), then ONE all-gather of
-        # [number of matches per dealt task ..., (i, j) ...] padded to it, through pinned staging both ways.
-        # (Padding to the a-priori bound min(N_i, N_j) per pair needs no scalar round trip but moved 14 MB at
-        # 4 ranks where the lists are 1 MB: 2.5 of 6.7 ms, profiles/r02ab_rundist_u38.json.)
+        # ---- match lists to rank 0, part 1: the largest per-rank total (one scalar all-reduce, read back through
+        # pinned memory behind an event so that waiting for it does not wait for the blend queued after it)
+        ntask = max(max(len(d) for d in dealt), 1)
+        tot = sum(len(m) for m in results) if tasks else 0
+        t_max = torch.tensor([tot], dtype=torch.int32, device=dev)
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+        t_host = self._pinned("scalar", 1)
+        t_host[:1].copy_(t_max, non_blocking=True)
+        ev_tot = torch.cuda.Event()
+        ev_tot.record()
+
+        # part 2 (after the blend and C2 are queued): ONE all-gather of [number of matches per dealt task ...,
+        # (i, j) ...] padded to that total, through pinned staging both ways.  (Padding to the a-priori bound
+        # min(N_i, N_j) per pair needs no scalar round trip but moved 14 MB at 4 ranks where the lists are 1 MB:
+        # 2.5 of 6.7 ms, profiles/r02ab_run_dist_4gpu_unordered38.json.)
         def gather_lists():
-            ntask = max(max(len(d) for d in dealt), 1)
-            tot = sum(len(m) for m in results) if tasks else 0
-            t = torch.tensor([tot], dtype=torch.int32, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            pad = ntask + 2 * max(int(t.item()), 1)
-            stage = self._pinned("send", pad)
+            stage = self._pinned("send", ntask + 2 * max(tot, 1))
             host = stage.numpy()
-            host[:pad] = 0
+            host[:ntask] = 0
             if tasks:
                 host[:len(tasks)] = [len(m) for m in results]
-                off = ntask
-                for m in results:
-                    if len(m):
-                        host[off:off + 2 * len(m)] = m.reshape(-1)
-                        off += 2 * len(m)
+                if tot:
+                    host[ntask:ntask + 2 * tot] = np.concatenate(results).reshape(-1)
+            ev_tot.synchronize()
+            pad = ntask + 2 * max(int(t_host[0]), 1)
+            if stage.numel() < pad:                              # another rank has more: same content, longer buffer
+                bigger = self._pinned("send2", pad)
+                bigger[:ntask + 2 * tot].copy_(stage[:ntask + 2 * tot])
+                stage, host = bigger, bigger.numpy()
+            host[ntask + 2 * tot:pad] = 0
             my = torch.empty(pad, dtype=torch.int32, device=dev)
             my.copy_(stage[:pad], non_blocking=True)
             allm = torch.empty(world * pad, dtype=torch.int32, device=dev)
@@ -339,13 +349,14 @@ class DistributedStitcher:
             full = [None] * len(pairs)
             for r in range(world):
                 seg = got[r * pad:(r + 1) * pad]
-                off = ntask
-                for q, t_ in enumerate(dealt[r]):
-                    c = int(seg[q])
-                    full[t_] = seg[off:off + 2 * c].reshape(-1, 2).copy()
-                    off += 2 * c
+                nt = len(dealt[r])
+                if not nt:
+                    continue
+                cuts = np.cumsum(seg[:nt].astype(np.int64))
+                lists = np.split(seg[ntask:ntask + 2 * int(cuts[-1])].reshape(-1, 2).copy(), cuts[:-1])
+                for t_, m in zip(dealt[r], lists):
+                    full[t_] = m
             return full
-        matches = self._timed("gather_matches", gather_lists)
 
         # ---- strip of the canvas, then C2
         main.wait_stream(side)                              # the image exchange has landed
@@ -382,6 +393,9 @@ class DistributedStitcher:
         self._timed("blend_strip", blend_strip)
         mosaic = torch.empty((world * rows_per, tw, 3), dtype=torch.float32, device=dev)
         self._timed("gather_strips", lambda: dist.all_gather_into_tensor(mosaic, strip))
+        # the match lists last: their host work (staging, parsing) runs while the GPU blends and gathers the strips
+        # — the composite depends on the images and the caller's geometry only
+        matches = self._timed("gather_matches", gather_lists)
         torch.cuda.current_stream().synchronize()
         side.synchronize()
         self.ms = {}
