@@ -487,7 +487,8 @@ def main():
             # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture of this
             # same workload (profiles/*_traffic.json, written by tools/ncu_summary.py); null if absent
             traffic, issue = None, None
-            tr_files = sorted((ROOT / "profiles").glob("*_traffic.json"))
+            # captures are tagged r02a .. r02z, r02aa ..: shorter tags are older
+            tr_files = sorted((ROOT / "profiles").glob("*_traffic.json"), key=lambda f: (len(f.name), f.name))
             if tr_files and not args.bands:
                 ent = json.loads(tr_files[-1].read_text()).get(top, {})
                 traffic = ent.get("dram_bytes_per_launch")

@@ -779,13 +779,10 @@ k_orientation(const OctMeta* __restrict__ octs, const float* __restrict__ arena,
 __global__ void __launch_bounds__(SCAN_THREADS)
 k_expand_scan(const int* __restrict__ cand_count, const unsigned char* __restrict__ valid,
               const int* __restrict__ npeaks, const float* __restrict__ dirs, int cap,
-              const pano_sspoint* __restrict__ pts,
               int* __restrict__ n_desc, int* __restrict__ n_refined,
-              int* __restrict__ desc_cand, float* __restrict__ desc_dir, int* __restrict__ desc_order) {
+              int* __restrict__ desc_cand, float* __restrict__ desc_dir) {
   __shared__ int s_warp[32];
   __shared__ int s_warp2[32];
-  __shared__ int s_bucket[16];                  // descriptors per scale class, then running positions
-  __shared__ int s_total;
   const int img = blockIdx.x;
   const int n = min(cand_count[img], cap);
   const int per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
@@ -831,44 +828,7 @@ k_expand_scan(const int* __restrict__ cand_count, const unsigned char* __restric
       off += np;
     }
   }
-  if (tid == SCAN_THREADS - 1) { n_desc[img] = off; n_refined[img] = s_warp2[31]; s_total = off; }
-  // Processing order of the image's descriptors for k_descriptor: LARGEST windows first.  The descriptor
-  // kernel hands keypoints out dynamically and a keypoint's cost grows with the square of its scale, so
-  // with the canonical order (octave, scale, raster) the last keypoints handed out are as likely large as
-  // small and the kernel ends on a long tail of half-idle SMs; descending scale makes the tail as short
-  // as the cheapest keypoints.  Results are written to their canonical slots: only the schedule changes.
-  if (tid < 16) s_bucket[tid] = 0;
-  __syncthreads();
-  const int total = s_total;
-  if (total > cap) {                            // overflowing list (the batch will be re-run with larger lists): identity
-    for (int d = tid; d < cap; d += SCAN_THREADS) desc_order[(size_t)img * cap + d] = d;
-    return;
-  }
-  for (int k = 0; k < per; ++k) {
-    int i = tid * per + k;
-    if (i < n && valid[base + i]) {
-      const int np = npeaks[base + i];
-      if (np) atomicAdd(&s_bucket[15 - min(pts[base + i].scale_id, 15)], np);
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    for (int b = 0; b < 16; ++b) { const int c = s_bucket[b]; s_bucket[b] = acc; acc += c; }
-  }
-  __syncthreads();
-  off = s_warp[wid] + incl - local;
-  for (int k = 0; k < per; ++k) {
-    int i = tid * per + k;
-    if (i < n && valid[base + i]) {
-      const int np = npeaks[base + i];
-      if (np) {
-        const int pos = atomicAdd(&s_bucket[15 - min(pts[base + i].scale_id, 15)], np);
-        for (int q = 0; q < np; ++q) desc_order[(size_t)img * cap + pos + q] = off + q;
-      }
-      off += np;
-    }
-  }
+  if (tid == SCAN_THREADS - 1) { n_desc[img] = off; n_refined[img] = s_warp2[31]; }
 }
 
 // ============================================================ K6 descriptor
@@ -1160,7 +1120,7 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
              const pano_sspoint* __restrict__ pts, const int* __restrict__ n_desc,
              const int* __restrict__ desc_cand, const float* __restrict__ desc_dir,
              DescParams dp, float* __restrict__ out_desc, double* __restrict__ out_coor,
-             int* __restrict__ work_counter, const int* __restrict__ desc_order) {
+             int* __restrict__ work_counter) {
   extern __shared__ __align__(16) unsigned char desc_smem_raw[];
   __shared__ uint64_t s_exptab[32];
   __shared__ int s_pref[DESC_MAX_IMG + 1];      // first flat index of each image's descriptors
@@ -1197,7 +1157,7 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
     size_t dslot = 0, pslot = 0;
     if (live) {
       while (flat >= s_pref[img + 1]) ++img;      // indices only grow: resume from the last image
-      dslot = (size_t)img * cap + desc_order[(size_t)img * cap + (flat - s_pref[img])];   // largest windows first (k_expand_scan)
+      dslot = (size_t)img * cap + (flat - s_pref[img]);
       pslot = (size_t)img * cap + desc_cand[dslot];
       const pano_sspoint p = pts[pslot];
       ort = desc_dir[dslot];
@@ -1377,7 +1337,7 @@ int host_gauss_kernel(float sigma, int window_factor, float* taps, int cap) {
 void sift_work_free(pano_ctx* ctx, SiftWork* wk) {
   if (!wk) return;
   ctx_free(ctx, wk->arena); ctx_free(ctx, wk->d_img); ctx_free(ctx, wk->d_oct); ctx_free(ctx, wk->d_maps); ctx_free(ctx, wk->d_tilespan);
-  ctx_free(ctx, wk->cand_count); ctx_free(ctx, wk->cand_keys); ctx_free(ctx, wk->sorted_keys); ctx_free(ctx, wk->desc_order);
+  ctx_free(ctx, wk->cand_count); ctx_free(ctx, wk->cand_keys); ctx_free(ctx, wk->sorted_keys);
   ctx_free(ctx, wk->refined); ctx_free(ctx, wk->kp_valid); ctx_free(ctx, wk->npeaks);
   ctx_free(ctx, wk->dirs); ctx_free(ctx, wk->n_refined);
   ctx_free(ctx, wk->desc_cand); ctx_free(ctx, wk->desc_dir);
@@ -1503,7 +1463,6 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->n_refined, n * sizeof(int)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->desc_cand, nlist * sizeof(int)));
   SIFT_TRY(ctx_alloc(ctx, (void**)&wk->desc_dir, nlist * sizeof(float)));
-  SIFT_TRY(ctx_alloc(ctx, (void**)&wk->desc_order, nlist * sizeof(int)));
 
   // featureset outputs (per-image capacity `cap`; compact on download)
   fs->ctx = ctx; fs->n_images = n; fs->cap = cap;
@@ -1595,7 +1554,7 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
                   wk->cand_count, wk->refined, wk->kp_valid, p->ori_radius, p->ori_hist_smooth_count, wk->npeaks, wk->dirs,
                   wk->cand_count + n + 1);
     SIFT_LAUNCH("k_expand_scan", k_expand_scan, n, SCAN_THREADS, 0, wk->cand_count, wk->kp_valid, wk->npeaks,
-                wk->dirs, cap, wk->refined, fs->d_count, wk->n_refined, wk->desc_cand, wk->desc_dir, wk->desc_order);
+                wk->dirs, cap, fs->d_count, wk->n_refined, wk->desc_cand, wk->desc_dir);
     DescParams dp{p->desc_hist_scale_factor, p->desc_int_factor};
     // PANO_DESC_V1=1: the first design (warp per keypoint, full-window scan), kept as an in-engine cross-check
     static const bool desc_v1 = getenv("PANO_DESC_V1") && atoi(getenv("PANO_DESC_V1")) != 0;
@@ -1610,8 +1569,7 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
       SIFT_CUDA(cudaFuncSetAttribute(k_descriptor, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
       grid = ctx->num_sms * DESC_MIN_CTAS;
       SIFT_LAUNCH("k_descriptor", k_descriptor, grid, DESC_THREADS, dsm, wk->d_oct, wk->d_img, wk->arena, n_oct, n, cap,
-                  wk->refined, fs->d_count, wk->desc_cand, wk->desc_dir, dp, fs->d_desc, fs->d_coor, wk->cand_count + n,
-                  wk->desc_order);
+                  wk->refined, fs->d_count, wk->desc_cand, wk->desc_dir, dp, fs->d_desc, fs->d_coor, wk->cand_count + n);
     }
   }
   wk->n_desc = fs->d_count;

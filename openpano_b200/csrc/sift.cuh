@@ -64,7 +64,6 @@ struct SiftWork {
   int* n_refined = nullptr;         // [n_img] (for traces)
   int* desc_cand = nullptr;         // [n_img * cap] candidate index of descriptor
   float* desc_dir = nullptr;        // [n_img * cap]
-  int* desc_order = nullptr;        // [n_img * cap] processing order of an image's descriptors (largest windows first)
 };
 
 struct pano_featureset {
