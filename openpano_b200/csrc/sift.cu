@@ -1544,7 +1544,8 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
     SIFT_LAUNCH("k_refine", k_refine, g4, 128, 0, wk->d_oct, wk->arena, n_oct, wk->cand_count, wk->sorted_keys, rp, cap,
                 wk->refined, wk->kp_valid);
     // PANO_ORI_V1=1: the first design (staged replay), kept as an in-engine cross-check
-    static const bool ori_v1 = getenv("PANO_ORI_V1") && atoi(getenv("PANO_ORI_V1")) != 0;
+    const char* ori_env = getenv("PANO_ORI_V1");            // read per call: the tests switch it
+    const bool ori_v1 = ori_env && atoi(ori_env) != 0;
     if (ori_v1)
       SIFT_LAUNCH("k_orientation", k_orientation_v1, ctx->num_sms * 8, ORI_WARPS * 32, 0, wk->d_oct, wk->arena, n_oct, n, cap,
                   wk->cand_count, wk->refined, wk->kp_valid, p->ori_radius, p->ori_hist_smooth_count, wk->npeaks, wk->dirs,
@@ -1557,7 +1558,8 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
                 wk->dirs, cap, fs->d_count, wk->n_refined, wk->desc_cand, wk->desc_dir);
     DescParams dp{p->desc_hist_scale_factor, p->desc_int_factor};
     // PANO_DESC_V1=1: the first design (warp per keypoint, full-window scan), kept as an in-engine cross-check
-    static const bool desc_v1 = getenv("PANO_DESC_V1") && atoi(getenv("PANO_DESC_V1")) != 0;
+    const char* desc_env = getenv("PANO_DESC_V1");
+    const bool desc_v1 = desc_env && atoi(desc_env) != 0;
     int grid = ctx->num_sms * DESC_CTAS_PER_SM;
     if (desc_v1) {
       const size_t dsm = sizeof(DescWarpSmem) * DESC_WARPS;
