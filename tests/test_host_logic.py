@@ -138,3 +138,22 @@ def test_stitch_lanes_surface_worker_errors():
         assert "lane failed" in str(ex)
     else:
         raise AssertionError("the worker's exception was swallowed")
+
+
+def test_descriptor_column_intervals_cover_the_window(tmp_path):
+    """csrc/desc_interval.h (the window enumeration of k_descriptor) compiled for the host with the parity flags:
+    for random keypoints — axis-aligned and near-axis orientations included — every position the reference's
+    calc_descriptor accepts (sift.cc:107-124, brute force over the whole window) lies inside its column's interval."""
+    import re
+    import subprocess
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "desc_interval_check"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-o", str(exe), str(root / "tools" / "probes" / "desc_interval_check.cc"), "-lm"],
+                   check=True)
+    out = subprocess.run([str(exe), "30000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    m = re.search(r"accepted (\d+)\s+listed (\d+).*missing (\d+)", out.stdout)
+    assert m and int(m.group(3)) == 0
+    accepted, listed = int(m.group(1)), int(m.group(2))
+    assert accepted > 10_000_000 and listed < 1.06 * accepted      # a superset, and a tight one
