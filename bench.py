@@ -537,7 +537,7 @@ def main():
         # ---- the other BASELINE.json configs (N == 1) / the sharded path (N > 1), same run, same engine
         configs, sharded = None, None
         st.release_images()
-        want = [] if args.configs == "none" else (["2mb", "3", "4", "5"] if args.configs == "all" else args.configs.split(","))
+        want = [] if args.configs == "none" else (["1", "2mb", "3", "4", "5"] if args.configs == "all" else args.configs.split(","))
         if world == 1 and want:
             from openpano_b200 import synth as _synth
             from openpano_b200._abi import default_params as _dp
@@ -551,6 +551,10 @@ def main():
                     configs[key] = fn()
                 except Exception as ex:      # one failing leg must not take the headline line down
                     configs[key] = {"error": repr(ex)}
+            if "1" in want:
+                leg("config1_cmu0_cylinder", lambda: bc.run_cylinder(
+                    eng, "cmu0_8x600x400, cylinder mode: SIFT + 7 adjacent matches + cylinder warp + linear blend",
+                    "cmu0_8x600x400", _dp(ordered_input=1), cpu_loader=loader, all_cpus=all_cpus))
             if "2mb" in want:
                 leg("config2_multiband5", lambda: bc.run_stack(
                     eng, "ordered_13x1500x1112, MULTIBAND 5", "ordered_13x1500x1112", _synth.ordered_pairs, 5,

@@ -287,6 +287,20 @@ int pano_cyl_warp(pano_ctx* ctx, const float* rgb_hwc, int w, int h, double h_fa
                   const pano_params* p, float* out_hwc, int out_w, int out_h,
                   double* kpts_xy, int n_kpts);
 
+/* The warp loop of CylinderStitcher::build_warp (cylstitcher.cc:65-67: `REP(k, n) warper.warp(*imgs[k].img,
+ * keypoints[k])`) as ONE launch over device-resident images: source and destination stay in HBM (the
+ * warped images feed pano_blend_dev), the call is asynchronous on the ctx stream; only the keypoints —
+ * a few thousand f64 pairs per image, host arithmetic — are rewritten in place before it returns. */
+typedef struct pano_cyl_job {
+  const float* d_rgb_hwc;   /* device, h×w×3 f32 */
+  int w, h;
+  float* d_out_hwc;         /* device, out_h×out_w×3 f32 (sizes from pano_cyl_warp_shape) */
+  int out_w, out_h;
+  double* kpts_xy;          /* host, n_kpts pairs, image-centred; may be NULL/0 */
+  int n_kpts;
+} pano_cyl_job;
+int pano_cyl_warp_batch_dev(pano_ctx* ctx, int n, const pano_cyl_job* jobs, double h_factor, const pano_params* p);
+
 /* ----------------------------------------------------------------- blend
  * Replaces BlenderBase::add_image + run (stitch/blender.hh:14-59) for
  * LinearBlender (blender.cc:24-96) and MultiBandBlender (multiband.cc:19-151).

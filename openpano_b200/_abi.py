@@ -95,6 +95,14 @@ class PanoRansacPair(C.Structure):
     ]
 
 
+class PanoCylJob(C.Structure):
+    _fields_ = [
+        ("d_rgb_hwc", C.c_void_p), ("w", C.c_int), ("h", C.c_int),
+        ("d_out_hwc", C.c_void_p), ("out_w", C.c_int), ("out_h", C.c_int),
+        ("kpts_xy", C.c_void_p), ("n_kpts", C.c_int),
+    ]
+
+
 class PanoBaPair(C.Structure):
     _fields_ = [
         ("from_", C.c_int), ("to", C.c_int),

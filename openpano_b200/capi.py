@@ -11,7 +11,7 @@ from pathlib import Path
 
 import numpy as np
 
-from ._abi import (PanoBaPair, PanoBlendGeom, PanoBlendImage, PanoMatches, PanoParams, PanoRansacPair, PanoSSPoint,
+from ._abi import (PanoBaPair, PanoBlendGeom, PanoCylJob, PanoBlendImage, PanoMatches, PanoParams, PanoRansacPair, PanoSSPoint,
                    default_params)
 
 LIB_PATH = Path(__file__).resolve().parent / "libpano_b200.so"
@@ -82,6 +82,7 @@ def _load():
         "pano_cyl_warp_shape": (C.c_int, [C.c_int, C.c_int, C.c_double, P, _ip, _ip, _dp, _dp]),
         "pano_cyl_warp": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_int, C.c_double, P, _fp, C.c_int,
                                     C.c_int, _dp, C.c_int]),
+        "pano_cyl_warp_batch_dev": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PanoCylJob), C.c_double, P]),
         "pano_blend_target_size": (C.c_int, [C.c_int, C.POINTER(PanoBlendImage), _ip, _ip]),
         "pano_blend": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PanoBlendImage), C.POINTER(PanoBlendGeom),
                                  C.c_int, P, _fp, C.c_int, C.c_int]),
@@ -525,6 +526,22 @@ class Engine:
         self._check(LIB.pano_cyl_warp(self._h, _f(img), img.shape[1], img.shape[0], h_factor, C.byref(params),
                                       _f(out), ow, oh, _d(k), len(k)))
         return out, k
+
+    def cyl_warp_batch_dev(self, src_ptrs, shapes, dst_ptrs, kpts=None, h_factor=1.0, params=None):
+        """Device pointers in, device pointers out (out sizes from cyl_warp_shape), asynchronous; kpts: optional
+        list of [n, 2] float64 arrays rewritten in place."""
+        params = params or default_params()
+        n = len(src_ptrs)
+        arr = (PanoCylJob * max(n, 1))()
+        for k in range(n):
+            h, w = shapes[k]
+            ow, oh, _, _ = self.cyl_warp_shape(w, h, h_factor, params)
+            arr[k].d_rgb_hwc, arr[k].w, arr[k].h = src_ptrs[k], w, h
+            arr[k].d_out_hwc, arr[k].out_w, arr[k].out_h = dst_ptrs[k], ow, oh
+            if kpts is not None and kpts[k] is not None and len(kpts[k]):
+                assert kpts[k].dtype == np.float64 and kpts[k].flags["C_CONTIGUOUS"]
+                arr[k].kpts_xy, arr[k].n_kpts = kpts[k].ctypes.data, len(kpts[k])
+        self._check(LIB.pano_cyl_warp_batch_dev(self._h, n, arr, h_factor, C.byref(params)))
 
     # -- blend
     @staticmethod

@@ -97,7 +97,88 @@ __global__ void k_cyl_warp(const float* __restrict__ src, int w, int h, float* _
   p[0] = o0; p[1] = o1; p[2] = o2;
 }
 
+// The same for a batch of device-resident images: blockIdx.z = image; per-image parameters and the
+// two per-column tables (concatenated) sit in device memory.
+struct CylJobDev {
+  const float* src; float* dst;
+  int w, h, ow, oh;
+  long long tab_off;           // first entry of this image's col_x[ow] followed by col_cos[ow]
+  double r, cy, offy, sizefactor_inv;
+};
+
+__global__ void k_cyl_warp_batch(const CylJobDev* __restrict__ jobs, const double* __restrict__ tabs) {
+  const CylJobDev jb = jobs[blockIdx.z];
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = blockIdx.y * blockDim.y + threadIdx.y;
+  if (j >= jb.ow || i >= jb.oh) return;
+  const double* col_x = tabs + jb.tab_off;
+  const double* col_cos = col_x + jb.ow;
+  double py = ((double)i - jb.offy) * jb.sizefactor_inv;
+  double x = col_x[j];
+  double y = py * jb.r / col_cos[j] + jb.cy;
+  float o0 = -1.f, o1 = -1.f, o2 = -1.f;
+  if (x >= 0 && x <= (double)(jb.w - 1) && y >= 0 && y <= (double)(jb.h - 1)) {
+    float c0, c1, c2;
+    if (interpolate_rgb(jb.src, jb.w, jb.h, (float)y, (float)x, &c0, &c1, &c2)) { o0 = c0; o1 = c1; o2 = c2; }
+  }
+  float* p = jb.dst + ((size_t)i * jb.ow + j) * 3;
+  p[0] = o0; p[1] = o1; p[2] = o2;
+}
+
 extern "C" {
+
+int pano_cyl_warp_batch_dev(pano_ctx* ctx, int n, const pano_cyl_job* jobs, double h_factor, const pano_params* p) {
+  ctx_enter(ctx);
+  if (!ctx || n < 0 || (n && !jobs) || !p) return PANO_ERR_INVALID;
+  if (n == 0) return PANO_OK;
+  std::vector<CylJobDev> dj(n);
+  std::vector<double> tabs;
+  int max_ow = 0, max_oh = 0;
+  for (int k = 0; k < n; ++k) {
+    const pano_cyl_job& jb = jobs[k];
+    if (!jb.d_rgb_hwc || !jb.d_out_hwc || jb.w <= 1 || jb.h <= 1 || jb.n_kpts < 0 || (jb.n_kpts && !jb.kpts_xy))
+      return ctx_fail(ctx, PANO_ERR_INVALID, "cyl_warp_batch: job %d has a null pointer or an empty image", k);
+    CylProj c = get_projector(jb.w, jb.h, h_factor, p);
+    if (c.r <= 0) return ctx_fail(ctx, PANO_ERR_INVALID, "cylinder radius <= 0");
+    int sw = jb.w, sh = jb.h;
+    double offx, offy;
+    project_shape(c, &sw, &sh, jb.kpts_xy, jb.n_kpts, &offx, &offy);       // keypoints: host arithmetic, in place
+    if (sw != jb.out_w || sh != jb.out_h || sw <= 0 || sh <= 0)
+      return ctx_fail(ctx, PANO_ERR_INVALID, "cyl_warp_batch: job %d output buffer is %dx%d but the warp is %dx%d", k,
+                      jb.out_w, jb.out_h, sw, sh);
+    const double sizefactor_inv = 1.0 / c.sizefactor;
+    const size_t t0 = tabs.size();
+    tabs.resize(t0 + 2 * (size_t)sw);
+    for (int j = 0; j < sw; ++j) {                                          // warp.cc:19-23 proj_r per column
+      double px = ((double)j - offx) * sizefactor_inv;
+      tabs[t0 + j] = c.r * tan(px) + c.cx;
+      tabs[t0 + sw + j] = cos(px);
+    }
+    dj[k] = CylJobDev{jb.d_rgb_hwc, jb.d_out_hwc, jb.w, jb.h, sw, sh, (long long)t0, (double)c.r, c.cy, offy, sizefactor_inv};
+    max_ow = std::max(max_ow, sw); max_oh = std::max(max_oh, sh);
+  }
+  CylJobDev* d_jobs = nullptr;
+  double* d_tabs = nullptr;
+  int rc = 0;
+  if ((rc = ctx_alloc(ctx, (void**)&d_jobs, dj.size() * sizeof(CylJobDev))) ||
+      (rc = ctx_alloc(ctx, (void**)&d_tabs, tabs.size() * sizeof(double)))) {
+    ctx_free(ctx, d_jobs); ctx_free(ctx, d_tabs);
+    return rc;
+  }
+  rc = ctx_put(ctx, d_jobs, dj.data(), dj.size() * sizeof(CylJobDev));
+  if (!rc) rc = ctx_put(ctx, d_tabs, tabs.data(), tabs.size() * sizeof(double));
+  if (!rc) {
+    dim3 b(32, 8), g(ceil_div(max_ow, 32), ceil_div(max_oh, 8), n);
+    ctx->launches++;
+    if (ctx->profiling) ctx_prof_begin(ctx, "k_cyl_warp");
+    k_cyl_warp_batch<<<g, b, 0, ctx->stream>>>(d_jobs, d_tabs);
+    if (ctx->profiling) ctx_prof_end(ctx);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = ctx_cuda(ctx, e, "k_cyl_warp_batch");
+  }
+  ctx_free(ctx, d_jobs); ctx_free(ctx, d_tabs);      // stream-ordered: released after the kernel
+  return rc;
+}
 
 int pano_cyl_warp_shape(int w, int h, double h_factor, const pano_params* p, int* ow, int* oh, double* offx,
                         double* offy) {

@@ -64,6 +64,55 @@ def check_matches(omt, got, pairs, want_feats, params=None):
     return n
 
 
+# ------------------------------------------------------------------ config 1: 8 x 600x400, cylinder mode
+def test_config1_cmu0_cylinder_hot_path(engine, orc, omt):
+    """BASELINE config 1 (CMU0, cylinder mode) at its shape: the hot-path stages CylinderStitcher::build chains
+    (cylstitcher.cc:20-87) — SIFT on the 8 views, the 7 adjacent-pair matches (:40-41), CylinderWarper::warp of every
+    image and of its keypoints (:65-67, one batched launch over device-resident images), LinearBlender over the
+    warped images (flat projection, :24-27) — each bit-identical to the oracle.  The geometry between them
+    (update_h_factor, transform estimation, perspective_correction) is host code outside the path: the blend
+    uses generator-known translations."""
+    views, org = synth.config_stack("cmu0_8x600x400")
+    imgs = quantised(views)
+    n, (h, w) = len(imgs), imgs[0].shape[:2]
+    params = default_params(ordered_input=1)
+    pairs = [(k, k + 1) for k in range(n - 1)]
+    want = orc_features(orc, imgs, params)
+    fs = engine.sift_detect_batch(imgs, params)
+    assert check_features(fs, want) > 3000
+    matches = engine.match_pairs(fs, pairs, params)
+    fs.free()
+    assert check_matches(omt, matches, pairs, want, params) > 500
+    # warp: images on the device, keypoints (image-centred) in place
+    ow, oh, _, _ = engine.cyl_warp_shape(w, h, 1.0, params)
+    assert (ow, oh) == orc.cyl_warp_shape(w, h, 1.0, params)[:2]
+    src = [engine.dev_alloc(im.nbytes) for im in imgs]
+    dst = [engine.dev_alloc(oh * ow * 12) for _ in imgs]
+    for d, im in zip(src, imgs):
+        engine.dev_upload(d, im)
+    kp = [np.ascontiguousarray(c).copy() for c, _ in want]      # Descriptor::coor is image-centred already
+    kp_in = [k.copy() for k in kp]
+    engine.cyl_warp_batch_dev(src, [(h, w)] * n, dst, kp, 1.0, params)
+    warped = []
+    for k in range(n):
+        out = np.empty((oh, ow, 3), np.float32)
+        engine.dev_download(out, dst[k])
+        o_img, o_kp = orc.cyl_warp(imgs[k], kp_in[k], 1.0, params)
+        assert np.array_equal(bits(out), bits(o_img)), f"warped image {k} differs"
+        assert np.array_equal(bits(kp[k]), bits(o_kp)), f"warped keypoints of image {k} differ"
+        warped.append(out)
+    # composite of the warped images, straight from the device buffers
+    items, geom = synth.translation_blend_setup(org, ow, oh)
+    tw, th = max(it[2] for it in items), max(it[3] for it in items)
+    d_out = engine.dev_alloc(tw * th * 12)
+    engine.blend_dev(dst, [(oh, ow)] * n, items, geom, d_out, tw, th, 0, params)
+    mosaic = np.empty((th, tw, 3), np.float32)
+    engine.dev_download(mosaic, d_out)
+    assert np.array_equal(bits(mosaic), bits(omt.blend(warped, items, geom, 0, params))), "mosaic differs"
+    for d in src + dst + [d_out]:
+        engine.dev_free(d)
+
+
 # ------------------------------------------------------------------ config 2: 13 ordered 1500x1112
 def test_config2_ordered13_whole_stack(engine, orc, omt):
     from openpano_b200.stitcher import Stitcher

@@ -1,4 +1,4 @@
-"""Per-config measurement legs of bench.py (BASELINE.json configs 2-5) and the sharded
+"""Per-config measurement legs of bench.py (BASELINE.json configs 1-5) and the sharded
 multi-GPU leg.  bench.py imports this; nothing here is on the product path.
 
 Every stack leg reports, for one pass of the hot path over the named stack:
@@ -303,6 +303,114 @@ def run_stack(eng, label, cfg_name, pairs_fn, bands, params, steps=5, max_output
            "kernels": {k: v for k, v in list(kernels.items())[:8]},
            "parity_sample": parity, "cpu_baseline": cpu}
     return res
+
+
+# ----------------------------------------------------------------------------- config 1: cylinder mode
+def run_cylinder(eng, label, cfg_name, params, steps=20, cpu_loader=None, all_cpus=None):
+    """BASELINE config 1 (CMU0, cylinder mode): the hot-path stages CylinderStitcher::build chains
+    (cylstitcher.cc:20-87) at that shape, device-resident — SIFT, the adjacent-pair matches, the batched
+    cylinder warp of every image (pano_cyl_warp_batch_dev) and the LinearBlender composite of the warped
+    images with generator-known translations.  The geometry between the stages (update_h_factor, RANSAC,
+    perspective_correction) is host code outside the path and not timed."""
+    from openpano_b200 import synth
+
+    hbm_peak, tf_peak, peak_src = load_peaks()
+    tm = Timer()
+    views, org = synth.config_stack(cfg_name)
+    h, w = views[0].shape[:2]
+    pix = quantise(views)
+    del views
+    imgs = [read_img_f32(p_) for p_ in pix]
+    n = len(imgs)
+    mpx = n * h * w / 1e6
+    ow, oh, _, _ = eng.cyl_warp_shape(w, h, 1.0, params)
+    items, geom = synth.translation_blend_setup(org, ow, oh)
+    tw, th = max(it[2] for it in items), max(it[3] for it in items)
+    pairs = [(k, k + 1) for k in range(n - 1)]
+    shapes, wshapes = [(h, w)] * n, [(oh, ow)] * n
+    d_img = [eng.dev_alloc(h * w * 12) for _ in range(n)]
+    d_warp = [eng.dev_alloc(oh * ow * 12) for _ in range(n)]
+    d_out = eng.dev_alloc(tw * th * 12)
+    for d, im in zip(d_img, imgs):
+        eng.dev_upload(d, im)
+    ws, hs = [w] * n, [h] * n
+
+    def step_device():
+        fs = eng.sift_detect_batch_ptr(d_img, ws, hs, params, device=True)
+        tot = eng.match_pairs_dev(fs, pairs, params)
+        eng.cyl_warp_batch_dev(d_img, shapes, d_warp, None, 1.0, params)
+        eng.blend_dev(d_warp, wshapes, items, geom, d_out, tw, th, 0, params)
+        fs.free()
+        return tot
+
+    fs = eng.sift_detect_batch_ptr(d_img, ws, hs, params, device=True)
+    counts = [fs.count(i) for i in range(n)]
+    d0 = fs.download(0)
+    fs.free()
+    n_matches = step_device()
+    step_device()
+    dev_ms = sorted(tm.ms(step_device) for _ in range(steps))
+    ms_device = dev_ms[len(dev_ms) // 2]
+    eng.profile(True)
+    eng.profile_reset()
+    step_device()
+    prof = eng.profile_read()
+    eng.profile(False)
+    ab = algorithmic_bytes(shapes, items, params, counts, 0)
+    ab["k_cyl_warp"] = n * (h * w + oh * ow) * 12                     # SURVEY.md 8d: 12*(P_in + P_out) per image
+    ab["k_linear_blend"] = n * oh * ow * 12 + tw * th * 12
+    flops = sum(2.0 * counts[i] * counts[j] * 128 for i, j in pairs)
+    kernels = kernel_table(prof, 1, ab, flops, hbm_peak, tf_peak)
+    warped0 = np.empty((oh, ow, 3), np.float32)
+    eng.dev_download(warped0, d_warp[0])
+
+    parity = None
+    try:
+        from tests.checker import get_checker
+        orc = get_checker("orc")
+        co, do = orc.sift_detect(imgs[0], params)
+        parity = {"features_image0": bool(np.array_equal(co.view(np.uint64), d0[0].view(np.uint64)) and
+                                          np.array_equal(do.view(np.uint32), d0[1].view(np.uint32))),
+                  "warped_image0": bool(np.array_equal(orc.cyl_warp(imgs[0], None, 1.0, params)[0].view(np.uint32),
+                                                       warped0.view(np.uint32))),
+                  "against": "oracle port (oracle/liboracle.so), bit-exact comparison"}
+    except Exception as ex:
+        parity = {"unavailable": repr(ex)}
+
+    cpu = None
+    if cpu_loader is not None:
+        try:
+            if all_cpus:
+                os.sched_setaffinity(0, all_cpus)
+            chk, kind = cpu_loader()
+            o_items, o_geom = synth.translation_blend_setup(org, w, h)
+            t1 = time.perf_counter()
+            nf, nm, _, secs = silence_stdout(lambda: chk.hotpath(imgs, pairs, o_items, o_geom, 0, params, use_flann=True))
+            t2 = time.perf_counter()
+            with ThreadPoolExecutor(n) as ex:                          # the reference warps under `omp parallel for` (cylstitcher.cc:66)
+                warped = list(ex.map(lambda im: chk.cyl_warp(im, None, 1.0, params)[0], imgs))
+            t3 = time.perf_counter()
+            silence_stdout(lambda: chk.blend(warped, items, geom, 0, params))
+            t4 = time.perf_counter()
+            total = secs[0] + secs[1] + (t3 - t2) + (t4 - t3)
+            cpu = {"value": mpx / total, "unit": "Mpx/s", "cores": chk.num_threads(), "kind": kind,
+                   "sample": f"{n} of {n} views, {len(pairs)} pairs, one pass ({total:.2f} s; SIFT + FLANN match + "
+                             "CylinderWarper::warp + LinearBlender::run on the warped images)",
+                   "stage_ms": {"features": secs[0] * 1e3, "match": secs[1] * 1e3, "warp": (t3 - t2) * 1e3,
+                                "blend": (t4 - t3) * 1e3}}
+        except Exception as ex:
+            cpu = {"value": None, "unit": "Mpx/s", "cores": 0, "kind": "unavailable", "sample": repr(ex)}
+
+    for p_ in d_img + d_warp + [d_out]:
+        eng.dev_free(p_)
+    eng.sync()
+    return {"workload": label, "images": n, "image_wh": [w, h], "pairs": len(pairs), "bands": 0,
+            "warped_wh": [ow, oh], "canvas_wh": [tw, th], "input_mpx": mpx,
+            "ms_device": ms_device, "value": mpx / (ms_device * 1e-3), "unit": "Mpx/s",
+            "features": int(sum(counts)), "matches": int(n_matches),
+            "roofline": top_roofline(kernels, peak_src),
+            "kernels": {k: v for k, v in list(kernels.items())[:9] + [(k, v) for k, v in kernels.items() if k == "k_cyl_warp"]},
+            "parity_sample": parity, "cpu_baseline": cpu}
 
 
 # ----------------------------------------------------------------------------- config 4: match sweep
