@@ -155,6 +155,35 @@ class EngineBackend:
             fs.free()
 
 
+# ----------------------------------------------------------------------------- match lists on the wire
+def pack_match_lists(results, ntask: int, out: np.ndarray) -> int:
+    """One rank's share of the match lists as a flat int32 record: [number of matches per dealt task ...
+    (ntask slots, unused ones 0), (i, j) (i, j) ...].  `out` must hold ntask + 2 * total ints; returns total."""
+    tot = sum(len(m) for m in results)
+    out[:ntask] = 0
+    if len(results):
+        out[:len(results)] = [len(m) for m in results]
+        if tot:
+            out[ntask:ntask + 2 * tot] = np.concatenate(results).reshape(-1)
+    return tot
+
+
+def unpack_match_lists(got: np.ndarray, dealt, ntask: int, pad: int, n_pairs: int):
+    """The inverse over all ranks: `got` = the ranks' records, each padded to `pad` ints, concatenated in rank
+    order; dealt[r] = the pair indices rank r decided, in the order of its record.  -> list of [c, 2] arrays."""
+    full = [None] * n_pairs
+    for r, mine in enumerate(dealt):
+        nt = len(mine)
+        if not nt:
+            continue
+        seg = got[r * pad:(r + 1) * pad]
+        cuts = np.cumsum(seg[:nt].astype(np.int64))
+        lists = np.split(seg[ntask:ntask + 2 * int(cuts[-1])].reshape(-1, 2).copy(), cuts[:-1])
+        for t_, m in zip(mine, lists):
+            full[t_] = m
+    return full
+
+
 # ----------------------------------------------------------------------------- device-resident path (NCCL)
 class DistributedStitcher:
     """The sharded hot path with every payload resident in HBM (one instance per
@@ -323,11 +352,7 @@ class DistributedStitcher:
         def gather_lists():
             stage = self._pinned("send", ntask + 2 * max(tot, 1))
             host = stage.numpy()
-            host[:ntask] = 0
-            if tasks:
-                host[:len(tasks)] = [len(m) for m in results]
-                if tot:
-                    host[ntask:ntask + 2 * tot] = np.concatenate(results).reshape(-1)
+            pack_match_lists(results if tasks else [], ntask, host)
             ev_tot.synchronize()
             pad = ntask + 2 * max(int(t_host[0]), 1)
             if stage.numel() < pad:                              # another rank has more: same content, longer buffer
@@ -345,18 +370,7 @@ class DistributedStitcher:
             back = self._pinned("recv", world * pad)
             back[:world * pad].copy_(allm, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            got = back.numpy()
-            full = [None] * len(pairs)
-            for r in range(world):
-                seg = got[r * pad:(r + 1) * pad]
-                nt = len(dealt[r])
-                if not nt:
-                    continue
-                cuts = np.cumsum(seg[:nt].astype(np.int64))
-                lists = np.split(seg[ntask:ntask + 2 * int(cuts[-1])].reshape(-1, 2).copy(), cuts[:-1])
-                for t_, m in zip(dealt[r], lists):
-                    full[t_] = m
-            return full
+            return unpack_match_lists(back.numpy(), dealt, ntask, pad, len(pairs))
 
         # ---- strip of the canvas, then C2
         main.wait_stream(side)                              # the image exchange has landed

@@ -157,3 +157,31 @@ def test_descriptor_column_intervals_cover_the_window(tmp_path):
     assert m and int(m.group(3)) == 0
     accepted, listed = int(m.group(1)), int(m.group(2))
     assert accepted > 10_000_000 and listed < 1.06 * accepted      # a superset, and a tight one
+
+
+def test_match_lists_wire_format_round_trip():
+    """DistributedStitcher's list gather: every rank packs [counts of its dealt tasks | pairs], padded to the
+    largest rank total; rank 0 unpacks the concatenation.  Uneven deals, empty lists and an idle rank included."""
+    from openpano_b200.parallel import deal_pairs, pack_match_lists, unpack_match_lists
+    rng = np.random.RandomState(3)
+    for world, n_img in ((2, 7), (4, 9), (8, 5), (3, 2)):
+        pairs = synth.all_pairs(n_img)
+        counts = [int(c) for c in rng.randint(50, 400, n_img)]
+        dealt = deal_pairs(pairs, counts, world)
+        assert sorted(t for d in dealt for t in d) == list(range(len(pairs)))
+        truth = {}
+        for t, (i, j) in enumerate(pairs):
+            c = 0 if t % 5 == 0 else int(rng.randint(0, min(counts[i], counts[j])))
+            truth[t] = rng.randint(0, 1000, (c, 2)).astype(np.int32)
+        ntask = max(max(len(d) for d in dealt), 1)
+        tots = [sum(len(truth[t]) for t in d) for d in dealt]
+        pad = ntask + 2 * max(max(tots), 1)
+        wire = np.full(world * pad, -7, np.int32)                      # stale contents of the staging buffers
+        for r, d in enumerate(dealt):
+            buf = wire[r * pad:(r + 1) * pad]
+            tot = pack_match_lists([truth[t] for t in d], ntask, buf)
+            assert tot == tots[r]
+            buf[ntask + 2 * tot:] = 0
+        full = unpack_match_lists(wire, dealt, ntask, pad, len(pairs))
+        for t in range(len(pairs)):
+            assert full[t].shape == truth[t].shape and np.array_equal(full[t], truth[t]), (world, t)
