@@ -144,7 +144,10 @@ typedef struct pano_featureset pano_featureset;
  *
  * Capacity: per-image keypoint lists start at 8192 entries and are NOT a limit — when
  * an image overflows them (the reference's vectors are unbounded, extrema.cc:56-57) the
- * batch is run again with doubled lists at the first count query, transparently. */
+ * batch is run again with doubled lists at the first count query, transparently.
+ * One parameter limit the reference does not have: descriptor windows of at most 127 pixels
+ * radius (sqrt(1/2) * GAUSS_SIGMA * max(1, SCALE_FACTOR) * DESC_HIST_SCALE_FACTOR * 5 <= 127;
+ * the defaults give 21) — wider settings return PANO_ERR_INVALID. */
 int pano_sift_detect_batch(pano_ctx* ctx, int n, const float* const* rgb_hwc,
                            const int* w, const int* h, const pano_params* p,
                            pano_featureset** out);

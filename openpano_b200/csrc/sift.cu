@@ -1313,6 +1313,7 @@ k_descriptor(const OctMeta* __restrict__ octs, const ImgMeta* __restrict__ imgs,
 }
 
 // ============================================================ host driver
+#define PANO_SQRT1_2_HOST 0.70710678118654752440
 
 int host_gauss_kernel(float sigma, int window_factor, float* taps, int cap) {
   // feature/gaussian.cc:17-40 (weights in f32, expf from the host libm: the very
@@ -1381,6 +1382,15 @@ int sift_run_batch(pano_ctx* ctx, int n, const float* const* d_src, const int* w
   if (n_oct < 1 || n_oct > SIFT_MAX_OCT || n_scale < 4 || n_scale - 1 > SIFT_MAX_LEVELS || n_scale - 2 > 7)
     return ctx_fail(ctx, PANO_ERR_INVALID, "sift: NUM_OCTAVE/NUM_SCALE out of supported range");
   if (cap < 256 || cap > SIFT_CAP_MAX) return ctx_fail(ctx, PANO_ERR_INVALID, "sift: list capacity %d out of range", cap);
+  {
+    // The descriptor kernels keep window columns and offsets in 8 bits: radius <= 127.  A keypoint's
+    // scale_factor is GAUSS_SIGMA * SCALE_FACTOR^((s + offset) / nscale) with an exponent below 1
+    // (extrema.cc:99), its window radius round(sqrt(1/2) * scale_factor * DESC_HIST_SCALE_FACTOR * 5) (sift.cc:100).
+    const double sf_max = (double)p->gauss_sigma * std::max(1.0, (double)p->scale_factor);
+    const double rad_max = PANO_SQRT1_2_HOST * sf_max * (double)p->desc_hist_scale_factor * 5.0;
+    if (!(rad_max <= 127.0))
+      return ctx_fail(ctx, PANO_ERR_INVALID, "sift: descriptor windows of up to %.0f pixels radius (limit 127): lower DESC_HIST_SCALE_FACTOR / GAUSS_SIGMA", rad_max);
+  }
 
   SiftWork* wk = new SiftWork;
   wk->n_img = n; wk->n_oct = n_oct; wk->n_scale = n_scale; wk->cap = cap;
