@@ -46,6 +46,18 @@ def test_sift_other_params(orc, ref):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("hist_scale,ori_radius", [(8, 4.5), (17, 9.0)])
+def test_sift_wide_windows(orc, ref, hist_scale, ori_radius):
+    """The parameter sets tests/test_gpu_sift.py::test_sift_wide_descriptor_windows runs on the GPU (descriptor
+    windows wider than one interval-table block of the kernel, wide orientation windows): the restatement
+    against the reference's own TUs, so that the GPU-vs-oracle result there is pinned to the reference too."""
+    img = synth.make_canvas(200, 280, 41)
+    p = default_params(desc_hist_scale_factor=hist_scale, ori_radius=ori_radius)
+    (ca, da), (cb, db) = orc.sift_detect(img, p), ref.sift_detect(img, p)
+    assert len(da) > 100
+    assert gu.same_bits(ca, cb) and gu.same_bits(da, db)
+
+
 def test_sift_flat_image(orc, ref):
     img = np.full((120, 160, 3), 0.25, np.float32)
     assert len(orc.sift_detect(img)[1]) == 0 and len(ref.sift_detect(img)[1]) == 0
